@@ -1,0 +1,1386 @@
+// omm_bake.cu -- device pipeline of libomm-b200.so: everything ommCpuBake does between "inputs are in HBM" and
+// "result arrays are in HBM" (SURVEY.md section 8a, rows a3-a21), as CUDA kernels for sm_100a.
+//
+// Pipeline (one stream, two host read-backs of a few counters):
+//   K1 SetupTriangles      fetch indices/UVs, pick subdivision level, 64-bit UV id (a3)
+//   K2 UvTableInsert/Lookup "first triangle wins" UV pre-dedup via a CAS hash table + atomicMin (a3)
+//   K3 BuildItems           compact unique triangles into work items, size their state blocks
+//   K4 ClassifyKernel       one thread per micro-triangle, warp-packed 2-bit states (a5-a14)          <-- hot kernel
+//   K5 ItemPostKernel       special-index detection + XXH64 of the 3-state bytes, one warp per item (a15, a16)
+//   K6 DigestInsert/Resolve "lowest item index wins" exact dedup (a16)
+//   K7 Histogram / SortKeys / radix sort / scan (a19, a20)
+//   K8 WriteDescsAndPack, WriteIndexBuffer (a21)
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (see NcclApi) so single-GPU use needs no libnccl
+
+#include <algorithm>
+#include <cmath>
+
+#include "omm_device_math.cuh"
+
+namespace ommb200 {
+
+#define CUDA_TRY(expr)                                                                                                  \
+    do {                                                                                                                \
+        cudaError_t _e = (expr);                                                                                        \
+        if (_e != cudaSuccess) {                                                                                        \
+            log.Logf(ommMessageSeverity_Fatal, "[omm-b200] CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), __FILE__, __LINE__, #expr); \
+            rc = ommResult_FAILURE;                                                                                     \
+            goto cleanup;                                                                                               \
+        }                                                                                                               \
+    } while (0)
+
+constexpr int kMaxLevel = 12;
+constexpr uint32_t kNoItem = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Work item record (one per unique UV triangle).
+// ---------------------------------------------------------------------------------------------------------------------
+struct ItemRec {
+    float2 p0, p1, p2;
+    uint32_t tri;        // triangle that created the item (first occurrence)
+    uint8_t level;
+    uint8_t format;      // ommFormat of the item
+    uint8_t degenerate;  // base UV triangle is degenerate (ref: util/geometry.h:44-47)
+    uint8_t pad;
+};
+
+struct SetupArgs {
+    const void* indices;
+    const void* texCoords;
+    const uint8_t* levels;    // optional per-triangle levels
+    const int32_t* formats;   // optional per-triangle formats
+    uint32_t triCount;
+    uint32_t texCoordStride;
+    int indexFormat;
+    int texCoordFormat;
+    int globalFormat;
+    int maxLevel;
+    float dynScale;
+    int edgeHeuristic;
+    int disableLevelLine;
+    uint32_t texW, texH;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// hashes
+// ---------------------------------------------------------------------------------------------------------------------
+// libstdc++ std::hash<float>: murmur-style _Hash_bytes(&v, 4, 0xc70f6907); +-0.0f hash to 0.
+__device__ __forceinline__ uint64_t StdHashFloat(float v) {
+    if (v == 0.0f) return 0;
+    const uint64_t mul = (((uint64_t)0xc6a4a793UL) << 32) + (uint64_t)0x5bd1e995UL;
+    uint64_t hash = (uint64_t)0xc70f6907UL ^ (4 * mul);
+    hash ^= (uint64_t)__float_as_uint(v);
+    hash *= mul;
+    hash = (hash ^ (hash >> 47)) * mul;
+    hash = hash ^ (hash >> 47);
+    return hash;
+}
+__device__ __forceinline__ void GlmHashCombine(uint64_t& seed, uint64_t hash) {  // ref: external/glm/glm/gtx/hash.inl:6-10
+    hash += 0x9e3779b9 + (seed << 6) + (seed >> 2);
+    seed ^= hash;
+}
+__device__ __forceinline__ uint64_t HashFloat2(float2 v) {
+    uint64_t seed = 0;
+    GlmHashCombine(seed, StdHashFloat(v.x));
+    GlmHashCombine(seed, StdHashFloat(v.y));
+    return seed;
+}
+__device__ __forceinline__ void OmmHashCombine(uint64_t& seed, uint64_t h) {  // ref: util/geometry.h:141-146
+    seed ^= h + 0x9e3779b9 + (seed << 6) + (seed >> 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1: per-triangle set-up (ref: bake_cpu_impl.cpp:579-633, util/geometry.h:148-239)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 FetchUV(const SetupArgs& a, uint32_t index) {
+    const uint8_t* base = (const uint8_t*)a.texCoords + (size_t)a.texCoordStride * index;
+    if (a.texCoordFormat == ommTexCoordFormat_UV32_FLOAT) {
+        // the stride may be any byte count: read component-wise through byte loads when unaligned
+        float x, y;
+        if ((((uintptr_t)base) & 3) == 0) {
+            x = __ldg((const float*)base);
+            y = __ldg((const float*)base + 1);
+        } else {
+            uint32_t xb = 0, yb = 0;
+            for (int i = 0; i < 4; ++i) {
+                xb |= (uint32_t)base[i] << (8 * i);
+                yb |= (uint32_t)base[4 + i] << (8 * i);
+            }
+            x = __uint_as_float(xb);
+            y = __uint_as_float(yb);
+        }
+        return make_float2(x, y);
+    }
+    uint32_t packed = 0;
+    for (int i = 0; i < 4; ++i) packed |= (uint32_t)base[i] << (8 * i);
+    const uint16_t lo = (uint16_t)(packed & 0xFFFFu), hi = (uint16_t)(packed >> 16);
+    if (a.texCoordFormat == ommTexCoordFormat_UV16_UNORM)  // glm::unpackUnorm2x16
+        return make_float2((float)lo * 1.5259021896696421759365224689097e-5f, (float)hi * 1.5259021896696421759365224689097e-5f);
+    // glm::unpackHalf2x16 -> detail::toFloat32: exact half -> float widening
+    return make_float2(__half2float(__ushort_as_half(lo)), __half2float(__ushort_as_half(hi)));
+}
+__device__ __forceinline__ uint32_t FetchIndex(const SetupArgs& a, size_t i) {
+    if (a.indexFormat == ommIndexFormat_UINT_8) return ((const uint8_t*)a.indices)[i];
+    if (a.indexFormat == ommIndexFormat_UINT_16) return ((const uint16_t*)a.indices)[i];
+    return ((const uint32_t*)a.indices)[i];
+}
+__device__ __forceinline__ float Area2D(float2 p0, float2 p1, float2 p2) {  // ref: bake_cpu_impl.cpp:464-468
+    const float v0x = p2.x - p0.x, v0y = p2.y - p0.y, v1x = p1.x - p0.x, v1y = p1.y - p0.y;
+    const float cz = v0x * v1y - v1x * v0y;
+    return 0.5f * sqrtf(cz * cz);  // |(0,0,cz)|; the zero components add exact zeros
+}
+__device__ __forceinline__ uint32_t AreaHeuristic(const SetupArgs& a, float2 p0, float2 p1, float2 p2) {  // ref: :470-509
+    const float sx = (float)a.texW, sy = (float)a.texH;
+    const float area = Area2D(make_float2(p0.x * sx, p0.y * sy), make_float2(p1.x * sx, p1.y * sy), make_float2(p2.x * sx, p2.y * sy));
+    const float target = a.dynScale * a.dynScale;
+    const float q = area / target;
+    // uint(float) as GCC/x86-64 does it: cvttss2si to int64, keep the low 32 bits
+    long long q64 = (q >= -9223372036854775808.f && q < 9223372036854775808.f) ? __float2ll_rz(q) : (long long)0x8000000000000000ull;
+    uint32_t v = (uint32_t)q64;
+    v--; v |= v >> 1; v |= v >> 2; v |= v >> 4; v |= v >> 8; v |= v >> 16; v++;
+    uint32_t r = (v & 0xAAAAAAAAu) != 0;
+    r |= (uint32_t)((v & 0xFFFF0000u) != 0) << 4;
+    r |= (uint32_t)((v & 0xFF00FF00u) != 0) << 3;
+    r |= (uint32_t)((v & 0xF0F0F0F0u) != 0) << 2;
+    r |= (uint32_t)((v & 0xCCCCCCCCu) != 0) << 1;
+    const uint32_t lvl = r >> 1;
+    return min(lvl, (uint32_t)a.maxLevel);
+}
+// squared longest edge in texels; the log2 part of the edge heuristic is finished on the host (see FinishEdgeHeuristic)
+__device__ __forceinline__ float EdgeHeuristicEMax(const SetupArgs& a, float2 p0, float2 p1, float2 p2) {  // ref: :511-522
+    const float sx = (float)a.texW, sy = (float)a.texH;
+    const float e0x = sx * (p1.x - p0.x), e0y = sy * (p1.y - p0.y);
+    const float e1x = sx * (p2.x - p0.x), e1y = sy * (p2.y - p0.y);
+    const float e2x = sx * (p2.x - p1.x), e2y = sy * (p2.y - p1.y);
+    const float l0 = e0x * e0x + e0y * e0y, l1 = e1x * e1x + e1y * e1y, l2 = e2x * e2x + e2y * e2y;
+    float eMax = l0;
+    if (eMax < l1) eMax = l1;
+    if (eMax < l2) eMax = l2;
+    return eMax;
+}
+
+struct HostLevelFix {  // triangles whose level needs libm's log2f (edge heuristic): finished on the host
+    uint32_t tri;
+    float eMax;
+};
+
+__global__ void SetupTriangles(SetupArgs a, float2* __restrict__ triUV, int8_t* __restrict__ triLevel, uint8_t* __restrict__ triFormat,
+                               uint8_t* __restrict__ triDegenerate, HostLevelFix* __restrict__ fixList, uint32_t* __restrict__ fixCount) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.triCount) return;
+    const uint32_t i0 = FetchIndex(a, (size_t)3 * t), i1 = FetchIndex(a, (size_t)3 * t + 1), i2 = FetchIndex(a, (size_t)3 * t + 2);
+    const float2 p0 = FetchUV(a, i0), p1 = FetchUV(a, i1), p2 = FetchUV(a, i2);
+    triUV[(size_t)3 * t] = p0;
+    triUV[(size_t)3 * t + 1] = p1;
+    triUV[(size_t)3 * t + 2] = p2;
+    const bool invalid = isnan(p0.x) || isnan(p0.y) || isnan(p1.x) || isnan(p1.y) || isnan(p2.x) || isnan(p2.y) || isinf(p0.x) || isinf(p0.y) ||
+                         isinf(p1.x) || isinf(p1.y) || isinf(p2.x) || isinf(p2.y);
+    const bool degenerate = TriIsDegenerate(p0, p1, p2);
+    int level;  // ref: bake_cpu_impl.cpp:542-560
+    if (a.levels && a.levels[t] <= 12) level = a.levels[t];
+    else if (a.dynScale > 0.f) {
+        if (degenerate || a.edgeHeuristic) {
+            level = -2;  // resolved by the host with the same libm as the reference
+            if (!invalid) {
+                const uint32_t slot = atomicAdd(fixCount, 1u);
+                fixList[slot].tri = t;
+                fixList[slot].eMax = EdgeHeuristicEMax(a, p0, p1, p2);
+            }
+        } else
+            level = (int)AreaHeuristic(a, p0, p1, p2);
+    } else
+        level = a.maxLevel;
+    // ref: bake_cpu_impl.cpp:562-575, 616 -- NaN/Inf triangles (and degenerate ones when the level-line test is off) are skipped
+    if (invalid || (a.disableLevelLine && degenerate)) level = -1;
+    triLevel[t] = (int8_t)level;
+    triFormat[t] = (uint8_t)((!a.formats || a.formats[t] == ommFormat_INVALID) ? a.globalFormat : a.formats[t]);
+    triDegenerate[t] = degenerate ? 1 : 0;
+}
+
+__global__ void ApplyLevelFixes(const HostLevelFix* __restrict__ fixList, const int8_t* __restrict__ fixedLevels, uint32_t n, int8_t* __restrict__ triLevel) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) triLevel[fixList[i].tri] = fixedLevels[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2: UV pre-dedup.  Key = the SDK's 64-bit hash_combine chain (ref: bake_cpu_impl.cpp:626-633); the table maps
+// key -> lowest triangle index having it, which is exactly "first seen wins" of the serial loop (:635-649).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;  // remapped below if a real key equals it
+
+__device__ __forceinline__ uint64_t TableSlot(uint64_t key, uint64_t mask) { return ((key * 0x9E3779B97F4A7C15ull) >> 17) & mask; }
+
+__device__ __forceinline__ void TableInsertMin(uint64_t* keys, uint32_t* vals, uint64_t mask, uint64_t key, uint32_t val) {
+    if (key == kEmptyKey) key = 0x7FFFFFFFFFFFFFFFull;  // keep the sentinel free (a 2^-64 aliasing, same class as a hash collision)
+    uint64_t slot = TableSlot(key, mask);
+    while (true) {
+        const uint64_t prev = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (prev == kEmptyKey || prev == key) {
+            atomicMin(&vals[slot], val);
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t TableFind(const uint64_t* keys, const uint32_t* vals, uint64_t mask, uint64_t key) {
+    if (key == kEmptyKey) key = 0x7FFFFFFFFFFFFFFFull;
+    uint64_t slot = TableSlot(key, mask);
+    while (true) {
+        const uint64_t k = keys[slot];
+        if (k == key) return vals[slot];
+        if (k == kEmptyKey) return kNoItem;
+        slot = (slot + 1) & mask;
+    }
+}
+
+__global__ void FillTable(uint64_t* keys, uint32_t* vals, uint64_t cap) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        keys[i] = kEmptyKey;
+        vals[i] = 0xFFFFFFFFu;
+    }
+}
+
+__global__ void UvTableInsert(const float2* __restrict__ triUV, const int8_t* __restrict__ triLevel, const uint8_t* __restrict__ triFormat, uint32_t triCount,
+                              uint64_t* __restrict__ triKey, uint64_t* keys, uint32_t* vals, uint64_t mask) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triCount) return;
+    const int level = triLevel[t];
+    if (level < 0) return;
+    uint64_t seed = 42;
+    OmmHashCombine(seed, HashFloat2(triUV[(size_t)3 * t]));
+    OmmHashCombine(seed, HashFloat2(triUV[(size_t)3 * t + 1]));
+    OmmHashCombine(seed, HashFloat2(triUV[(size_t)3 * t + 2]));
+    OmmHashCombine(seed, (uint64_t)(int64_t)level);
+    OmmHashCombine(seed, (uint64_t)(int64_t)(int32_t)triFormat[t]);
+    triKey[t] = seed;
+    TableInsertMin(keys, vals, mask, seed, t);
+}
+
+// flag[t] = 1 when triangle t opens a work item
+__global__ void UvTableResolve(const int8_t* __restrict__ triLevel, const uint64_t* __restrict__ triKey, uint32_t triCount, const uint64_t* __restrict__ keys,
+                               const uint32_t* __restrict__ vals, uint64_t mask, int disableDup, uint32_t* __restrict__ triFirst,
+                               uint32_t* __restrict__ isItem) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triCount) return;
+    if (triLevel[t] < 0) {
+        triFirst[t] = kNoItem;
+        isItem[t] = 0;
+        return;
+    }
+    // ref: bake_cpu_impl.cpp:636 -- with DisableDuplicateDetection every valid triangle becomes its own work item
+    const uint32_t first = disableDup ? t : TableFind(keys, vals, mask, triKey[t]);
+    triFirst[t] = first;
+    isItem[t] = (first == t) ? 1u : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K3: build work items.  State block of an item: 2 bits per micro-triangle, padded to one 32-bit word.
+// A "unit" is the work of one warp: 32 consecutive micro-triangles of one item.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __restrict__ triLevel, const uint8_t* __restrict__ triFormat,
+                           const uint8_t* __restrict__ triDegenerate, const uint32_t* __restrict__ isItem, const uint32_t* __restrict__ itemScan,
+                           uint32_t triCount, ItemRec* __restrict__ items, unsigned long long* __restrict__ itemUnits,
+                           unsigned long long* __restrict__ itemWords, uint32_t* __restrict__ levelHist) {
+    __shared__ uint32_t sh[16];
+    if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < triCount && isItem[t];
+    if (active) atomicAdd(&sh[triLevel[t]], 1u);
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&levelHist[threadIdx.x], sh[threadIdx.x]);
+    if (!active) return;
+    const uint32_t w = itemScan[t];
+    ItemRec it;
+    it.p0 = triUV[(size_t)3 * t];
+    it.p1 = triUV[(size_t)3 * t + 1];
+    it.p2 = triUV[(size_t)3 * t + 2];
+    it.tri = t;
+    it.level = (uint8_t)triLevel[t];
+    it.format = triFormat[t];
+    it.degenerate = triDegenerate[t];
+    it.pad = 0;
+    items[w] = it;
+    const unsigned long long n = 1ull << (2 * it.level);
+    itemUnits[w] = n >= 32 ? n / 32 : 1;
+    itemWords[w] = n >= 16 ? n / 16 : 1;
+}
+
+__global__ void MapTrianglesToItems(const uint32_t* __restrict__ triFirst, const uint32_t* __restrict__ itemScan, uint32_t triCount, uint32_t* __restrict__ triItem) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triCount) return;
+    const uint32_t first = triFirst[t];
+    triItem[t] = first == kNoItem ? kNoItem : itemScan[first];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4: classification -- the hot kernel.  One thread per micro-triangle; a warp owns 32 consecutive bird-curve indices
+// of one work item (spatially adjacent => the same few texels), packs the 32 two-bit states with two warp OR-reductions
+// and stores them as one 8-byte word pair.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t FindItem(const unsigned long long* __restrict__ unitStart, uint32_t numItems, unsigned long long unit) {
+    // largest i with unitStart[i] <= unit   (unitStart is the exclusive prefix sum of units per item)
+    uint32_t lo = 0, hi = numItems;
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(&unitStart[mid]) <= unit) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) ClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items, const unsigned long long* __restrict__ unitStart,
+                                                      const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
+                                                      unsigned long long unitBegin, unsigned long long unitEnd, uint32_t* __restrict__ stateWords) {
+    const unsigned long long unit = unitBegin + (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (unit >= unitEnd) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = itemBegin + FindItem(unitStart + itemBegin, itemEnd - itemBegin, unit);
+    const ItemRec it = items[w];
+    const uint32_t level = it.level;
+    const uint32_t n = 1u << (2 * level);
+    const uint32_t first = (uint32_t)(unit - __ldg(&unitStart[w])) * 32u;
+    const uint32_t idx = first + lane;
+    uint32_t state = 0;
+    if (idx < n) state = (uint32_t)ClassifyMicroTriangle(P, it.p0, it.p1, it.p2, it.degenerate != 0, idx, level);
+    const uint32_t mine = state << (2 * (lane & 15));
+    const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? mine : 0u);
+    const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, lane >= 16 ? mine : 0u);
+    if (lane == 0) {
+        uint32_t* dst = stateWords + __ldg(&wordStart[w]) + (first >> 4);
+        if (n >= 32) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+        else *dst = lo;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K5: per-item post pass, one warp per item: uniform-state / rejection test (ref: bake_cpu_impl.cpp:1432-1472) and
+// XXH64(seed 42) of the item's 3-state byte array (UT folded into UO, one byte per micro-triangle; ref: :374-377,
+// :1038-1040).  XXH64 follows the published specification (xxHash doc/xxhash_spec.md; SDK pins submodule c961fbe6).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr uint64_t XP1 = 0x9E3779B185EBCA87ull, XP2 = 0xC2B2AE3D27D4EB4Full, XP3 = 0x165667B19E3779F9ull, XP4 = 0x85EBCA77C2B2AE63ull,
+                   XP5 = 0x27D4EB2F165667C5ull;
+__device__ __forceinline__ uint64_t Rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint64_t XxhRound(uint64_t acc, uint64_t in) { return Rotl64(acc + in * XP2, 31) * XP1; }
+__device__ __forceinline__ uint64_t XxhMerge(uint64_t acc, uint64_t v) { return (acc ^ XxhRound(0, v)) * XP1 + XP4; }
+__device__ __forceinline__ uint64_t XxhAvalanche(uint64_t h) {
+    h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+    return h;
+}
+// 8 two-bit states (16 bits) -> 8 bytes of 3-state values {0,1,3}
+__device__ __forceinline__ uint64_t Expand3State(uint32_t bits16) {
+    uint64_t v = (uint64_t)(bits16 & 0xFFu) | ((uint64_t)(bits16 & 0xFF00u) << 24);
+    v = (v | (v << 12)) & 0x000F000F000F000Full;
+    v = (v | (v << 6)) & 0x0303030303030303ull;
+    return v | ((v >> 1) & 0x0101010101010101ull);
+}
+
+__global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
+                                                      const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, float rejectionThreshold,
+                                                      int disableSpecial, uint64_t* __restrict__ digest, int32_t* __restrict__ special) {
+    const uint32_t w = itemBegin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= itemEnd) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t level = items[w].level;
+    const uint32_t n = 1u << (2 * level);
+    const uint32_t* words = stateWords + wordStart[w];
+    const uint32_t word0 = __ldg(words);
+    const uint32_t s0 = word0 & 3u;
+
+    uint64_t h;
+    bool allEqual;
+    uint32_t known;
+    if (n < 32) {
+        // levels 0..2: 1, 4 or 16 micro-triangles in one word
+        const uint32_t validMask = n == 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u);
+        allEqual = ((word0 ^ (s0 * 0x55555555u)) & validMask) == 0;
+        known = __popc(~(word0 >> 1) & 0x55555555u & validMask);
+        const uint64_t lo = Expand3State(word0 & 0xFFFFu), hi = Expand3State(word0 >> 16);
+        h = 42ull + XP5 + (uint64_t)n;
+        if (n == 16) {
+            h ^= XxhRound(0, lo); h = Rotl64(h, 27) * XP1 + XP4;
+            h ^= XxhRound(0, hi); h = Rotl64(h, 27) * XP1 + XP4;
+        } else if (n == 4) {
+            h ^= (lo & 0xFFFFFFFFull) * XP1; h = Rotl64(h, 23) * XP2 + XP3;
+        } else {
+            h ^= (lo & 0xFFull) * XP5; h = Rotl64(h, 11) * XP1;
+        }
+        h = XxhAvalanche(h);
+    } else {
+        const uint32_t numWords = n >> 4;
+        const uint32_t pattern = s0 * 0x55555555u;
+        uint32_t diff = 0;
+        known = 0;
+        // accumulator lane j (= threadIdx lane & 3) consumes bytes [8j, 8j+8) of every 32-byte stripe
+        const uint32_t j = lane & 3;
+        uint64_t acc = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
+        for (uint32_t base = 0; base < numWords; base += 32) {
+            const uint32_t mine = (base + lane < numWords) ? __ldg(words + base + lane) : pattern;
+            diff |= mine ^ pattern;
+            if (base + lane < numWords) known += __popc(~(mine >> 1) & 0x55555555u);
+            const uint32_t stripes = min(16u, (numWords - base) >> 1);
+            for (uint32_t s = 0; s < stripes; ++s) {
+                const uint32_t wsrc = __shfl_sync(0xFFFFFFFFu, mine, 2 * s + (j >> 1));
+                const uint32_t bits16 = (j & 1) ? (wsrc >> 16) : (wsrc & 0xFFFFu);
+                acc = XxhRound(acc, Expand3State(bits16));
+            }
+        }
+        allEqual = __reduce_or_sync(0xFFFFFFFFu, diff) == 0;
+        known = __reduce_add_sync(0xFFFFFFFFu, known);
+        const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2),
+                       v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+        h = Rotl64(v1, 1) + Rotl64(v2, 7) + Rotl64(v3, 12) + Rotl64(v4, 18);
+        h = XxhMerge(h, v1); h = XxhMerge(h, v2); h = XxhMerge(h, v3); h = XxhMerge(h, v4);
+        h += (uint64_t)n;
+        h = XxhAvalanche(h);
+    }
+    if (lane == 0) {
+        int common = (int)s0;
+        if (!allEqual && rejectionThreshold > 0.f) {
+            const float frac = (float)known / (float)n;
+            if (frac < rejectionThreshold) {
+                allEqual = true;
+                common = ommOpacityState_UnknownTransparent;
+            }
+        }
+        digest[w] = h;
+        special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K6: exact dedup on digests: the lowest item index with a digest survives (ref: bake_cpu_impl.cpp:1043-1063).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void DigestInsert(const uint64_t* __restrict__ digest, uint32_t numItems, uint64_t* keys, uint32_t* vals, uint64_t mask) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < numItems) TableInsertMin(keys, vals, mask, digest[w], w);
+}
+__global__ void DigestResolve(const uint64_t* __restrict__ digest, uint32_t numItems, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                              uint64_t mask, int disableDup, uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= numItems) return;
+    const uint32_t s = disableDup ? w : TableFind(keys, vals, mask, digest[w]);
+    survivor[w] = s;
+    if (s != w) special[w] = -1;  // donated its primitives; never serialized (ref: :1059-1060)
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K7: histograms + sort keys
+// ---------------------------------------------------------------------------------------------------------------------
+// hist layout: [0..25] array histogram (format-1)*13+level, [26..51] index histogram
+__global__ void ItemHistogramAndKeys(const ItemRec* __restrict__ items, const int32_t* __restrict__ special, uint32_t numItems, uint32_t* __restrict__ hist,
+                                     uint32_t* __restrict__ sortKeys, uint32_t* __restrict__ sortVals) {
+    __shared__ uint32_t sh[26];
+    if (threadIdx.x < 26) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < numItems) {
+        const ItemRec it = items[w];
+        uint32_t key = 0;  // special / merged items sort last and are never serialized
+        if (special[w] == 0) {
+            atomicAdd(&sh[(it.format - 1) * 13 + it.level], 1u);
+            // ref: bake_cpu_impl.cpp:1734-1747 -- level, then Morton code of the 13-bit quantised, MirrorOnce-folded UV centroid
+            const float cx = (it.p0.x + it.p1.x + it.p2.x) / 3.f, cy = (it.p0.y + it.p1.y + it.p2.y) / 3.f;
+            const int qx = f2i(8192.f * cx), qy = f2i(8192.f * cy);
+            const int mx = clampi(f2i(fabsf((float)qx + 0.5f)), 0, 8191), my = clampi(f2i(fabsf((float)qy + 0.5f)), 0, 8191);
+            uint32_t x = (uint32_t)mx, y = (uint32_t)my;
+            x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+            y = (y | (y << 8)) & 0x00FF00FFu; y = (y | (y << 4)) & 0x0F0F0F0Fu; y = (y | (y << 2)) & 0x33333333u; y = (y | (y << 1)) & 0x55555555u;
+            key = (((uint32_t)it.level << 26) | x | (y << 1)) + 1u;
+        }
+        // The SDK sorts (key, index) pairs descending (std::greater, :1751).  A stable descending radix sort fed in
+        // reversed index order yields the same order: equal keys keep the higher index first.
+        const uint32_t pos = numItems - 1 - w;
+        sortKeys[pos] = key;
+        sortVals[pos] = w;
+    }
+    __syncthreads();
+    if (threadIdx.x < 26 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void TriangleFinalItems(const uint32_t* __restrict__ triItem, const uint32_t* __restrict__ survivor, const ItemRec* __restrict__ items,
+                                   const int32_t* __restrict__ special, uint32_t triCount, uint32_t* __restrict__ triFinal, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[26];
+    if (threadIdx.x < 26) sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < triCount) {
+        const uint32_t w = triItem[t];
+        uint32_t f = kNoItem;
+        if (w != kNoItem) {
+            f = survivor[w];
+            if (special[f] == 0) atomicAdd(&sh[(items[f].format - 1) * 13 + items[f].level], 1u);
+        }
+        triFinal[t] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x < 26 && sh[threadIdx.x]) atomicAdd(&hist[26 + threadIdx.x], sh[threadIdx.x]);
+}
+
+// sizes of the serialized blocks in sorted order (ref: bake_cpu_impl.cpp:1819: global format's bit count, at least one byte)
+__global__ void SortedBlockSizes(const uint32_t* __restrict__ sortedItems, const ItemRec* __restrict__ items, uint32_t numDescs, int globalBitCount,
+                                 unsigned long long* __restrict__ blockBytes, uint32_t* __restrict__ descOfItem) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= numDescs) return;
+    const uint32_t w = sortedItems[k];
+    const unsigned long long n = 1ull << (2 * items[w].level);
+    const unsigned long long bytes = (n * (unsigned long long)globalBitCount) >> 3;
+    blockBytes[k] = bytes > 1 ? bytes : 1;
+    descOfItem[w] = k;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K8: serialization (ref: bake_cpu_impl.cpp:1788-1821, 1856-1902).  One warp per descriptor copies / repacks the block.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t CompressEvenBits16(uint32_t x) {  // 16 two-bit fields -> their low bits, 16 bits
+    return ExtractEvenBits(x);
+}
+__global__ void __launch_bounds__(256) WriteDescsAndPack(const uint32_t* __restrict__ sortedItems, const ItemRec* __restrict__ items,
+                                                         const unsigned long long* __restrict__ wordStart, const uint32_t* __restrict__ stateWords,
+                                                         const unsigned long long* __restrict__ blockOffset, uint32_t numDescs,
+                                                         unsigned long long arrayBytes, ommCpuOpacityMicromapDesc* __restrict__ descArray,
+                                                         uint8_t* __restrict__ arrayData) {
+    const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (k >= numDescs) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = sortedItems[k];
+    const ItemRec it = items[w];
+    const unsigned long long off = blockOffset[k];
+    if (lane == 0) {
+        ommCpuOpacityMicromapDesc d;
+        d.offset = (uint32_t)off;
+        d.subdivisionLevel = it.level;
+        d.format = it.format;
+        descArray[k] = d;
+    }
+    const uint32_t n = 1u << (2 * it.level);
+    const uint32_t* src = stateWords + wordStart[w];
+    uint8_t* dst = arrayData + off;
+    if (it.format == ommFormat_OC1_4_State) {
+        if (n >= 16 && (off & 3) == 0) {
+            const uint32_t numWords = n >> 4;
+            if (numWords >= 4 && (off & 15) == 0 && ((wordStart[w] & 3) == 0)) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src);
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+                for (uint32_t i = lane; i < (numWords >> 2); i += 32) d4[i] = __ldg(s4 + i);
+            } else {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+                for (uint32_t i = lane; i < numWords; i += 32) d32[i] = __ldg(src + i);
+            }
+        } else {
+            const uint32_t numBytes = n >= 4 ? n >> 2 : 1;
+            for (uint32_t b = lane; b < numBytes; b += 32)
+                if (off + b < arrayBytes) dst[b] = (uint8_t)(__ldg(src + (b >> 2)) >> ((b & 3) * 8));
+        }
+    } else {
+        // 2-state: one bit per micro-triangle (the state's low bit)
+        const uint32_t numBytes = n >= 8 ? n >> 3 : 1;
+        for (uint32_t b = lane; b < numBytes; b += 32) {
+            const uint32_t bits = CompressEvenBits16(__ldg(src + (b >> 1)));
+            if (off + b < arrayBytes) dst[b] = (uint8_t)(bits >> ((b & 1) * 8));
+        }
+    }
+}
+
+__global__ void WriteIndexBuffer(const uint32_t* __restrict__ triFinal, const int32_t* __restrict__ special, const uint32_t* __restrict__ descOfItem,
+                                 uint32_t triCount, int unresolved, int indexBytes, void* __restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triCount) return;
+    const uint32_t f = triFinal[t];
+    int32_t v = unresolved;
+    if (f != kNoItem) v = special[f] != 0 ? special[f] : (int32_t)descOfItem[f];
+    if (indexBytes == 4) ((int32_t*)out)[t] = v;
+    else if (indexBytes == 2) ((int16_t*)out)[t] = (int16_t)v;
+    else ((int8_t*)out)[t] = (int8_t)v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// texture upload + summed-area table (ref: texture_impl.cpp:77-224)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void SatRows(const void* __restrict__ texels, int isFp32, unsigned long long texelOffset, int w, int h, float cutoff, uint32_t* __restrict__ sat) {
+    // one warp per row: inclusive prefix sum of (alpha > cutoff) along x
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= h) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (int base = 0; base < w; base += 32) {
+        const int x = base + lane;
+        uint32_t v = 0;
+        if (x < w) {
+            const unsigned long long idx = texelOffset + (unsigned long long)row * w + x;
+            const float a = isFp32 ? ((const float*)texels)[idx] : (float)((const uint8_t*)texels)[idx] * (1.f / 255.f);
+            v = a > cutoff ? 1u : 0u;
+        }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= d) v += o;
+        }
+        v += carry;
+        if (x < w) sat[(size_t)row * w + x] = v;
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+}
+__global__ void SatCols(int w, int h, uint32_t* __restrict__ sat) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    uint32_t acc = 0;
+    for (int y = 0; y < h; ++y) {
+        acc += sat[(size_t)y * w + x];
+        sat[(size_t)y * w + x] = acc;
+    }
+}
+
+int DeviceCount() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int CurrentDeviceOr(int fallback) {
+    int d = fallback;
+    if (cudaGetDevice(&d) != cudaSuccess) {
+        cudaGetLastError();
+        return fallback;
+    }
+    return d;
+}
+
+static ommResult RequireDevice(const Logger& log, int device) {
+    if (DeviceCount() <= 0) {
+        log.Log(ommMessageSeverity_Fatal, "[omm-b200] no CUDA device is visible; this library has no CPU fallback");
+        return ommResult_FAILURE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        cudaGetLastError();
+        log.Logf(ommMessageSeverity_Fatal, "[omm-b200] cudaSetDevice(%d) failed", device);
+        return ommResult_FAILURE;
+    }
+    return ommResult_SUCCESS;
+}
+
+ommResult UploadTexture(TextureObject* tex, const Logger& log) {
+    ommResult rc = RequireDevice(log, tex->device);
+    if (rc != ommResult_SUCCESS) return rc;
+    const size_t spp = tex->format == ommCpuTextureFormat_FP32 ? 4 : 1;
+    size_t totalTexels = 0;
+    for (uint32_t i = 0; i < tex->mipCount; ++i) totalTexels += (size_t)tex->dev.mips[i].w * tex->dev.mips[i].h;
+    CUDA_TRY(cudaMalloc(&tex->devTexels, totalTexels * spp));
+    CUDA_TRY(cudaMemcpy(tex->devTexels, tex->hostTexels, totalTexels * spp, cudaMemcpyHostToDevice));
+    tex->dev.texels = tex->devTexels;
+    tex->dev.isFp32 = tex->format == ommCpuTextureFormat_FP32;
+    tex->dev.sat = nullptr;
+    if (tex->HasAlphaCutoff()) {  // ref: texture_impl.cpp:91 -- SAT <=> alphaCutoff >= 0
+        CUDA_TRY(cudaMalloc(&tex->devSat, totalTexels * sizeof(uint32_t)));
+        for (uint32_t i = 0; i < tex->mipCount; ++i) {
+            const DevMip& m = tex->dev.mips[i];
+            uint32_t* sat = tex->devSat + m.satOffset;
+            SatRows<<<(m.h + 7) / 8, 256>>>(tex->devTexels, tex->dev.isFp32, m.texelOffset, m.w, m.h, tex->alphaCutoff, sat);
+            SatCols<<<(m.w + 255) / 256, 256>>>(m.w, m.h, sat);
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        tex->dev.sat = tex->devSat;
+    }
+cleanup:
+    if (rc != ommResult_SUCCESS) DestroyTextureDevice(tex);
+    return rc;
+}
+void DestroyTextureDevice(TextureObject* tex) {
+    if (tex->devTexels || tex->devSat) cudaSetDevice(tex->device);
+    if (tex->devTexels) cudaFree(tex->devTexels);
+    if (tex->devSat) cudaFree(tex->devSat);
+    tex->devTexels = nullptr;
+    tex->devSat = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// staging of the per-bake inputs
+// ---------------------------------------------------------------------------------------------------------------------
+static uint32_t MaxIndex(ommIndexFormat fmt, const void* idx, size_t count) {
+    uint32_t m = 0;
+    if (fmt == ommIndexFormat_UINT_8) {
+        const uint8_t* p = (const uint8_t*)idx;
+        for (size_t i = 0; i < count; ++i) m = p[i] > m ? p[i] : m;
+    } else if (fmt == ommIndexFormat_UINT_16) {
+        const uint16_t* p = (const uint16_t*)idx;
+        for (size_t i = 0; i < count; ++i) m = p[i] > m ? p[i] : m;
+    } else {
+        const uint32_t* p = (const uint32_t*)idx;
+        for (size_t i = 0; i < count; ++i) m = p[i] > m ? p[i] : m;
+    }
+    return m;
+}
+static uint32_t TexCoordSize(ommTexCoordFormat f) { return f == ommTexCoordFormat_UV32_FLOAT ? 8u : 4u; }  // ref: util/texture.h:148-160
+static uint32_t IndexSize(ommIndexFormat f) { return f == ommIndexFormat_UINT_8 ? 1u : (f == ommIndexFormat_UINT_16 ? 2u : 4u); }
+
+ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, StagedInputs* out) {
+    const Logger& log = baker->log;
+    ommResult rc = RequireDevice(log, baker->device);
+    if (rc != ommResult_SUCCESS) return rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    out->baker = baker;
+    out->desc = desc;
+    out->device = baker->device;
+    out->triangleCount = desc.indexCount / 3u;
+    out->texCoordStride = desc.texCoordStrideInBytes == 0 ? TexCoordSize(desc.texCoordFormat) : desc.texCoordStrideInBytes;
+    {
+        const size_t usedIndices = (size_t)out->triangleCount * 3;
+        const size_t indexBytes = usedIndices * IndexSize(desc.indexFormat);
+        const uint32_t maxIndex = usedIndices ? MaxIndex(desc.indexFormat, desc.indexBuffer, usedIndices) : 0;
+        out->texCoordBytes = (size_t)maxIndex * out->texCoordStride + TexCoordSize(desc.texCoordFormat);
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        CUDA_TRY(cudaMalloc(&out->devIndices, indexBytes ? indexBytes : 4));
+        CUDA_TRY(cudaMalloc(&out->devTexCoords, out->texCoordBytes + 8));
+        CUDA_TRY(cudaMemcpyAsync(out->devIndices, desc.indexBuffer, indexBytes, cudaMemcpyHostToDevice, 0));
+        CUDA_TRY(cudaMemcpyAsync(out->devTexCoords, desc.texCoords, out->texCoordBytes, cudaMemcpyHostToDevice, 0));
+        out->h2dBytes = indexBytes + out->texCoordBytes;
+        if (desc.subdivisionLevels) {
+            CUDA_TRY(cudaMalloc(&out->devLevels, out->triangleCount ? out->triangleCount : 1));
+            CUDA_TRY(cudaMemcpyAsync(out->devLevels, desc.subdivisionLevels, out->triangleCount, cudaMemcpyHostToDevice, 0));
+            out->h2dBytes += out->triangleCount;
+        }
+        if (desc.formats) {
+            CUDA_TRY(cudaMalloc(&out->devFormats, (size_t)(out->triangleCount ? out->triangleCount : 1) * 4));
+            CUDA_TRY(cudaMemcpyAsync(out->devFormats, desc.formats, (size_t)out->triangleCount * 4, cudaMemcpyHostToDevice, 0));
+            out->h2dBytes += (uint64_t)out->triangleCount * 4;
+        }
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        CUDA_TRY(cudaEventElapsedTime(&out->h2dMs, e0, e1));
+    }
+cleanup:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (rc != ommResult_SUCCESS) DestroyStagedDevice(out);
+    return rc;
+}
+void DestroyStagedDevice(StagedInputs* s) {
+    cudaSetDevice(s->device);
+    if (s->devIndices) cudaFree(s->devIndices);
+    if (s->devTexCoords) cudaFree(s->devTexCoords);
+    if (s->devLevels) cudaFree(s->devLevels);
+    if (s->devFormats) cudaFree(s->devFormats);
+    s->devIndices = s->devTexCoords = nullptr;
+    s->devLevels = nullptr;
+    s->devFormats = nullptr;
+}
+
+// ref: bake_cpu_impl.cpp:524-527 -- finished on the host so that log2f is the very libm the SDK build calls
+static int8_t FinishEdgeHeuristic(float eMax, float dynScale, int maxLevel) {
+    const float n = eMax < 1e-6 ? 0 : std::log2(eMax) / 2.f - std::log2(dynScale);
+    const int lvl = (int)std::ceil(n);
+    return (int8_t)std::clamp<int>(lvl, 0, maxLevel);
+}
+
+static uint64_t NextPow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Simple bump list of device allocations made during one bake (stream-ordered, freed at the end).
+struct Scratch {
+    cudaStream_t stream;
+    std::vector<void*> ptrs;
+    template <class T>
+    cudaError_t alloc(T** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), stream);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = (T*)q;
+        return e;
+    }
+    void freeAll() {
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
+        ptrs.clear();
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time.  The only collective of the path: an all-gather (with per-rank counts, issued as one group of
+// broadcasts) of the per-item state blocks, after which dedup / sort / offsets are computed redundantly on every rank.
+// ---------------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+static NcclApi& Nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+        api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.GroupStart && api.GroupEnd;
+    });
+    return api;
+}
+
+struct ShardBound {
+    unsigned long long unit, word;
+    uint32_t item, pad;
+};
+// bounds[r] = first work item of rank r (r = 0..world): items are split where the running unit count crosses r*U/world
+__global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart, uint32_t entries, int world,
+                            ShardBound* __restrict__ bounds) {
+    const int r = threadIdx.x;
+    if (r > world) return;
+    const unsigned long long total = unitStart[entries - 1];
+    const unsigned long long target = r == world ? total : (total / (unsigned long long)world) * (unsigned long long)r;
+    uint32_t lo = 0, hi = entries - 1;  // smallest i with unitStart[i] >= target
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (unitStart[mid] >= target) hi = mid;
+        else lo = mid + 1;
+    }
+    bounds[r].item = lo;
+    bounds[r].unit = unitStart[lo];
+    bounds[r].word = wordStart[lo];
+}
+
+// workload metric of the SDK (ref: bake_cpu_impl.cpp:662-680): sum over work items of int(aabb.x*texW) * int(aabb.y*texH)
+__global__ void WorkloadKernel(const ItemRec* __restrict__ items, uint32_t numItems, float texW, float texH, unsigned long long* __restrict__ total) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (w < numItems) {
+        const ItemRec it = items[w];
+        const float sx = fminStd(fminStd(it.p0.x, it.p1.x), it.p2.x), sy = fminStd(fminStd(it.p0.y, it.p1.y), it.p2.y);
+        const float ex = fmaxStd(fmaxStd(it.p0.x, it.p1.x), it.p2.x), ey = fmaxStd(fmaxStd(it.p0.y, it.p1.y), it.p2.y);
+        const int ax = f2i((ex - sx) * texW), ay = f2i((ey - sy) * texH);
+        v = (unsigned long long)(long long)(int)((unsigned)ax * (unsigned)ay);
+    }
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
+}
+
+__global__ void CountDisabled(const int8_t* __restrict__ triLevel, uint32_t triCount, uint32_t* __restrict__ count) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, t < triCount && triLevel[t] < 0);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (uint32_t)__popc(m));
+}
+
+static const char* SpecialIndexText(int s) {  // ref: log.h:20-31
+    switch (s) {
+    case ommSpecialIndex_FullyTransparent: return "Fully Transparent";
+    case ommSpecialIndex_FullyOpaque: return "Fully Opaque";
+    case ommSpecialIndex_FullyUnknownTransparent: return "Fully Unknown Transparent";
+    case ommSpecialIndex_FullyUnknownOpaque: return "Fully Unknown Opaque";
+    default: return "Unknown State";
+    }
+}
+
+ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* tm) {
+    const Logger& log = baker->log;
+    ommResult rc = RequireDevice(log, baker->device);
+    if (rc != ommResult_SUCCESS) return rc;
+    const ommCpuBakeInputDesc& d = in.desc;
+    const TextureObject* tex = HandlePtr<TextureObject>(d.texture);
+    const uint32_t flags = (uint32_t)d.bakeFlags;
+    const uint32_t T = in.triangleCount;
+    const int disableDup = (flags & ommCpuBakeFlags_DisableDuplicateDetection) != 0;
+    const bool validation = (flags & ommCpuBakeFlags_EnableValidation) != 0;
+    const bool limitWorkload = d.maxWorkloadSize != 0xFFFFFFFFFFFFFFFFull;
+    const int world = baker->shard.world, rank = baker->shard.rank;
+    const int TPB = 256;
+    uint32_t launches = 0;
+
+    cudaStream_t stream = (cudaStream_t)userStream;
+    bool ownStream = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Scratch scratch{};
+    void* cubTemp = nullptr;
+    size_t cubTempBytes = 0;
+
+    // device arrays
+    float2* triUV = nullptr;
+    int8_t* triLevel = nullptr;
+    uint8_t *triFormat = nullptr, *triDegenerate = nullptr;
+    HostLevelFix* fixList = nullptr;
+    uint32_t* counters = nullptr;  // [0] edge-heuristic fix count, [1] disabled triangles, [8..23] work items per level
+    unsigned long long* workloadDev = nullptr;
+    uint64_t *triKey = nullptr, *tableKeys = nullptr;
+    uint32_t *tableVals = nullptr, *triFirst = nullptr, *isItem = nullptr, *itemScan = nullptr, *triItem = nullptr, *triFinal = nullptr;
+    ItemRec* items = nullptr;
+    unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr;
+    ShardBound* boundsDev = nullptr;
+    uint32_t* stateWords = nullptr;
+    uint64_t* digest = nullptr;
+    int32_t* special = nullptr;
+    uint32_t *survivor = nullptr, *hist = nullptr, *sortKeysIn = nullptr, *sortValsIn = nullptr, *sortKeysOut = nullptr, *sortValsOut = nullptr,
+             *descOfItem = nullptr;
+    unsigned long long *blockBytes = nullptr, *blockOffset = nullptr;
+    unsigned long long totalUnits = 0, totalWords = 0, microTris = 0, myMicroTris = 0;
+    uint32_t W = 0;
+    uint32_t countersHost[32];
+    uint32_t histHost[52];
+    ShardBound bounds[65];
+    uint32_t numDescs = 0;
+    unsigned long long arrayBytes = 0;
+    int indexBytes = 4;
+    const uint32_t gridT = (T + TPB - 1) / TPB;
+
+    BakeParams P{};
+    SetupArgs sa{};
+    memset(histHost, 0, sizeof(histHost));
+    memset(countersHost, 0, sizeof(countersHost));
+    memset(bounds, 0, sizeof(bounds));
+
+    if (world > 64) return ommResult_INVALID_ARGUMENT;
+    if (!stream) {
+        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+            cudaGetLastError();
+            return ommResult_FAILURE;
+        }
+        ownStream = true;
+    }
+    scratch.stream = stream;
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
+    CUDA_TRY(cudaEventRecord(ev[0], stream));
+
+    // ---- parameters ----
+    P.tex = tex->dev;
+    P.addrMode = d.runtimeSamplerDesc.addressingMode;
+    P.filterLinear = d.runtimeSamplerDesc.filter == ommTextureFilterMode_Linear;
+    P.borderAlpha = d.runtimeSamplerDesc.borderAlpha;
+    P.cutoff = d.alphaCutoff;
+    P.stateGT = d.alphaCutoffGreater;
+    P.stateLE = d.alphaCutoffLessEqual;
+    P.globalFormat = d.format;
+    P.promotion = d.unknownStatePromotion;
+    P.pow2Mip0 = tex->dev.mips[0].isPow2;
+    P.useCoarse = tex->dev.sat != nullptr && tex->mipCount == 1 && P.filterLinear;
+    P.disableFine = (flags & (1u << 9)) != 0;
+    P.disableLevelLine = (flags & (1u << 8)) != 0;
+    P.aabbTesting = (flags & (1u << 7)) != 0;
+
+    sa.indices = in.devIndices;
+    sa.texCoords = in.devTexCoords;
+    sa.levels = in.devLevels;
+    sa.formats = in.devFormats;
+    sa.triCount = T;
+    sa.texCoordStride = in.texCoordStride;
+    sa.indexFormat = d.indexFormat;
+    sa.texCoordFormat = d.texCoordFormat;
+    sa.globalFormat = d.format;
+    sa.maxLevel = d.maxSubdivisionLevel;
+    sa.dynScale = d.dynamicSubdivisionScale;
+    sa.edgeHeuristic = (flags & (1u << 11)) != 0;
+    sa.disableLevelLine = P.disableLevelLine;
+    sa.texW = (uint32_t)tex->dev.mips[0].w;
+    sa.texH = (uint32_t)tex->dev.mips[0].h;
+
+    // ---- K1: triangles ----
+    if (T > 0) {
+        CUDA_TRY(scratch.alloc(&triUV, (size_t)3 * T));
+        CUDA_TRY(scratch.alloc(&triLevel, T));
+        CUDA_TRY(scratch.alloc(&triFormat, T));
+        CUDA_TRY(scratch.alloc(&triDegenerate, T));
+        CUDA_TRY(scratch.alloc(&fixList, T));
+        CUDA_TRY(scratch.alloc(&counters, 32));
+        CUDA_TRY(scratch.alloc(&workloadDev, 1));
+        CUDA_TRY(scratch.alloc(&triKey, T));
+        CUDA_TRY(scratch.alloc(&triFirst, T));
+        CUDA_TRY(scratch.alloc(&isItem, T));
+        CUDA_TRY(scratch.alloc(&itemScan, T));
+        CUDA_TRY(scratch.alloc(&triItem, T));
+        CUDA_TRY(scratch.alloc(&triFinal, T));
+        CUDA_TRY(scratch.alloc(&boundsDev, 65));
+        CUDA_TRY(cudaMemsetAsync(counters, 0, 32 * sizeof(uint32_t), stream));
+        CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
+        SetupTriangles<<<gridT, TPB, 0, stream>>>(sa, triUV, triLevel, triFormat, triDegenerate, fixList, counters);
+        launches++;
+        if (sa.dynScale > 0.f) {
+            uint32_t fixCount = 0;
+            CUDA_TRY(cudaMemcpyAsync(&fixCount, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (fixCount) {
+                std::vector<HostLevelFix> fixes(fixCount);
+                std::vector<int8_t> lv(fixCount);
+                CUDA_TRY(cudaMemcpyAsync(fixes.data(), fixList, sizeof(HostLevelFix) * fixCount, cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                for (uint32_t i = 0; i < fixCount; ++i) lv[i] = FinishEdgeHeuristic(fixes[i].eMax, sa.dynScale, sa.maxLevel);
+                int8_t* lvDev = nullptr;
+                CUDA_TRY(scratch.alloc(&lvDev, fixCount));
+                CUDA_TRY(cudaMemcpyAsync(lvDev, lv.data(), fixCount, cudaMemcpyHostToDevice, stream));
+                ApplyLevelFixes<<<(fixCount + TPB - 1) / TPB, TPB, 0, stream>>>(fixList, lvDev, fixCount, triLevel);
+                launches++;
+                CUDA_TRY(cudaStreamSynchronize(stream));  // lv (host vector) must outlive the copy
+            }
+        }
+        if (validation) {
+            CountDisabled<<<gridT, TPB, 0, stream>>>(triLevel, T, counters + 1);
+            launches++;
+        }
+
+        // ---- K2: UV pre-dedup ----
+        const uint64_t cap = NextPow2((uint64_t)T * 2 + 16);
+        if (!disableDup) {
+            CUDA_TRY(scratch.alloc(&tableKeys, cap));
+            CUDA_TRY(scratch.alloc(&tableVals, cap));
+            FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
+            UvTableInsert<<<gridT, TPB, 0, stream>>>(triUV, triLevel, triFormat, T, triKey, tableKeys, tableVals, cap - 1);
+            launches += 2;
+        }
+        UvTableResolve<<<gridT, TPB, 0, stream>>>(triLevel, triKey, T, tableKeys, tableVals, cap - 1, disableDup, triFirst, isItem);
+        launches++;
+
+        // ---- K3: items ----
+        {
+            size_t need = 0, tmp = 0;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, isItem, itemScan, (int)T, stream));
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)T + 1, stream));
+            need = std::max(need, tmp);
+            CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                                (int)T, 0, 32, stream));
+            need = std::max(need, tmp);
+            cubTempBytes = need;
+            CUDA_TRY(scratch.alloc((uint8_t**)&cubTemp, cubTempBytes));
+            tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, isItem, itemScan, (int)T, stream));
+            launches += 2;
+        }
+        CUDA_TRY(scratch.alloc(&items, T));
+        CUDA_TRY(scratch.alloc(&itemUnits, (size_t)T + 1));
+        CUDA_TRY(scratch.alloc(&itemWords, (size_t)T + 1));
+        CUDA_TRY(scratch.alloc(&unitStart, (size_t)T + 1));
+        CUDA_TRY(scratch.alloc(&wordStart, (size_t)T + 1));
+        CUDA_TRY(cudaMemsetAsync(itemUnits, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
+        CUDA_TRY(cudaMemsetAsync(itemWords, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
+        BuildItems<<<gridT, TPB, 0, stream>>>(triUV, triLevel, triFormat, triDegenerate, isItem, itemScan, T, items, itemUnits, itemWords, counters + 8);
+        MapTrianglesToItems<<<gridT, TPB, 0, stream>>>(triFirst, itemScan, T, triItem);
+        launches += 2;
+        {
+            // exclusive scans over T+1 entries: entry [W] (and everything after it) holds the grand total
+            size_t tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemUnits, unitStart, (int)T + 1, stream));
+            tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemWords, wordStart, (int)T + 1, stream));
+            launches += 4;
+        }
+        ShardBounds<<<1, 96, 0, stream>>>(unitStart, wordStart, T + 1, world, boundsDev);
+        launches++;
+        CUDA_TRY(cudaMemcpyAsync(countersHost, counters, sizeof(countersHost), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (world + 1), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&totalUnits, unitStart + T, 8, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&totalWords, wordStart + T, 8, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int l = 0; l <= kMaxLevel; ++l) {
+            W += countersHost[8 + l];
+            microTris += (unsigned long long)countersHost[8 + l] << (2 * l);
+        }
+        // ref: bake_cpu_impl.cpp:652-657
+        if (validation && countersHost[1] != 0)
+            log.Logf(ommMessageSeverity_Info, "[Info] - The workload consists of %d unclassifiable triangles, these will be classified as unresolvedTriState = %s.",
+                     countersHost[1], SpecialIndexText((int)d.unresolvedTriState));
+        // ref: bake_cpu_impl.cpp:682-713
+        if ((validation || limitWorkload) && W > 0) {
+            unsigned long long workload = 0;
+            WorkloadKernel<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, W, (float)tex->dev.mips[0].w, (float)tex->dev.mips[0].h, workloadDev);
+            launches++;
+            CUDA_TRY(cudaMemcpyAsync(&workload, workloadDev, 8, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (limitWorkload && workload > d.maxWorkloadSize) {
+                rc = ommResult_WORKLOAD_TOO_BIG;
+                goto cleanup;
+            }
+            if (validation && workload > (1ull << 27))
+                log.Logf(ommMessageSeverity_PerfWarning,
+                         "[Perf Warning] - The workload consists of %lld work items (number of texels to classify), which corresponds to roughly %lld 1024x1024 "
+                         "textures. This is unusually large and may result in long bake times.",
+                         (long long)workload, (long long)(workload >> 20));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ev[1], stream));
+
+    // ---- K4: classification of this rank's shard of work items ----
+    if (W > 0) {
+        const uint32_t itemBegin = bounds[rank].item, itemEnd = bounds[rank + 1].item;
+        const unsigned long long unitBegin = bounds[rank].unit, unitEnd = bounds[rank + 1].unit;
+        CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
+        if (itemEnd > itemBegin) {
+            const unsigned long long blocks = (unitEnd - unitBegin + 7) / 8;
+            const unsigned long long kMaxGrid = 0x7FFFFFFFull;
+            for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
+                const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
+                ClassifyKernel<<<(uint32_t)nb, 256, 0, stream>>>(P, items, unitStart, wordStart, itemBegin, itemEnd, unitBegin + b0 * 8, unitEnd, stateWords);
+                launches++;
+            }
+        }
+        // exact share of micro-triangles classified here (small levels occupy a whole unit, so count through the words)
+        myMicroTris = world == 1 ? microTris : (bounds[rank + 1].word - bounds[rank].word) * 16ull;
+        if (world > 1) {
+            NcclApi& nccl = Nccl();
+            if (!nccl.ok || !baker->shard.ncclComm) {
+                log.Log(ommMessageSeverity_Fatal, "[omm-b200] sharded bake requested but NCCL is not initialised");
+                rc = ommResult_FAILURE;
+                goto cleanup;
+            }
+            bool ncclOk = nccl.GroupStart() == ncclSuccess;
+            for (int r = 0; r < world && ncclOk; ++r) {
+                const size_t count = (size_t)(bounds[r + 1].word - bounds[r].word);
+                if (count == 0) continue;
+                uint32_t* seg = stateWords + bounds[r].word;
+                ncclOk = nccl.Broadcast(seg, seg, count, ncclUint32, r, (ncclComm_t)baker->shard.ncclComm, stream) == ncclSuccess;
+            }
+            ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
+            if (!ncclOk) {
+                log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL all-gather of the state blocks failed");
+                rc = ommResult_FAILURE;
+                goto cleanup;
+            }
+        }
+    }
+    CUDA_TRY(cudaEventRecord(ev[2], stream));
+
+    // ---- K5..K7: post ----
+    if (W > 0) {
+        const uint32_t gridW = (W + TPB - 1) / TPB;
+        CUDA_TRY(scratch.alloc(&digest, W));
+        CUDA_TRY(scratch.alloc(&special, W));
+        CUDA_TRY(scratch.alloc(&survivor, W));
+        CUDA_TRY(scratch.alloc(&hist, 64));
+        CUDA_TRY(scratch.alloc(&sortKeysIn, W));
+        CUDA_TRY(scratch.alloc(&sortValsIn, W));
+        CUDA_TRY(scratch.alloc(&sortKeysOut, W));
+        CUDA_TRY(scratch.alloc(&sortValsOut, W));
+        CUDA_TRY(scratch.alloc(&descOfItem, W));
+        CUDA_TRY(scratch.alloc(&blockBytes, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&blockOffset, (size_t)W + 1));
+        CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
+        ItemPostKernel<<<(W + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
+                                                        (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, digest, special);
+        launches++;
+        const uint64_t cap = NextPow2((uint64_t)W * 2 + 16);
+        if (!disableDup) {
+            // the UV table (capacity >= 2T+16 >= 2W+16) is reused for the digests
+            FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
+            DigestInsert<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1);
+            launches += 2;
+        }
+        DigestResolve<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
+        ItemHistogramAndKeys<<<gridW, TPB, 0, stream>>>(items, special, W, hist, sortKeysIn, sortValsIn);
+        TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, items, special, T, triFinal, hist);
+        launches += 3;
+        {
+            size_t tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(cubTemp, tmp, sortKeysIn, sortKeysOut, sortValsIn, sortValsOut, (int)W, 0, 32, stream));
+            launches += 8;
+        }
+        CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+
+    // ---- sizes (ref: bake_cpu_impl.cpp:1763-1777) ----
+    {
+        const uint32_t bitCount = (uint32_t)d.format;
+        uint32_t globalFormatDescs = 0;
+        unsigned long long globalFormatBytes = 0;
+        for (int l = 0; l <= kMaxLevel; ++l) {
+            const uint32_t cnt = histHost[(d.format - 1) * 13 + l];
+            globalFormatDescs += cnt;
+            const unsigned long long bytes = ((1ull << (2 * l)) * bitCount) >> 3;
+            globalFormatBytes += (unsigned long long)cnt * (bytes > 1 ? bytes : 1);
+        }
+        for (int i = 0; i < 26; ++i) numDescs += histHost[i];
+        if (numDescs != globalFormatDescs) {
+            // The SDK sizes its arrays from the global format only and then walks every item (undefined behaviour with mixed
+            // per-triangle formats, SURVEY 7 "reference quirks").  Refuse instead of overrunning.
+            log.Log(ommMessageSeverity_Fatal, "[omm-b200] per-triangle formats that differ from desc.format are not supported");
+            rc = ommResult_FAILURE;
+            goto cleanup;
+        }
+        arrayBytes = globalFormatBytes;
+        if (arrayBytes > 0xFFFFFFFFull) {  // ref: :1774-1775
+            rc = ommResult_FAILURE;
+            goto cleanup;
+        }
+    }
+
+    // ---- K8: serialize ----
+    {
+        const bool allow8 = (flags & ommCpuBakeFlags_Allow8BitIndices) != 0, force32 = (flags & ommCpuBakeFlags_Force32BitIndices) != 0;
+        ommIndexFormat ifmt = ommIndexFormat_UINT_32;  // ref: :1873-1902
+        if (allow8 && (int32_t)T <= 127 && !force32) { ifmt = ommIndexFormat_UINT_8; indexBytes = 1; }
+        else if ((int32_t)T <= 32767 && !force32) { ifmt = ommIndexFormat_UINT_16; indexBytes = 2; }
+        res->device = baker->device;
+        res->arrayDataSize = (uint32_t)arrayBytes;
+        res->descCount = numDescs;
+        res->indexCount = T;
+        res->indexFormat = ifmt;
+        CUDA_TRY(cudaMalloc(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4));
+        if (numDescs) {
+            CUDA_TRY(cudaMalloc(&res->devArrayData, (size_t)arrayBytes + 16));
+            CUDA_TRY(cudaMalloc(&res->devDescArray, (size_t)numDescs * sizeof(ommCpuOpacityMicromapDesc)));
+            SortedBlockSizes<<<(numDescs + TPB - 1) / TPB, TPB, 0, stream>>>(sortValsOut, items, numDescs, (int)d.format, blockBytes, descOfItem);
+            size_t tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, blockOffset, (int)numDescs, stream));
+            WriteDescsAndPack<<<(numDescs + 7) / 8, 256, 0, stream>>>(sortValsOut, items, wordStart, stateWords, blockOffset, numDescs, arrayBytes,
+                                                                      (ommCpuOpacityMicromapDesc*)res->devDescArray, (uint8_t*)res->devArrayData);
+            launches += 4;
+        }
+        if (T > 0) {
+            WriteIndexBuffer<<<gridT, TPB, 0, stream>>>(triFinal, special, descOfItem, T, (int)d.unresolvedTriState, indexBytes, res->devIndexBuffer);
+            launches++;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(ev[3], stream));
+
+    // histograms (ref: bake_cpu_impl.cpp:1826-1852): non-zero entries, 2-state before 4-state, level ascending
+    {
+        uint32_t na = 0, ni = 0;
+        for (uint32_t f = 1; f <= 2; ++f)
+            for (uint32_t l = 0; l <= (uint32_t)kMaxLevel; ++l) {
+                const uint32_t ca = histHost[(f - 1) * 13 + l], ci = histHost[26 + (f - 1) * 13 + l];
+                if (ca) res->hostArrayHist[na++] = ommCpuOpacityMicromapUsageCount{ca, (uint16_t)l, (uint16_t)f};
+                if (ci) res->hostIndexHist[ni++] = ommCpuOpacityMicromapUsageCount{ci, (uint16_t)l, (uint16_t)f};
+            }
+        res->desc.descArrayHistogramCount = na;
+        res->desc.indexHistogramCount = ni;
+    }
+
+    scratch.freeAll();
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[0], ev[1]); tm->setupMs = ms;
+        cudaEventElapsedTime(&ms, ev[1], ev[2]); tm->classifyMs = ms;
+        cudaEventElapsedTime(&ms, ev[2], ev[3]); tm->postMs = ms;
+        cudaEventElapsedTime(&ms, ev[0], ev[3]); tm->totalDeviceMs = ms;
+        tm->workItems = W;
+        tm->kernelLaunches = launches;
+        tm->arrayDataBytes = numDescs ? arrayBytes : 0;
+        tm->descCount = numDescs;
+        tm->microTriangles = myMicroTris;
+        tm->reserved = 0;
+    }
+
+cleanup:
+    scratch.freeAll();
+    for (int i = 0; i < 4; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
+    if (ownStream) {
+        cudaStreamSynchronize(stream);
+        cudaStreamDestroy(stream);
+    }
+    if (rc != ommResult_SUCCESS) {
+        cudaGetLastError();
+        DestroyResultDevice(res);
+    }
+    return rc;
+}
+
+ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes) {
+    const Logger& log = res->log;
+    ommResult rc = ommResult_SUCCESS;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (res->downloaded) return ommResult_SUCCESS;
+    const size_t idxBytes = (size_t)res->indexCount * (res->indexFormat == ommIndexFormat_UINT_32 ? 4 : (res->indexFormat == ommIndexFormat_UINT_16 ? 2 : 1));
+    CUDA_TRY(cudaSetDevice(res->device));
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    if (res->descCount) {
+        res->hostArrayData = res->alloc.alloc(res->arrayDataSize, 64);
+        res->hostDescArray = res->alloc.alloc((size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), 64);
+        if (!res->hostArrayData || !res->hostDescArray) { rc = ommResult_FAILURE; goto cleanup; }
+        CUDA_TRY(cudaMemcpyAsync(res->hostArrayData, res->devArrayData, res->arrayDataSize, cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaMemcpyAsync(res->hostDescArray, res->devDescArray, (size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), cudaMemcpyDeviceToHost, 0));
+    }
+    res->hostIndexBuffer = res->alloc.alloc((size_t)res->indexCount * 4, 64);
+    if (!res->hostIndexBuffer) { rc = ommResult_FAILURE; goto cleanup; }
+    CUDA_TRY(cudaMemcpyAsync(res->hostIndexBuffer, res->devIndexBuffer, idxBytes, cudaMemcpyDeviceToHost, 0));
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    if (d2hMs) CUDA_TRY(cudaEventElapsedTime(d2hMs, e0, e1));
+    if (d2hBytes) *d2hBytes = (uint64_t)res->arrayDataSize + (uint64_t)res->descCount * 8 + idxBytes;
+    res->desc.arrayData = res->hostArrayData;
+    res->desc.arrayDataSize = res->descCount ? res->arrayDataSize : 0;
+    res->desc.descArray = (const ommCpuOpacityMicromapDesc*)res->hostDescArray;
+    res->desc.descArrayCount = res->descCount;
+    res->desc.descArrayHistogram = res->hostArrayHist;
+    res->desc.indexBuffer = res->hostIndexBuffer;
+    res->desc.indexCount = res->indexCount;
+    res->desc.indexFormat = res->indexFormat;
+    res->desc.indexHistogram = res->hostIndexHist;
+    res->downloaded = true;
+cleanup:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
+
+void DestroyResultDevice(BakeResultObject* res) {
+    if (res->devArrayData || res->devDescArray || res->devIndexBuffer) cudaSetDevice(res->device);
+    if (res->devArrayData) cudaFree(res->devArrayData);
+    if (res->devDescArray) cudaFree(res->devDescArray);
+    if (res->devIndexBuffer) cudaFree(res->devIndexBuffer);
+    res->devArrayData = res->devDescArray = res->devIndexBuffer = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// multi-GPU plumbing
+// ---------------------------------------------------------------------------------------------------------------------
+ommResult GetNcclUniqueId(void* out, size_t size) {
+    if (!out || size < sizeof(ncclUniqueId)) return ommResult_INVALID_ARGUMENT;
+    NcclApi& nccl = Nccl();
+    if (!nccl.ok) return ommResult_FAILURE;
+    ncclUniqueId id;
+    if (nccl.GetUniqueId(&id) != ncclSuccess) return ommResult_FAILURE;
+    memcpy(out, &id, sizeof(id));
+    return ommResult_SUCCESS;
+}
+ommResult InitSharding(BakerObject* baker, int rank, int world, const void* idBytes, size_t idSize) {
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return ommResult_INVALID_ARGUMENT;
+    DestroySharding(baker);
+    if (world == 1) return ommResult_SUCCESS;
+    if (!idBytes || idSize < sizeof(ncclUniqueId)) return ommResult_INVALID_ARGUMENT;
+    if (RequireDevice(baker->log, baker->device) != ommResult_SUCCESS) return ommResult_FAILURE;
+    NcclApi& nccl = Nccl();
+    if (!nccl.ok) {
+        baker->log.Log(ommMessageSeverity_Fatal, "[omm-b200] libnccl.so.2 could not be loaded");
+        return ommResult_FAILURE;
+    }
+    ncclUniqueId id;
+    memcpy(&id, idBytes, sizeof(id));
+    ncclComm_t comm = nullptr;
+    if (nccl.CommInitRank(&comm, world, id, rank) != ncclSuccess) return ommResult_FAILURE;
+    baker->shard.rank = rank;
+    baker->shard.world = world;
+    baker->shard.ncclComm = comm;
+    return ommResult_SUCCESS;
+}
+void DestroySharding(BakerObject* baker) {
+    if (baker->shard.ncclComm) {
+        Nccl().CommDestroy((ncclComm_t)baker->shard.ncclComm);
+        baker->shard.ncclComm = nullptr;
+    }
+    baker->shard.rank = 0;
+    baker->shard.world = 1;
+}
+
+}  // namespace ommb200

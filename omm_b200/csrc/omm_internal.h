@@ -1,0 +1,174 @@
+// omm_internal.h -- types shared by the C-ABI shim (omm_api.cpp) and the device pipeline (omm_bake.cu).
+#pragma once
+
+#define OMMB200_BUILDING_LIBRARY 1
+#include "../../include/omm_b200.h"
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace ommb200 {
+
+// ---- host allocator plumbing (ref: libraries/omm-lib/src/std_allocator.h:45-117) -----------------------------
+// Every host allocation whose lifetime is visible through the ABI goes through the caller's
+// ommMemoryAllocatorInterface; when the caller gives none, an aligned malloc is used.
+struct HostAllocator {
+    ommMemoryAllocatorInterface iface{};
+    void* alloc(size_t size, size_t alignment = 64) const { return iface.allocate(iface.userArg, size ? size : 1, alignment); }
+    void release(void* p) const {
+        if (p) iface.free(iface.userArg, p);
+    }
+};
+void SetDefaultAllocatorIfUnset(ommMemoryAllocatorInterface& iface);
+
+template <class T, class... Args>
+T* AllocObject(const HostAllocator& a, Args&&... args) {
+    void* mem = a.alloc(sizeof(T), alignof(T) < 16 ? 16 : alignof(T));
+    if (!mem) return nullptr;
+    return new (mem) T(static_cast<Args&&>(args)...);
+}
+template <class T>
+void FreeObject(const HostAllocator& a, T* obj) {
+    if (!obj) return;
+    obj->~T();
+    a.release(obj);
+}
+
+// ---- logger (ref: libraries/omm-lib/src/log.h:33-140) ---------------------------------------------------------
+struct Logger {
+    ommMessageInterface sink{};
+    bool HasLogger() const { return sink.messageCallback != nullptr; }
+    void Log(ommMessageSeverity sev, const char* msg) const {
+        if (sink.messageCallback) sink.messageCallback(sev, msg, sink.userArg);
+    }
+    void Logf(ommMessageSeverity sev, const char* fmt, ...) const {
+        if (!sink.messageCallback) return;
+        char buf[256];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        sink.messageCallback(sev, buf, sink.userArg);
+    }
+    ommResult InvalidArg(const char* msg) const {
+        Log(ommMessageSeverity_Fatal, msg);
+        return ommResult_INVALID_ARGUMENT;
+    }
+};
+
+// ---- handle tags (ref: libraries/omm-lib/src/omm_handle.h:17-53): low 3 bits of the pointer ------------------
+enum class HandleTag : uintptr_t { Reserved = 0, GpuBaker = 1, Pipeline = 2, CpuBaker = 3, Texture = 4 };
+template <class H, class T>
+H MakeHandle(T* p, HandleTag tag) { return (H)((uintptr_t)p | (uintptr_t)tag); }
+template <class T, class H>
+T* HandlePtr(H h) { return (T*)((uintptr_t)h & ~(uintptr_t)7); }
+template <class H>
+HandleTag HandleTagOf(H h) { return (HandleTag)((uintptr_t)h & 7); }
+
+// ---- device-side view of the alpha texture --------------------------------------------------------------------
+constexpr int kMaxMips = 17;  // 65536 = 2^16 is the largest legal dimension (ref: texture_impl.h:153)
+struct DevMip {
+    int w, h;
+    int log2w, log2h;  // ctz(size) (ref: util/bit_tricks.h:66-78)
+    int isPow2;
+    float rcpw, rcph;           // 1.f / size (ref: texture_impl.cpp:102)
+    unsigned long long texelOffset;  // element offset of this mip in the texel buffer
+    unsigned long long satOffset;    // element offset of this mip in the SAT buffer
+};
+struct DevTexture {
+    const void* texels;       // row-major, float or uint8_t
+    const uint32_t* sat;      // inclusive summed-area table of (alpha > cutoff), or nullptr
+    int isFp32;
+    int mipCount;
+    DevMip mips[kMaxMips];
+};
+
+struct TextureObject {
+    HostAllocator alloc;
+    ommCpuTextureFormat format = ommCpuTextureFormat_MAX_NUM;
+    ommCpuTextureFlags flags = ommCpuTextureFlags_None;
+    float alphaCutoff = -1.f;
+    uint32_t mipCount = 0;
+    int device = 0;
+    void* hostTexels = nullptr;  // tight row-major copy of all mips (for ommCpuGetTextureDesc)
+    size_t hostBytes = 0;
+    void* devTexels = nullptr;
+    uint32_t* devSat = nullptr;
+    DevTexture dev{};
+    bool HasAlphaCutoff() const { return alphaCutoff >= 0.f; }
+};
+
+// ---- result ------------------------------------------------------------------------------------------------------
+struct BakeResultObject {
+    HostAllocator alloc;
+    Logger log;
+    ommCpuBakeResultDesc desc{};
+    // host arrays (allocated with `alloc`)
+    void* hostArrayData = nullptr;
+    void* hostDescArray = nullptr;
+    void* hostIndexBuffer = nullptr;
+    ommCpuOpacityMicromapUsageCount hostArrayHist[26];
+    ommCpuOpacityMicromapUsageCount hostIndexHist[26];
+    // device-resident copies (freed with the result)
+    int device = 0;
+    void* devArrayData = nullptr;
+    void* devDescArray = nullptr;
+    void* devIndexBuffer = nullptr;
+    uint32_t arrayDataSize = 0, descCount = 0, indexCount = 0;
+    ommIndexFormat indexFormat = ommIndexFormat_UINT_32;
+    bool downloaded = false;
+    struct BakerObject* baker = nullptr;
+};
+
+// ---- staged (HBM-resident) inputs -------------------------------------------------------------------------------
+struct StagedInputs {
+    struct BakerObject* baker = nullptr;
+    ommCpuBakeInputDesc desc{};  // copy; texCoords/indexBuffer/... pointers are NOT used after staging
+    int device = 0;
+    void* devIndices = nullptr;
+    void* devTexCoords = nullptr;
+    uint8_t* devLevels = nullptr;
+    int32_t* devFormats = nullptr;
+    uint32_t triangleCount = 0;
+    uint32_t texCoordStride = 0;
+    size_t texCoordBytes = 0;
+    uint64_t h2dBytes = 0;
+    float h2dMs = 0.f;
+};
+
+struct ShardState {
+    int rank = 0, world = 1;
+    void* ncclComm = nullptr;  // ncclComm_t
+};
+
+struct BakerObject {
+    HostAllocator alloc;
+    Logger log;
+    int device = 0;
+    ShardState shard;
+    std::mutex mu;
+    ommB200BakeTimings last{};
+    bool haveTimings = false;
+};
+
+// implemented in omm_bake.cu
+ommResult UploadTexture(TextureObject* tex, const Logger& log);
+void DestroyTextureDevice(TextureObject* tex);
+ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, StagedInputs* out);
+void DestroyStagedDevice(StagedInputs* s);
+// Runs the whole device pipeline.  On success fills res (device buffers; host histograms) and timings.
+ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* t);
+ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes);
+void DestroyResultDevice(BakeResultObject* res);
+int DeviceCount();
+ommResult InitSharding(BakerObject* baker, int rank, int world, const void* id, size_t idSize);
+ommResult GetNcclUniqueId(void* out, size_t size);
+void DestroySharding(BakerObject* baker);
+int CurrentDeviceOr(int fallback);
+
+}  // namespace ommb200

@@ -222,3 +222,90 @@ def make_input(baker, wl: Workload, **overrides):
     inp = BakeInput(texture=tex, indices=wl.indices, texcoords=wl.texcoords, texcoord_format=wl.texcoord_format,
                     subdivision_levels=wl.subdivision_levels, formats=wl.formats, **kw)
     return inp, tex
+
+
+def random_mesh(seed: int, num_tris: int, tex_size=(256, 256), tri_texels: float = 12.0, uv_lo: float = 0.0, uv_hi: float = 1.0,
+                tex_kind: str = "noise", unorm8: bool = False, mips: int = 1, index_dtype=np.uint32, shared_vertices: bool = True,
+                degenerate_frac: float = 0.0, nan_frac: float = 0.0, reuse_frac: float = 0.0, **desc) -> Workload:
+    """General-purpose parity workload: random triangles of about `tri_texels` texels across, centred uniformly in
+    [uv_lo, uv_hi]^2 (values outside [0,1] exercise the address modes), over a noise / circle / blocky texture.
+    `degenerate_frac` of the triangles are collapsed to lines or points, `nan_frac` get a NaN/Inf coordinate and
+    `reuse_frac` repeat the UVs of an earlier triangle."""
+    w, h = tex_size
+    n = num_tris
+    cx = uv_lo + (uv_hi - uv_lo) * _unit(seed, n, 1)
+    cy = uv_lo + (uv_hi - uv_lo) * _unit(seed, n, 2)
+    rad = tri_texels / max(w, h) * (0.3 + 0.7 * _unit(seed, n, 3))
+    uv = np.empty((n, 3, 2), dtype=np.float64)
+    for k in range(3):
+        ang = 2 * np.pi * (_unit(seed, n, 4 + k) / 3.0 + k / 3.0)
+        uv[:, k, 0] = cx + rad * np.cos(ang)
+        uv[:, k, 1] = cy + rad * np.sin(ang)
+    uv = uv.astype(np.float32)
+    sel = _unit(seed, n, 8)
+    kind = _unit(seed, n, 9)
+    deg = sel < degenerate_frac
+    line = deg & (kind < 0.6)
+    point = deg & (kind >= 0.6)
+    # line: third vertex on the segment p0-p1 (exact midpoint of equal endpoints keeps area exactly 0 for axis-aligned lines)
+    uv[line, 2] = uv[line, 0]
+    uv[point, 1] = uv[point, 0]
+    uv[point, 2] = uv[point, 0]
+    bad = (sel >= degenerate_frac) & (sel < degenerate_frac + nan_frac)
+    uv[bad & (kind < 0.5), 1, 0] = np.float32(np.nan)
+    uv[bad & (kind >= 0.5), 2, 1] = np.float32(np.inf)
+    if reuse_frac > 0:
+        pick = _unit(seed, n, 10) < reuse_frac
+        src = np.arange(n)
+        earlier = (_unit(seed, n, 11) * np.maximum(src, 1)).astype(np.int64)
+        src = np.where(pick & (src > 0), earlier, src)
+        for _ in range(32):
+            src = src[src]
+        uv = uv[src]
+    if shared_vertices and np.dtype(index_dtype) != np.dtype(np.uint32):
+        maxv = {np.dtype(np.uint8): 255, np.dtype(np.uint16): 65535}[np.dtype(index_dtype)]
+        assert 3 * n <= maxv + 1
+    idx = np.arange(3 * n).astype(index_dtype)
+    size = max(w, h)
+    if tex_kind == "noise":
+        base = noise_texture(1 << int(np.ceil(np.log2(size))), cells=(8, 4), weights=(3, 1), seed=seed ^ 0x7E57, as_unorm8=True)[:h, :w]
+    elif tex_kind == "blocky":
+        yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+        base = ((((xx // 7) + (yy // 5)) % 3 == 0) * 255).astype(np.uint8)
+    elif tex_kind == "circle":
+        yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+        r = np.sqrt(((xx + 0.5) / w - 0.5) ** 2 + ((yy + 0.5) / h - 0.5) ** 2)
+        base = np.clip((r - 0.3) * 4 * 255, 0, 255).astype(np.uint8)
+    else:
+        raise ValueError(tex_kind)
+    chain = [base]
+    for _ in range(1, mips):
+        p = chain[-1]
+        hh, ww = max(1, p.shape[0] // 2), max(1, p.shape[1] // 2)
+        q = p[:hh * 2, :ww * 2].astype(np.uint16) if p.shape[0] >= 2 and p.shape[1] >= 2 else None
+        if q is None:
+            chain.append(p[:hh, :ww].copy())
+        else:
+            chain.append(((q[0::2, 0::2] + q[1::2, 0::2] + q[0::2, 1::2] + q[1::2, 1::2]) // 4).astype(np.uint8))
+    if not unorm8:
+        chain = [(m.astype(np.float32) * np.float32(1.0 / 255.0)).astype(np.float32) for m in chain]
+    d = dict(addressing_mode=capi.ADDR_WRAP, filter=capi.FILTER_LINEAR, alpha_cutoff=0.5, format=capi.FORMAT_4_STATE,
+             unknown_state_promotion=capi.PROMOTE_FORCE_OPAQUE, max_subdivision_level=4, dynamic_subdivision_scale=0.0)
+    tex_cut = desc.pop("tex_alpha_cutoff", -1.0)
+    tex_flags = desc.pop("tex_flags", capi.TEXFLAG_NONE)
+    levels = desc.pop("subdivision_levels", None)
+    formats = desc.pop("formats", None)
+    d.update(desc)
+    return Workload(name=f"random_mesh(seed={seed},n={n},{w}x{h},{tex_kind})", mips=chain, indices=idx, texcoords=uv.reshape(-1, 2),
+                    tex_alpha_cutoff=tex_cut, tex_flags=tex_flags, desc=d, subdivision_levels=levels, formats=formats)
+
+
+def pack_unorm16(uv: np.ndarray) -> np.ndarray:
+    """glm::packUnorm2x16 of float UVs (round(clamp(v,0,1) * 65535))."""
+    q = np.round(np.clip(uv.astype(np.float32), 0.0, 1.0) * np.float32(65535.0)).astype(np.uint32)
+    return (q[:, 0] | (q[:, 1] << 16)).astype(np.uint32)
+
+
+def pack_half(uv: np.ndarray) -> np.ndarray:
+    hbits = uv.astype(np.float16).view(np.uint16).astype(np.uint32)
+    return (hbits[:, 0] | (hbits[:, 1] << 16)).astype(np.uint32)

@@ -1,0 +1,33 @@
+"""GPU parity proper: libomm-b200.so (CUDA, through the C ABI) against the strongest CPU checker available (the SDK
+build when it travelled with the repo, else the port) on the same host buffers.  Bit-exact: arrayData, descArray,
+descArrayHistogram, indexBuffer (+format), indexHistogram."""
+import pytest
+
+import parity_cases as PC
+
+CASES = PC.cases()
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_product_matches_checker(name, product_lib, checker_lib):
+    mk, ov = CASES[name]
+    wl = mk()
+    want = PC.run_bake(checker_lib, wl, **ov)
+    got = PC.run_bake(product_lib, wl, **ov)
+    assert got.diff(want) == [], f"{name}: CUDA result differs from {checker_lib.path}"
+
+
+@pytest.mark.parametrize("name", ["uv16_unorm", "uv16_float", "uv32_stride20"])
+def test_product_matches_checker_uv_formats(name, product_lib, checker_lib):
+    wl = PC.uv_format_cases()[name]
+    want = PC.run_bake(checker_lib, wl)
+    got = PC.run_bake(product_lib, wl)
+    assert got.diff(want) == []
+
+
+def test_product_matches_port_too(product_lib, port_lib):
+    """The port travels everywhere; keep one direct comparison against it."""
+    from omm_b200 import workloads as W
+    wl = W.config3(num_tris=400, tex_size=256, level=5)
+    assert PC.run_bake(product_lib, wl).diff(PC.run_bake(port_lib, wl)) == []
