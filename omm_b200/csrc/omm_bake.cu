@@ -279,7 +279,7 @@ __global__ void UvTableResolve(const int8_t* __restrict__ triLevel, const uint64
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K3: build work items.  State block of an item: 2 bits per micro-triangle, padded to one 32-bit word.
+// K3: build work items.  State block of an item: 2 bits per micro-triangle, padded to four 32-bit words.
 // A "unit" is the work of one warp: 32 consecutive micro-triangles of one item.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __restrict__ triLevel, const uint8_t* __restrict__ triFormat,
@@ -308,7 +308,7 @@ __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __res
     items[w] = it;
     const unsigned long long n = 1ull << (2 * it.level);
     itemUnits[w] = n >= 32 ? n / 32 : 1;
-    itemWords[w] = n >= 16 ? n / 16 : 1;
+    itemWords[w] = n >= 64 ? n / 16 : 4;  // blocks start 16-byte aligned so the warp stores and the pack copies can be vectorised
 }
 
 __global__ void MapTrianglesToItems(const uint32_t* __restrict__ triFirst, const uint32_t* __restrict__ itemScan, uint32_t triCount, uint32_t* __restrict__ triItem) {
@@ -877,6 +877,13 @@ __global__ void WorkloadKernel(const ItemRec* __restrict__ items, uint32_t numIt
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
 }
 
+__global__ void SumMicroTriangles(const ItemRec* __restrict__ items, uint32_t itemBegin, uint32_t itemEnd, unsigned long long* __restrict__ total) {
+    const uint32_t w = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = w < itemEnd ? (1ull << (2 * items[w].level)) : 0ull;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
+}
+
 __global__ void CountDisabled(const int8_t* __restrict__ triLevel, uint32_t triCount, uint32_t* __restrict__ count) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, t < triCount && triLevel[t] < 0);
@@ -1130,9 +1137,15 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 launches++;
             }
         }
-        // exact share of micro-triangles classified here (small levels occupy a whole unit, so count through the words)
-        myMicroTris = world == 1 ? microTris : (bounds[rank + 1].word - bounds[rank].word) * 16ull;
+        myMicroTris = microTris;
         if (world > 1) {
+            // exact share of micro-triangles classified on this rank
+            CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
+            if (itemEnd > itemBegin) {
+                SumMicroTriangles<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(items, itemBegin, itemEnd, workloadDev);
+                launches++;
+            }
+            CUDA_TRY(cudaMemcpyAsync(&myMicroTris, workloadDev, 8, cudaMemcpyDeviceToHost, stream));
             NcclApi& nccl = Nccl();
             if (!nccl.ok || !baker->shard.ncclComm) {
                 log.Log(ommMessageSeverity_Fatal, "[omm-b200] sharded bake requested but NCCL is not initialised");

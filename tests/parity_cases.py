@@ -95,9 +95,12 @@ def uv_format_cases():
 
 def run_bake(lib, wl, **overrides):
     from omm_b200 import Baker
-    with Baker(lib) as b:
+    msgs = []
+    with Baker(lib, on_message=lambda sev, m: msgs.append((sev, m))) as b:
         inp, tex = W.make_input(b, wl, **overrides)
         try:
             return b.bake(inp)
+        except Exception as e:
+            raise RuntimeError(f"{e}; messages: {msgs}") from e
         finally:
             tex.destroy()
