@@ -298,6 +298,8 @@ def run_b200(a):
             dt = float(t.item())
         lib.dll.ommB200GetLastBakeTimings(baker.handle, C.byref(tm))
         h2d, d2h = int(tm.h2dBytes), int(tm.d2hBytes)
+        host_break = {"stage_ms": tm.hostStageMs, "bake_ms": tm.hostBakeMs, "download_ms": tm.hostDownloadMs, "h2d_ms": tm.h2dMs, "d2h_ms": tm.d2hMs,
+                      "device_total_ms": tm.totalDeviceMs}
         if it >= min(a.warmup, 2):
             e2e_s.append(dt)
             launches += tm.kernelLaunches
@@ -334,7 +336,7 @@ def run_b200(a):
                        "sharding": "none" if world == 1 else f"work items split over {world} ranks, 1 NCCL all-gather of state blocks"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * sum(e2e_s) / len(e2e_s), "call": "ommCpuBake + ommCpuGetBakeResultDesc, pinned host inputs -> host result"},
+                    "ms_per_step": 1e3 * sum(e2e_s) / len(e2e_s), "call": "ommCpuBake + ommCpuGetBakeResultDesc, pinned host inputs -> host result", "last_step_breakdown": host_break},
             "gpu_launches": launches,
             "roofline": roofline,
         }

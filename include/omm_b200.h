@@ -346,6 +346,11 @@ typedef struct ommB200BakeTimings {
     uint64_t arrayDataBytes;     /* arrayDataSize of the result                         */
     uint32_t descCount;
     uint32_t reserved;
+    /* host wall clock of the same call, milliseconds (std::chrono::steady_clock) */
+    float hostStageMs;    /* ommB200StageInputs part: index scan, allocations, H2D      */
+    float hostBakeMs;     /* device pipeline incl. the two small read-backs              */
+    float hostDownloadMs; /* host allocation + D2H of the result arrays                  */
+    float hostTotalMs;    /* whole ommCpuBake call                                       */
 } ommB200BakeTimings;
 
 /* Select the CUDA device used by bakers created afterwards on this thread's process (default: current device). */

@@ -162,6 +162,7 @@ class B200BakeTimings(C.Structure):
         ("microTriangles", C.c_uint64), ("workItems", C.c_uint32), ("kernelLaunches", C.c_uint32),
         ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64), ("arrayDataBytes", C.c_uint64),
         ("descCount", C.c_uint32), ("reserved", C.c_uint32),
+        ("hostStageMs", C.c_float), ("hostBakeMs", C.c_float), ("hostDownloadMs", C.c_float), ("hostTotalMs", C.c_float),
     ]
 
 

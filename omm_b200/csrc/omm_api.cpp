@@ -5,6 +5,7 @@
 // Reference behaviour restated here: libraries/omm-lib/src/bake.cpp:36-135, 410-479 (entry points),
 // bake_cpu_impl.cpp:97-119, 235-290 (validation + messages), texture_impl.cpp:43-224 (texture validation and copy),
 // std_allocator.h:45-117 (default allocator), omm_handle.h:17-53 (handle tags), debug_impl.cpp:512-641 (stats).
+#include <chrono>
 #include <cstdlib>
 #include <map>
 
@@ -119,7 +120,8 @@ static void DestroyResult(BakeResultObject* r) {
     if (!r) return;
     DestroyResultDevice(r);
     const HostAllocator alloc = r->alloc;
-    alloc.release(r->hostArrayData);
+    if (r->arrayDataFromPinnedPool) PinnedPoolRelease(r->hostArrayData);
+    else alloc.release(r->hostArrayData);
     alloc.release(r->hostDescArray);
     alloc.release(r->hostIndexBuffer);
     FreeObject(alloc, r);
@@ -141,10 +143,12 @@ OMM_API ommResult ommCreateBaker(const ommBakerCreationDesc* desc, ommBaker* out
     if (desc->type != ommBakerType_CPU) return ommResult_INVALID_ARGUMENT;
     HostAllocator alloc;
     alloc.iface = desc->memoryAllocatorInterface;
+    const bool defaultAllocator = alloc.iface.allocate == nullptr;
     SetDefaultAllocatorIfUnset(alloc.iface);
     BakerObject* b = AllocObject<BakerObject>(alloc);
     if (!b) return ommResult_FAILURE;
     b->alloc = alloc;
+    b->usesDefaultAllocator = defaultAllocator;
     b->log.sink = desc->messageInterface;
     b->device = g_requestedDevice >= 0 ? g_requestedDevice : CurrentDeviceOr(0);
     *outBaker = MakeHandle<ommBaker>(b, HandleTag::CpuBaker);
@@ -288,17 +292,25 @@ static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, Bak
     return ommResult_SUCCESS;
 }
 
-static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* stream, bool download, ommCpuBakeResult* out) {
+static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* stream, bool download, float stageMs, ommCpuBakeResult* out) {
     BakeResultObject* r = AllocObject<BakeResultObject>(b->alloc);
     if (!r) return ommResult_FAILURE;
     r->alloc = b->alloc;
+    r->usesDefaultAllocator = b->usesDefaultAllocator;
     r->log = b->log;
     r->baker = b;
     ommB200BakeTimings tm{};
     tm.h2dMs = staged.h2dMs;
     tm.h2dBytes = staged.h2dBytes;
+    tm.hostStageMs = stageMs;
+    const auto t0 = std::chrono::steady_clock::now();
     ommResult rc = BakeOnDevice(b, staged, stream, r, &tm);
+    const auto t1 = std::chrono::steady_clock::now();
     if (rc == ommResult_SUCCESS && download) rc = DownloadResult(r, &tm.d2hMs, &tm.d2hBytes);
+    const auto t2 = std::chrono::steady_clock::now();
+    tm.hostBakeMs = std::chrono::duration<float, std::milli>(t1 - t0).count();
+    tm.hostDownloadMs = std::chrono::duration<float, std::milli>(t2 - t1).count();
+    tm.hostTotalMs = stageMs + tm.hostBakeMs + tm.hostDownloadMs;
     if (rc != ommResult_SUCCESS) {
         DestroyResult(r);
         return rc;
@@ -317,9 +329,11 @@ OMM_API ommResult ommCpuBake(ommBaker baker, const ommCpuBakeInputDesc* d, ommCp
     const ommResult v = CheckBakeArgs(baker, d, &b);
     if (v != ommResult_SUCCESS) return v;
     StagedInputs staged;
+    const auto t0 = std::chrono::steady_clock::now();
     ommResult rc = StageInputs(b, *d, &staged);
     if (rc != ommResult_SUCCESS) return rc;
-    rc = RunBake(b, staged, nullptr, true, outBakeResult);
+    const float stageMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    rc = RunBake(b, staged, nullptr, true, stageMs, outBakeResult);
     DestroyStagedDevice(&staged);
     return rc;
 }
@@ -426,7 +440,7 @@ OMM_API ommResult ommB200BakeResident(ommBaker baker, ommB200StagedInputs staged
     BakerObject* b = HandlePtr<BakerObject>(baker);
     StagedInputs* s = (StagedInputs*)staged;
     if (s->baker != b) return b->log.InvalidArg("[omm-b200] staged inputs belong to a different baker");
-    return RunBake(b, *s, cudaStream, false, outBakeResult);
+    return RunBake(b, *s, cudaStream, false, 0.f, outBakeResult);
 }
 OMM_API ommResult ommB200GetDeviceResultDesc(ommCpuBakeResult bakeResult, ommB200DeviceResultDesc* out) {
     if (bakeResult == 0 || out == nullptr) return ommResult_INVALID_ARGUMENT;

@@ -334,20 +334,32 @@ __device__ __forceinline__ uint32_t FindItem(const unsigned long long* __restric
     return lo;
 }
 
-__global__ void __launch_bounds__(256) ClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items, const unsigned long long* __restrict__ unitStart,
-                                                      const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
-                                                      unsigned long long unitBegin, unsigned long long unitEnd, uint32_t* __restrict__ stateWords) {
-    const unsigned long long unit = unitBegin + (unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+constexpr int kClassifyWarps = 8;  // warps (= units) per block
+
+template <class Cfg>
+__global__ void __launch_bounds__(kClassifyWarps * 32) ClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items,
+                                                                      const unsigned long long* __restrict__ unitStart,
+                                                                      const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
+                                                                      unsigned long long unitBegin, unsigned long long unitEnd,
+                                                                      uint32_t* __restrict__ stateWords) {
+    // The block's first unit is located with one binary search; its warps walk forward from there (a block of 8 units
+    // spans at most 8 work items, and exactly one for items of level >= 4).
+    __shared__ uint32_t sFirstItem;
+    const unsigned long long blockUnit = unitBegin + (unsigned long long)blockIdx.x * kClassifyWarps;
+    if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(unitStart + itemBegin, itemEnd - itemBegin, blockUnit);
+    __syncthreads();
+    const unsigned long long unit = blockUnit + (threadIdx.x >> 5);
     if (unit >= unitEnd) return;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t w = itemBegin + FindItem(unitStart + itemBegin, itemEnd - itemBegin, unit);
+    uint32_t w = sFirstItem;
+    while (w + 1 < itemEnd && __ldg(&unitStart[w + 1]) <= unit) ++w;
     const ItemRec it = items[w];
     const uint32_t level = it.level;
     const uint32_t n = 1u << (2 * level);
     const uint32_t first = (uint32_t)(unit - __ldg(&unitStart[w])) * 32u;
     const uint32_t idx = first + lane;
     uint32_t state = 0;
-    if (idx < n) state = (uint32_t)ClassifyMicroTriangle(P, it.p0, it.p1, it.p2, it.degenerate != 0, idx, level);
+    if (idx < n) state = (uint32_t)ClassifyMicroTriangle<Cfg>(P, it.p0, it.p1, it.p2, it.degenerate != 0, idx, level);
     const uint32_t mine = state << (2 * (lane & 15));
     const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? mine : 0u);
     const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, lane >= 16 ? mine : 0u);
@@ -356,6 +368,24 @@ __global__ void __launch_bounds__(256) ClassifyKernel(const BakeParams P, const 
         if (n >= 32) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
         else *dst = lo;
     }
+}
+
+typedef void (*ClassifyFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
+                           unsigned long long, uint32_t*);
+// Picks the compile-time specialisation matching the sampler / texture; every other combination runs the generic kernel.
+static ClassifyFn SelectClassifyKernel(const BakeParams& P) {
+    const bool allPow2 = [&] {
+        for (int i = 0; i < P.tex.mipCount; ++i)
+            if (!P.tex.mips[i].isPow2) return false;
+        return true;
+    }();
+    if (P.tex.isFp32) {
+        if (P.addrMode == ommTextureAddressMode_Wrap && allPow2) return ClassifyKernel<KernelCfg<kAddrWrapPow2, true>>;
+        if (P.addrMode == ommTextureAddressMode_Clamp) return ClassifyKernel<KernelCfg<kAddrClamp, true>>;
+        return ClassifyKernel<KernelCfg<kAddrGeneric, true>>;
+    }
+    if (P.addrMode == ommTextureAddressMode_Wrap && allPow2) return ClassifyKernel<KernelCfg<kAddrWrapPow2, false>>;
+    return ClassifyKernel<KernelCfg<kAddrGeneric, false>>;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -652,6 +682,63 @@ int CurrentDeviceOr(int fallback) {
     return d;
 }
 
+// Stream-ordered allocations come from the device's default memory pool; keep freed blocks cached between bakes.
+static void ConfigurePoolOnce(int device) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> g(mu);
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    cudaGetLastError();
+    done[device] = true;
+}
+
+struct PinnedBlock {
+    void* ptr;
+    size_t bytes;
+    bool inUse;
+};
+static std::mutex g_pinnedMu;
+static std::vector<PinnedBlock> g_pinned;
+static size_t g_pinnedTotal = 0;
+void* PinnedPoolAcquire(size_t bytes) {
+    std::lock_guard<std::mutex> g(g_pinnedMu);
+    int best = -1;
+    for (int i = 0; i < (int)g_pinned.size(); ++i)
+        if (!g_pinned[i].inUse && g_pinned[i].bytes >= bytes && (best < 0 || g_pinned[i].bytes < g_pinned[best].bytes)) best = i;
+    if (best >= 0) {
+        g_pinned[best].inUse = true;
+        return g_pinned[best].ptr;
+    }
+    const size_t rounded = (bytes + (bytes >> 3) + ((size_t)2 << 20)) & ~(((size_t)2 << 20) - 1);  // 12.5 % slack, 2 MiB granules
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, rounded, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    g_pinned.push_back({p, rounded, true});
+    g_pinnedTotal += rounded;
+    return p;
+}
+void PinnedPoolRelease(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(g_pinnedMu);
+    for (size_t i = 0; i < g_pinned.size(); ++i)
+        if (g_pinned[i].ptr == p) {
+            g_pinned[i].inUse = false;
+            if (g_pinnedTotal > ((size_t)12 << 30)) {  // keep at most 12 GiB cached
+                cudaFreeHost(p);
+                g_pinnedTotal -= g_pinned[i].bytes;
+                g_pinned.erase(g_pinned.begin() + i);
+            }
+            return;
+        }
+}
+
 static ommResult RequireDevice(const Logger& log, int device) {
     if (DeviceCount() <= 0) {
         log.Log(ommMessageSeverity_Fatal, "[omm-b200] no CUDA device is visible; this library has no CPU fallback");
@@ -662,6 +749,7 @@ static ommResult RequireDevice(const Logger& log, int device) {
         log.Logf(ommMessageSeverity_Fatal, "[omm-b200] cudaSetDevice(%d) failed", device);
         return ommResult_FAILURE;
     }
+    ConfigurePoolOnce(device);
     return ommResult_SUCCESS;
 }
 
@@ -738,18 +826,18 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
         CUDA_TRY(cudaEventCreate(&e0));
         CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, 0));
-        CUDA_TRY(cudaMalloc(&out->devIndices, indexBytes ? indexBytes : 4));
-        CUDA_TRY(cudaMalloc(&out->devTexCoords, out->texCoordBytes + 8));
+        CUDA_TRY(cudaMallocAsync(&out->devIndices, indexBytes ? indexBytes : 4, 0));
+        CUDA_TRY(cudaMallocAsync(&out->devTexCoords, out->texCoordBytes + 8, 0));
         CUDA_TRY(cudaMemcpyAsync(out->devIndices, desc.indexBuffer, indexBytes, cudaMemcpyHostToDevice, 0));
         CUDA_TRY(cudaMemcpyAsync(out->devTexCoords, desc.texCoords, out->texCoordBytes, cudaMemcpyHostToDevice, 0));
         out->h2dBytes = indexBytes + out->texCoordBytes;
         if (desc.subdivisionLevels) {
-            CUDA_TRY(cudaMalloc(&out->devLevels, out->triangleCount ? out->triangleCount : 1));
+            CUDA_TRY(cudaMallocAsync((void**)&out->devLevels, out->triangleCount ? out->triangleCount : 1, 0));
             CUDA_TRY(cudaMemcpyAsync(out->devLevels, desc.subdivisionLevels, out->triangleCount, cudaMemcpyHostToDevice, 0));
             out->h2dBytes += out->triangleCount;
         }
         if (desc.formats) {
-            CUDA_TRY(cudaMalloc(&out->devFormats, (size_t)(out->triangleCount ? out->triangleCount : 1) * 4));
+            CUDA_TRY(cudaMallocAsync((void**)&out->devFormats, (size_t)(out->triangleCount ? out->triangleCount : 1) * 4, 0));
             CUDA_TRY(cudaMemcpyAsync(out->devFormats, desc.formats, (size_t)out->triangleCount * 4, cudaMemcpyHostToDevice, 0));
             out->h2dBytes += (uint64_t)out->triangleCount * 4;
         }
@@ -765,10 +853,10 @@ cleanup:
 }
 void DestroyStagedDevice(StagedInputs* s) {
     cudaSetDevice(s->device);
-    if (s->devIndices) cudaFree(s->devIndices);
-    if (s->devTexCoords) cudaFree(s->devTexCoords);
-    if (s->devLevels) cudaFree(s->devLevels);
-    if (s->devFormats) cudaFree(s->devFormats);
+    if (s->devIndices) cudaFreeAsync(s->devIndices, 0);
+    if (s->devTexCoords) cudaFreeAsync(s->devTexCoords, 0);
+    if (s->devLevels) cudaFreeAsync(s->devLevels, 0);
+    if (s->devFormats) cudaFreeAsync(s->devFormats, 0);
     s->devIndices = s->devTexCoords = nullptr;
     s->devLevels = nullptr;
     s->devFormats = nullptr;
@@ -1129,11 +1217,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         const unsigned long long unitBegin = bounds[rank].unit, unitEnd = bounds[rank + 1].unit;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
         if (itemEnd > itemBegin) {
-            const unsigned long long blocks = (unitEnd - unitBegin + 7) / 8;
+            const unsigned long long blocks = (unitEnd - unitBegin + kClassifyWarps - 1) / kClassifyWarps;
             const unsigned long long kMaxGrid = 0x7FFFFFFFull;
+            const ClassifyFn classify = SelectClassifyKernel(P);
             for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
                 const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
-                ClassifyKernel<<<(uint32_t)nb, 256, 0, stream>>>(P, items, unitStart, wordStart, itemBegin, itemEnd, unitBegin + b0 * 8, unitEnd, stateWords);
+                classify<<<(uint32_t)nb, kClassifyWarps * 32, 0, stream>>>(P, items, unitStart, wordStart, itemBegin, itemEnd,
+                                                                          unitBegin + b0 * kClassifyWarps, unitEnd, stateWords);
                 launches++;
             }
         }
@@ -1244,10 +1334,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         res->descCount = numDescs;
         res->indexCount = T;
         res->indexFormat = ifmt;
-        CUDA_TRY(cudaMalloc(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4));
+        CUDA_TRY(cudaMallocAsync(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4, stream));
         if (numDescs) {
-            CUDA_TRY(cudaMalloc(&res->devArrayData, (size_t)arrayBytes + 16));
-            CUDA_TRY(cudaMalloc(&res->devDescArray, (size_t)numDescs * sizeof(ommCpuOpacityMicromapDesc)));
+            CUDA_TRY(cudaMallocAsync(&res->devArrayData, (size_t)arrayBytes + 16, stream));
+            CUDA_TRY(cudaMallocAsync(&res->devDescArray, (size_t)numDescs * sizeof(ommCpuOpacityMicromapDesc), stream));
             SortedBlockSizes<<<(numDescs + TPB - 1) / TPB, TPB, 0, stream>>>(sortValsOut, items, numDescs, (int)d.format, blockBytes, descOfItem);
             size_t tmp = cubTempBytes;
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, blockOffset, (int)numDescs, stream));
@@ -1318,7 +1408,11 @@ ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, 0));
     if (res->descCount) {
-        res->hostArrayData = res->alloc.alloc(res->arrayDataSize, 64);
+        if (res->usesDefaultAllocator && res->arrayDataSize >= (1u << 20)) {
+            res->hostArrayData = PinnedPoolAcquire(res->arrayDataSize);
+            res->arrayDataFromPinnedPool = res->hostArrayData != nullptr;
+        }
+        if (!res->hostArrayData) res->hostArrayData = res->alloc.alloc(res->arrayDataSize, 64);
         res->hostDescArray = res->alloc.alloc((size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), 64);
         if (!res->hostArrayData || !res->hostDescArray) { rc = ommResult_FAILURE; goto cleanup; }
         CUDA_TRY(cudaMemcpyAsync(res->hostArrayData, res->devArrayData, res->arrayDataSize, cudaMemcpyDeviceToHost, 0));
@@ -1349,9 +1443,9 @@ cleanup:
 
 void DestroyResultDevice(BakeResultObject* res) {
     if (res->devArrayData || res->devDescArray || res->devIndexBuffer) cudaSetDevice(res->device);
-    if (res->devArrayData) cudaFree(res->devArrayData);
-    if (res->devDescArray) cudaFree(res->devDescArray);
-    if (res->devIndexBuffer) cudaFree(res->devIndexBuffer);
+    if (res->devArrayData) cudaFreeAsync(res->devArrayData, 0);
+    if (res->devDescArray) cudaFreeAsync(res->devDescArray, 0);
+    if (res->devIndexBuffer) cudaFreeAsync(res->devIndexBuffer, 0);
     res->devArrayData = res->devDescArray = res->devIndexBuffer = nullptr;
 }
 

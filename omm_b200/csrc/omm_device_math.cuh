@@ -125,7 +125,7 @@ __device__ __forceinline__ Tri MicroTri(float2 p0, float2 p1, float2 p2, uint32_
 }
 
 // ---- texture addressing (ref: util/texture.h:35-91) ----------------------------------------------------------------
-__device__ __forceinline__ int Addr1(int mode, int pow2, int c, int size, int sizeLog2) {
+__device__ __forceinline__ int Addr1Generic(int mode, int pow2, int c, int size, int sizeLog2) {
     switch (mode) {
     case ommTextureAddressMode_Wrap:
         return pow2 ? (int)((uint32_t)c & (uint32_t)(size - 1)) : (int)((uint32_t)c % (uint32_t)size);
@@ -152,31 +152,50 @@ __device__ __forceinline__ int Addr1(int mode, int pow2, int c, int size, int si
     }
 }
 
+// Compile-time specialisations of the kernel for the common sampler / texture combinations; kAddrGeneric keeps every
+// combination available through the run-time switch above.
+enum AddrSel { kAddrGeneric = 0, kAddrWrapPow2 = 1, kAddrClamp = 2 };
+template <int kAddr_, bool kFp32_>
+struct KernelCfg {
+    static constexpr int kAddr = kAddr_;
+    static constexpr bool kFp32 = kFp32_;
+};
+
+template <class Cfg>
+__device__ __forceinline__ int Addr1(int mode, int pow2, int c, int size, int sizeLog2) {
+    if (Cfg::kAddr == kAddrWrapPow2) return (int)((uint32_t)c & (uint32_t)(size - 1));
+    if (Cfg::kAddr == kAddrClamp) return clampi(c, 0, size - 1);
+    return Addr1Generic(mode, pow2, c, size, sizeLog2);
+}
+
+template <class Cfg>
 __device__ __forceinline__ float TexLoad(const DevTexture& t, const DevMip& m, int x, int y) {  // ref: texture_impl.h:178-202
-    const unsigned long long idx = m.texelOffset + (unsigned long long)x + (unsigned long long)y * (unsigned long long)m.w;
-    if (t.isFp32) return __ldg((const float*)t.texels + idx);
+    const unsigned long long idx = m.texelOffset + (unsigned long long)((unsigned)x + (unsigned)y * (unsigned)m.w);
+    if (Cfg::kFp32) return __ldg((const float*)t.texels + idx);
     return (float)__ldg((const uint8_t*)t.texels + idx) * (1.f / 255.f);
 }
 // texel (x,y) through address mode + border colour
+template <class Cfg>
 __device__ __forceinline__ float TexFetch(const BakeParams& P, const DevMip& m, int cx, int cy) {
-    if (cx == kTexCoordBorder || cy == kTexCoordBorder) return P.borderAlpha;
-    return TexLoad(P.tex, m, cx, cy);
+    if (Cfg::kAddr == kAddrGeneric && (cx == kTexCoordBorder || cy == kTexCoordBorder)) return P.borderAlpha;
+    return TexLoad<Cfg>(P.tex, m, cx, cy);
 }
 __device__ __forceinline__ float GlmLerp(float x, float y, float a) { return x * (1.f - a) + y * a; }
 
 // ref: texture_impl.cpp:261-278 -- run-time bilinear point sample (per-mip pow2 flag).  The SDK reads out of bounds for
 // Border addressing when the footprint leaves the texture; here such texels are borderAlpha (documented deviation on
 // an input the SDK itself cannot process).
+template <class Cfg>
 __device__ __forceinline__ float TexBilinear(const BakeParams& P, const DevMip& m, float2 p) {
     const float px = p.x * (float)m.w - 0.5f, py = p.y * (float)m.h - 0.5f;
     const float fx = floorf(px), fy = floorf(py);
     const int ix = f2i(fx), iy = f2i(fy);
-    const int x0 = Addr1(P.addrMode, m.isPow2, ix, m.w, m.log2w), y0 = Addr1(P.addrMode, m.isPow2, iy, m.h, m.log2h);
-    const int x1 = Addr1(P.addrMode, m.isPow2, ix + 1, m.w, m.log2w), y1 = Addr1(P.addrMode, m.isPow2, iy + 1, m.h, m.log2h);
-    const float a = TexFetch(P, m, x0, y0);
-    const float b = TexFetch(P, m, x0, y1);
-    const float c = TexFetch(P, m, x1, y0);
-    const float d = TexFetch(P, m, x1, y1);
+    const int x0 = Addr1<Cfg>(P.addrMode, m.isPow2, ix, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, m.isPow2, iy, m.h, m.log2h);
+    const int x1 = Addr1<Cfg>(P.addrMode, m.isPow2, ix + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, m.isPow2, iy + 1, m.h, m.log2h);
+    const float a = TexFetch<Cfg>(P, m, x0, y0);
+    const float b = TexFetch<Cfg>(P, m, x0, y1);
+    const float c = TexFetch<Cfg>(P, m, x1, y0);
+    const float d = TexFetch<Cfg>(P, m, x1, y1);
     const float wx = px - fx, wy = py - fy;
     const float ac = GlmLerp(a, c, wx);
     const float bd = GlmLerp(b, d, wx);
@@ -205,19 +224,31 @@ __device__ __forceinline__ bool IsZero(float v, float eps) { return v < eps && v
 __device__ __forceinline__ float Len2(float x, float y) { return sqrtf(x * x + y * y); }
 __device__ __forceinline__ bool InUnitSquare(float x, float y) { return x >= 0.f && x <= 1.f && y >= 0.f && y <= 1.f; }
 
-struct EdgeSeg {
-    float2 p0, p1;
-    float length;
-};
-__device__ __forceinline__ bool PointOnEdge(const EdgeSeg& e, float x, float y) {
-    const float l = Len2(x - e.p0.x, y - e.p0.y) + Len2(x - e.p1.x, y - e.p1.y) - e.length;
+// |p - p0| + |p - p1| - |p1 - p0| within 1e-5 (ref: bake_kernels_cpu.h:115-133).  The segment length is only ever used
+// here, so it is computed on demand (the reference computes it eagerly; the value is the same).
+__device__ __forceinline__ bool PointOnEdge(float2 p0, float2 p1, float x, float y) {
+    const float length = Len2(p1.x - p0.x, p1.y - p0.y);
+    const float l = Len2(x - p0.x, y - p0.y) + Len2(x - p1.x, y - p1.y) - length;
     return IsZero(l, 1e-5f);
 }
-// h = (a - cutoff, b, c, d); locals named as in the reference.
+
+// Exact pre-filter for "x = RN(n / c0) lies in [0,1]" that avoids the division when the answer is certainly no:
+//   * x <= 1  <=>  n/c0 <= 1 exactly: if n/c0 > 1 then |n| >= nextafter(|c0|), so n/c0 >= 1 + 2^-23/mant(c0) > 1 + 2^-24 and the
+//     correctly rounded quotient is >= 1 + 2^-23 > 1; if n/c0 <= 1, RN is monotonic and RN(1) = 1.
+//   * x >= 0 fails when n and c0 have strictly opposite signs, except when the quotient underflows to -0 (which compares
+//     >= 0): that needs |n| <= 2^-150 |c0|, excluded here by requiring |n| > 2^-100.
+// "true" means "cannot be decided cheaply or is inside": the caller then evaluates the reference expression itself.
+__device__ __forceinline__ bool QuotientMayBeInUnitRange(float n, float c0) {
+    const bool le1 = c0 > 0.f ? (n <= c0) : (n >= c0);
+    if (!le1) return false;                       // also rejects NaN numerators, like the reference's (x <= 1.f)
+    const bool oppositeSigns = (n > 0.f && c0 < 0.f) || (n < 0.f && c0 > 0.f);
+    if (oppositeSigns && fabsf(n) > 7.888609052e-31f) return false;
+    return true;
+}
+
+// h = (a - cutoff, b, c, d); locals named as in the reference (ref: bake_kernels_cpu.h:144-238).
 __device__ __noinline__ bool EdgeHyperbola(float2 p0, float2 p1, float hx, float hy, float hz, float hw) {
     if (p0.x > p1.x) { const float2 t = p0; p0 = p1; p1 = t; }
-    EdgeSeg edge;
-    edge.p0 = p0; edge.p1 = p1; edge.length = Len2(p1.x - p0.x, p1.y - p0.y);
     const float a = hx, b = hy, c = hz, d = hw;
     const float k_denum = p1.x - p0.x;
     if (IsZero(k_denum, 1e-6f)) {
@@ -226,8 +257,9 @@ __device__ __noinline__ bool EdgeHyperbola(float2 p0, float2 p1, float hx, float
         const float c0 = d * n + c;
         const float c1 = a + b * n;
         if (IsZero(c0, 1e-6f)) return false;
+        if (!(x >= 0.f && x <= 1.f)) return false;  // InUnitSquare would fail on x whatever y is
         const float y = -c1 / c0;
-        return InUnitSquare(x, y) && PointOnEdge(edge, x, y);
+        return InUnitSquare(x, y) && PointOnEdge(p0, p1, x, y);
     }
     const float k_enum = p1.y - p0.y;
     const float k = k_enum / k_denum;
@@ -237,20 +269,28 @@ __device__ __noinline__ bool EdgeHyperbola(float2 p0, float2 p1, float hx, float
     const float c2 = a + c * m;
     if (IsZero(c0, 1e-6f)) {
         if (IsZero(c1, 1e-6f)) return false;
+        if (!QuotientMayBeInUnitRange(-c2, c1)) return false;
         const float x = -c2 / c1;
         const float y = k * x + m;
-        return InUnitSquare(x, y) && PointOnEdge(edge, x, y);
+        return InUnitSquare(x, y) && PointOnEdge(p0, p1, x, y);
     }
     const float innerRoot = c1 * c1 - 4.f * c0 * c2;
     if (innerRoot > 0.f) {
         const float root = sqrtf(innerRoot);
-        const float x0 = 0.5f * (-c1 + root) / c0;
-        const float x1 = 0.5f * (-c1 - root) / c0;
-        const float y0 = k * x0 + m;
-        const float y1 = k * x1 + m;
-        const bool i0 = InUnitSquare(x0, y0) && PointOnEdge(edge, x0, y0);
-        const bool i1 = InUnitSquare(x1, y1) && PointOnEdge(edge, x1, y1);
-        return i0 || i1;
+        const float n0 = 0.5f * (-c1 + root);
+        const float n1 = 0.5f * (-c1 - root);
+        bool hit = false;
+        if (QuotientMayBeInUnitRange(n0, c0)) {
+            const float x0 = n0 / c0;
+            const float y0 = k * x0 + m;
+            hit = InUnitSquare(x0, y0) && PointOnEdge(p0, p1, x0, y0);
+        }
+        if (!hit && QuotientMayBeInUnitRange(n1, c0)) {
+            const float x1 = n1 / c0;
+            const float y1 = k * x1 + m;
+            hit = InUnitSquare(x1, y1) && PointOnEdge(p0, p1, x1, y1);
+        }
+        return hit;
     }
     return false;
 }
@@ -260,16 +300,16 @@ struct Coverage {
 };
 
 // ref: bake_kernels_cpu.h:241-399.  `tri` is the micro-triangle in UV space (original winding).
-template <bool kDegenerate>
+template <class Cfg, bool kDegenerate>
 __device__ __forceinline__ void LevelLineCell(const BakeParams& P, const DevMip& m, const Tri& tri, int px, int py, Coverage& cov) {
     const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
-    const int x0 = Addr1(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
-    const int x1 = Addr1(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
+    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
+    const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
     // gatherRed = (c00, c01, c11, c10)
-    const float gx = TexFetch(P, m, x0, y0);
-    const float gy = TexFetch(P, m, x0, y1);
-    const float gz = TexFetch(P, m, x1, y1);
-    const float gw = TexFetch(P, m, x1, y0);
+    const float gx = TexFetch<Cfg>(P, m, x0, y0);
+    const float gy = TexFetch<Cfg>(P, m, x0, y1);
+    const float gz = TexFetch<Cfg>(P, m, x1, y1);
+    const float gw = TexFetch<Cfg>(P, m, x1, y0);
     if (!kDegenerate) {
         const float ipx = pfx * m.rcpw, ipy = pfy * m.rcph;
         const bool o0 = P.cutoff < gx, o1 = P.cutoff < gy, o2 = P.cutoff < gz, o3 = P.cutoff < gw;
@@ -309,21 +349,23 @@ __device__ __forceinline__ void LevelLineCell(const BakeParams& P, const DevMip&
 }
 
 // ref: bake_kernels_cpu.h:404-452 (only reachable through internal flag bits 7/8)
+template <class Cfg>
 __device__ __forceinline__ void ConservativeBilinearCell(const BakeParams& P, const DevMip& m, int px, int py, Coverage& cov) {
     const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
     const int ix = f2i(pfx), iy = f2i(pfy);
-    const int x0 = Addr1(P.addrMode, P.pow2Mip0, ix, m.w, m.log2w), y0 = Addr1(P.addrMode, P.pow2Mip0, iy, m.h, m.log2h);
-    const int x1 = Addr1(P.addrMode, P.pow2Mip0, ix + 1, m.w, m.log2w), y1 = Addr1(P.addrMode, P.pow2Mip0, iy + 1, m.h, m.log2h);
-    const float gx = TexFetch(P, m, x0, y0), gy = TexFetch(P, m, x0, y1), gz = TexFetch(P, m, x1, y1), gw = TexFetch(P, m, x1, y0);
+    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, ix, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, iy, m.h, m.log2h);
+    const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, ix + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, iy + 1, m.h, m.log2h);
+    const float gx = TexFetch<Cfg>(P, m, x0, y0), gy = TexFetch<Cfg>(P, m, x0, y1), gz = TexFetch<Cfg>(P, m, x1, y1), gw = TexFetch<Cfg>(P, m, x1, y0);
     const float mn = fminStd(fminStd(fminStd(gx, gy), gz), gw);
     const float mx = fmaxStd(fmaxStd(fmaxStd(gx, gy), gz), gw);
     if (P.cutoff < mx) cov.above += 1;
     if (P.cutoff > mn) cov.below += 1;
 }
 // ref: bake_cpu_impl.cpp:994-1009
+template <class Cfg>
 __device__ __forceinline__ void NearestCell(const BakeParams& P, const DevMip& m, int px, int py, Coverage& cov) {
-    const int cx = Addr1(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), cy = Addr1(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
-    const float alpha = TexFetch(P, m, cx, cy);
+    const int cx = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), cy = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
+    const float alpha = TexFetch<Cfg>(P, m, cx, cy);
     if (P.cutoff < alpha) cov.above += 1;
     else cov.below += 1;
 }
@@ -421,15 +463,16 @@ __device__ __forceinline__ bool RasterLineConservative(float2 lp0, float2 lp1, i
 
 // ---- coarse SAT classification of one micro-triangle (ref: bake_cpu_impl.cpp:749-801) ----------------------------
 // returns -1 when the coarse pass leaves the micro-triangle untouched, else the state it sets.
+template <class Cfg>
 __device__ __forceinline__ int CoarseState(const BakeParams& P, const Tri& st) {
     const DevMip& m = P.tex.mips[0];
     if (f2i(st.aabb_s.x) != f2i(st.aabb_e.x) || f2i(st.aabb_s.y) != f2i(st.aabb_e.y)) return -1;
     const float fsx = st.aabb_s.x * (float)m.w - 0.5f, fsy = st.aabb_s.y * (float)m.h - 0.5f;
     const float fex = st.aabb_e.x * (float)m.w - 0.5f, fey = st.aabb_e.y * (float)m.h - 0.5f;
-    const int sx = Addr1(P.addrMode, P.pow2Mip0, f2i(floorf(fsx)), m.w, m.log2w);
-    const int sy = Addr1(P.addrMode, P.pow2Mip0, f2i(floorf(fsy)), m.h, m.log2h);
-    const int ex = Addr1(P.addrMode, P.pow2Mip0, f2i(floorf(fex)) + 1, m.w, m.log2w);
-    const int ey = Addr1(P.addrMode, P.pow2Mip0, f2i(floorf(fey)) + 1, m.h, m.log2h);
+    const int sx = Addr1<Cfg>(P.addrMode, P.pow2Mip0, f2i(floorf(fsx)), m.w, m.log2w);
+    const int sy = Addr1<Cfg>(P.addrMode, P.pow2Mip0, f2i(floorf(fsy)), m.h, m.log2h);
+    const int ex = Addr1<Cfg>(P.addrMode, P.pow2Mip0, f2i(floorf(fex)) + 1, m.w, m.log2w);
+    const int ey = Addr1<Cfg>(P.addrMode, P.pow2Mip0, f2i(floorf(fey)) + 1, m.h, m.log2h);
     if (ex < sx || ey < sy) return -1;
     if (sx < 0 || sy < 0 || sx >= m.w || sy >= m.h) return -1;
     if (ex < 0 || ey < 0 || ex >= m.w || ey >= m.h) return -1;
@@ -450,12 +493,13 @@ __device__ __forceinline__ int CoarseState(const BakeParams& P, const Tri& st) {
 // Exact early-out: under ForceOpaque / ForceTransparent the final state depends only on whether both counters are
 // non-zero (bake_kernels_cpu.h:27-50), counters never decrease, and every later mip only adds to them, so the walk can
 // stop the moment both are non-zero.  Under Nearest promotion the counts matter and the full walk is done.
+template <class Cfg>
 __device__ __forceinline__ int ClassifyMicroTriangle(const BakeParams& P, float2 b0, float2 b1, float2 b2, bool baseDegenerate, uint32_t index,
                                                     uint32_t level) {
     const Tri st = MicroTri(b0, b1, b2, index, level);
     int state = ommOpacityState_UnknownOpaque;
     if (P.useCoarse) {
-        const int cs = CoarseState(P, st);
+        const int cs = CoarseState<Cfg>(P, st);
         if (cs >= 0) state = cs;
     }
     if (P.disableFine) return state;
@@ -466,17 +510,17 @@ __device__ __forceinline__ int ClassifyMicroTriangle(const BakeParams& P, float2
         if (!P.disableLevelLine) {
             for (int mip = 0; mip < P.tex.mipCount; ++mip) {
                 const DevMip& m = P.tex.mips[mip];
-                if (P.cutoff < TexBilinear(P, m, st.p0)) cov.above++;
+                if (P.cutoff < TexBilinear<Cfg>(P, m, st.p0)) cov.above++;
                 else cov.below++;
                 bool stop;
                 if (!baseDegenerate) {
                     stop = RasterTriConservative(st, m.w, m.h, -0.5f, [&](int x, int y) {
-                        LevelLineCell<false>(P, m, st, x, y, cov);
+                        LevelLineCell<Cfg, false>(P, m, st, x, y, cov);
                         return earlyOut && cov.above != 0 && cov.below != 0;
                     });
                 } else {
                     stop = RasterLineConservative(st.aabb_s, st.aabb_e, m.w, m.h, -0.5f, [&](int x, int y) {
-                        LevelLineCell<true>(P, m, st, x, y, cov);
+                        LevelLineCell<Cfg, true>(P, m, st, x, y, cov);
                         return earlyOut && cov.above != 0 && cov.below != 0;
                     });
                 }
@@ -487,17 +531,17 @@ __device__ __forceinline__ int ClassifyMicroTriangle(const BakeParams& P, float2
             const DevMip& m = P.tex.mips[0];
             const float2 c1 = make_float2(st.aabb_e.x, st.aabb_s.y), c2 = make_float2(st.aabb_s.x, st.aabb_e.y);
             const Tri t0 = MakeTri(st.aabb_s, c1, c2), t1 = MakeTri(st.aabb_e, c1, c2);
-            RasterTriConservative(t0, m.w, m.h, -0.5f, [&](int x, int y) { ConservativeBilinearCell(P, m, x, y, cov); return false; });
-            RasterTriConservative(t1, m.w, m.h, -0.5f, [&](int x, int y) { ConservativeBilinearCell(P, m, x, y, cov); return false; });
+            RasterTriConservative(t0, m.w, m.h, -0.5f, [&](int x, int y) { ConservativeBilinearCell<Cfg>(P, m, x, y, cov); return false; });
+            RasterTriConservative(t1, m.w, m.h, -0.5f, [&](int x, int y) { ConservativeBilinearCell<Cfg>(P, m, x, y, cov); return false; });
         } else {
             const DevMip& m = P.tex.mips[0];
-            RasterTriConservative(st, m.w, m.h, -0.5f, [&](int x, int y) { ConservativeBilinearCell(P, m, x, y, cov); return false; });
+            RasterTriConservative(st, m.w, m.h, -0.5f, [&](int x, int y) { ConservativeBilinearCell<Cfg>(P, m, x, y, cov); return false; });
         }
     } else {
         for (int mip = 0; mip < P.tex.mipCount; ++mip) {
             const DevMip& m = P.tex.mips[mip];
             const bool stop = RasterTriConservative(st, m.w, m.h, 0.f, [&](int x, int y) {
-                NearestCell(P, m, x, y, cov);
+                NearestCell<Cfg>(P, m, x, y, cov);
                 return earlyOut && cov.above != 0 && cov.below != 0;
             });
             if (stop) break;

@@ -122,6 +122,8 @@ struct BakeResultObject {
     uint32_t arrayDataSize = 0, descCount = 0, indexCount = 0;
     ommIndexFormat indexFormat = ommIndexFormat_UINT_32;
     bool downloaded = false;
+    bool arrayDataFromPinnedPool = false;  // hostArrayData came from the library's page-locked pool (default allocator only)
+    bool usesDefaultAllocator = false;
     struct BakerObject* baker = nullptr;
 };
 
@@ -148,6 +150,7 @@ struct ShardState {
 
 struct BakerObject {
     HostAllocator alloc;
+    bool usesDefaultAllocator = false;
     Logger log;
     int device = 0;
     ShardState shard;
@@ -170,5 +173,8 @@ ommResult InitSharding(BakerObject* baker, int rank, int world, const void* id, 
 ommResult GetNcclUniqueId(void* out, size_t size);
 void DestroySharding(BakerObject* baker);
 int CurrentDeviceOr(int fallback);
+// Page-locked host blocks recycled across bakes (used for big result arrays when the caller left the allocator to us).
+void* PinnedPoolAcquire(size_t bytes);
+void PinnedPoolRelease(void* p);
 
 }  // namespace ommb200
