@@ -395,5 +395,8 @@ OMM_API ommResult ommB200DownloadResult(ommCpuBakeResult bakeResult);
  */
 OMM_API ommResult ommB200InitSharding(ommBaker baker, int rank, int worldSize, const void* ncclUniqueIdBytes, size_t idSize);
 OMM_API ommResult ommB200GetNcclUniqueId(void* outBytes, size_t idSize);
+/* The partition used by sharded bakes, exposed for tests: unitPrefix is the exclusive prefix sum (entries = items + 1,
+ * last entry = total) of per-item warp units (max(4^level / 32, 1)); outFirstItem receives worldSize + 1 item indices. */
+OMM_API ommResult ommB200ComputeShardBounds(const uint64_t* unitPrefix, uint32_t entries, int worldSize, uint32_t* outFirstItem);
 
 #endif /* OMM_B200_H_ */

@@ -213,7 +213,7 @@ CORE_SYMBOLS = [
 B200_SYMBOLS = [
     "ommDebugGetStats", "ommB200SetDevice", "ommB200GetDeviceCount", "ommB200GetLastBakeTimings", "ommB200StageInputs",
     "ommB200DestroyStagedInputs", "ommB200BakeResident", "ommB200GetDeviceResultDesc", "ommB200DownloadResult",
-    "ommB200InitSharding", "ommB200GetNcclUniqueId",
+    "ommB200InitSharding", "ommB200GetNcclUniqueId", "ommB200ComputeShardBounds",
 ]
 
 
@@ -270,6 +270,8 @@ class OmmLib:
             d.ommB200InitSharding.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
             d.ommB200GetNcclUniqueId.restype = C.c_int
             d.ommB200GetNcclUniqueId.argtypes = [C.c_void_p, C.c_size_t]
+            d.ommB200ComputeShardBounds.restype = C.c_int
+            d.ommB200ComputeShardBounds.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
 
     def exported(self, name: str) -> bool:
         return hasattr(self.dll, name)

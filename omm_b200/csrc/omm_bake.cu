@@ -932,22 +932,33 @@ struct ShardBound {
     unsigned long long unit, word;
     uint32_t item, pad;
 };
-// bounds[r] = first work item of rank r (r = 0..world): items are split where the running unit count crosses r*U/world
-__global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart, uint32_t entries, int world,
-                            ShardBound* __restrict__ bounds) {
-    const int r = threadIdx.x;
-    if (r > world) return;
+// First work item of rank r (r = 0..world): items are split where the running unit count crosses r*U/world, so every
+// rank owns a contiguous run of whole work items and the state words of a rank are contiguous too.
+__host__ __device__ inline uint32_t ShardFirstItem(const unsigned long long* unitStart, uint32_t entries, int world, int r) {
     const unsigned long long total = unitStart[entries - 1];
-    const unsigned long long target = r == world ? total : (total / (unsigned long long)world) * (unsigned long long)r;
+    const unsigned long long target = r >= world ? total : (total / (unsigned long long)world) * (unsigned long long)r;
     uint32_t lo = 0, hi = entries - 1;  // smallest i with unitStart[i] >= target
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (unitStart[mid] >= target) hi = mid;
         else lo = mid + 1;
     }
+    return lo;
+}
+__global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart, uint32_t entries, int world,
+                            ShardBound* __restrict__ bounds) {
+    const int r = threadIdx.x;
+    if (r > world) return;
+    const uint32_t lo = ShardFirstItem(unitStart, entries, world, r);
     bounds[r].item = lo;
     bounds[r].unit = unitStart[lo];
     bounds[r].word = wordStart[lo];
+}
+// host mirror of the partition (same function), exported for the CPU-side multi-rank tests
+ommResult ComputeShardBounds(const unsigned long long* unitStart, uint32_t entries, int world, uint32_t* outFirstItem) {
+    if (!unitStart || !outFirstItem || entries == 0 || world < 1) return ommResult_INVALID_ARGUMENT;
+    for (int r = 0; r <= world; ++r) outFirstItem[r] = ShardFirstItem(unitStart, entries, world, r);
+    return ommResult_SUCCESS;
 }
 
 // workload metric of the SDK (ref: bake_cpu_impl.cpp:662-680): sum over work items of int(aabb.x*texW) * int(aabb.y*texH)

@@ -1,0 +1,80 @@
+"""Worker for the sharded-bake parity test (launched with torch.distributed.run, one rank per GPU): every rank bakes
+the same inputs with work items sharded over the ranks and must end up with the byte-identical full result."""
+import ctypes as C
+import hashlib
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from omm_b200 import Baker, capi, load_product_library  # noqa: E402
+from omm_b200 import workloads as W  # noqa: E402
+import parity_cases as PC  # noqa: E402
+
+
+def digest(res):
+    h = hashlib.sha256()
+    for k in ("array_data", "desc_array", "desc_histogram", "index_buffer", "index_histogram"):
+        h.update(getattr(res, k).tobytes())
+    h.update(bytes([res.index_format]))
+    return h.hexdigest()
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    lib = load_product_library()
+    assert lib.dll.ommB200SetDevice(local) == capi.SUCCESS
+    cases = {
+        "c3_l6": W.config3(num_tris=3000, tex_size=512, level=6),
+        "c5_mixed": W.config5(num_tris=4000, tex_size=256, distinct=300, flat_tris=600, max_level=8),
+        "c2": W.config2(num_quads=400, tex_size=256, level=4),
+        "tiny_levels": PC.cases()["per_triangle_levels"][0](),
+    }
+    out = {}
+    for name, wl in cases.items():
+        # single-GPU result on this rank
+        with Baker(lib) as b:
+            inp, tex = W.make_input(b, wl)
+            single = b.bake(inp)
+            tex.destroy()
+        # sharded result
+        b = Baker(lib)
+        idbuf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            raw = (C.c_uint8 * 128)()
+            assert lib.dll.ommB200GetNcclUniqueId(raw, 128) == capi.SUCCESS
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
+        assert lib.dll.ommB200InitSharding(b.handle, rank, world, raw, 128) == capi.SUCCESS
+        inp, tex = W.make_input(b, wl)
+        sharded = b.bake(inp)
+        mine = sharded.timings.microTriangles
+        tex.destroy()
+        b.destroy()
+        assert sharded.diff(single) == [], f"rank {rank} {name}: sharded result differs from the single-GPU result"
+        t = torch.tensor([mine], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        out[name] = {"digest": digest(sharded), "micro_triangles_all_ranks": int(t.item()), "micro_triangles_single": int(single.timings.microTriangles)}
+        assert out[name]["micro_triangles_all_ranks"] == out[name]["micro_triangles_single"], out[name]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    for g in gathered[1:]:
+        assert g == gathered[0], "ranks disagree"
+    if rank == 0:
+        print("SHARDED_OK " + json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

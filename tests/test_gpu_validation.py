@@ -1,0 +1,172 @@
+"""Validation behaviour that needs a texture (hence a GPU): return codes and message texts of ommCpuBake for invalid
+descs, compared verbatim with the SDK build when it travelled (ref: bake_cpu_impl.cpp:235-290, 652-657, 682-713;
+support/tests/test_omm_log.cpp:146-208)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from omm_b200 import Baker, capi
+from omm_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _attempt(lib, mutate, tex_cutoff=-1.0, flags=0):
+    msgs = []
+    wl = W.random_mesh(5, 50, tex_size=(64, 64), tex_alpha_cutoff=tex_cutoff)
+    with Baker(lib, on_message=lambda sev, m: msgs.append((sev, m))) as b:
+        inp, tex = W.make_input(b, wl, bake_flags=flags)
+        d = inp.to_desc()
+        mutate(d)
+        h = C.c_void_p()
+        rc = lib.dll.ommCpuBake(b.handle, C.byref(d), C.byref(h))
+        if rc == capi.SUCCESS:
+            lib.dll.ommCpuDestroyBakeResult(h)
+        else:
+            assert not h.value
+        tex.destroy()
+    return rc, msgs
+
+
+def _set(field, value):
+    def f(d):
+        setattr(d, field, value)
+    return f
+
+
+def _sampler(addr=None, filt=None):
+    def f(d):
+        if addr is not None:
+            d.runtimeSamplerDesc.addressingMode = addr
+        if filt is not None:
+            d.runtimeSamplerDesc.filter = filt
+    return f
+
+
+CASES = {
+    "alphaMode": (_set("alphaMode", capi.ALPHA_MAX), "[Invalid Argument] - alphaMode is not set"),
+    "addressing": (_sampler(addr=capi.ADDR_MAX), "[Invalid Argument] - runtimeSamplerDesc.addressingMode is not set"),
+    "filter": (_sampler(filt=capi.FILTER_MAX), "[Invalid Argument] - runtimeSamplerDesc.filter is not set"),
+    "texCoordFormat": (_set("texCoordFormat", capi.UV_MAX), "[Invalid Argument] - texCoordFormat is not set"),
+    "texCoords": (_set("texCoords", None), "[Invalid Argument] - texCoords is not set"),
+    "indexFormat": (_set("indexFormat", capi.INDEX_MAX), "[Invalid Argument] - indexFormat is not set"),
+    "indexBuffer": (_set("indexBuffer", None), "[Invalid Argument] - indexBuffer is not set"),
+    "indexCount": (_set("indexCount", 0), "[Invalid Argument] - indexCount is not set"),
+    "maxLevel": (_set("maxSubdivisionLevel", 13), "[Invalid Argument] - maxSubdivisionLevel (13) is greater than maximum supported (12)"),
+    "gt_state_2state": (lambda d: (setattr(d, "format", capi.FORMAT_2_STATE), setattr(d, "alphaCutoffGreater", capi.STATE_UO)),
+                        "[Invalid Argument] - alphaCutoffGreater=UnknownOpaque is not compatible with OC1_2_State"),
+    "le_state_2state": (lambda d: (setattr(d, "format", capi.FORMAT_2_STATE), setattr(d, "alphaCutoffLessEqual", capi.STATE_UT)),
+                        "[Invalid Argument] - alphaCutoffLessEqual=UnknownTransparent is not compatible with OC1_2_State"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_invalid_desc_messages(name, product_lib, checker_lib):
+    mutate, text = CASES[name]
+    rc, msgs = _attempt(product_lib, mutate)
+    assert rc == capi.INVALID_ARGUMENT
+    assert msgs == [(capi.SEVERITY_FATAL, text)]
+    if "libomm-lib" in checker_lib.path:
+        assert _attempt(checker_lib, mutate) == (rc, msgs)
+
+
+def test_texture_cutoff_mismatch_message(product_lib, checker_lib):
+    rc, msgs = _attempt(product_lib, _set("alphaCutoff", 0.25), tex_cutoff=0.5)
+    assert rc == capi.INVALID_ARGUMENT
+    assert msgs == [(capi.SEVERITY_FATAL, "[Invalid Argument] - Texture object alpha cutoff threshold (0.500000) is different from alpha cutoff threshold in bake input (0.250000)")]
+    if "libomm-lib" in checker_lib.path:
+        assert _attempt(checker_lib, _set("alphaCutoff", 0.25), tex_cutoff=0.5) == (rc, msgs)
+
+
+def test_workload_limit_and_validation_messages(product_lib, checker_lib):
+    # ref: test_omm_bake_cpu.cpp:2022-2032 (WORKLOAD_TOO_BIG) and bake_cpu_impl.cpp:652-657 / 700-709 (info + perf warning)
+    rc, msgs = _attempt(product_lib, _set("maxWorkloadSize", 10))
+    assert rc == capi.WORKLOAD_TOO_BIG and msgs == []
+    wl = W.random_mesh(6, 200, tex_size=(64, 64), nan_frac=0.2, uv_lo=-40.0, uv_hi=40.0, tri_texels=64 * 300.0)
+    out = []
+    for lib in [product_lib] + ([checker_lib] if "libomm-lib" in checker_lib.path else []):
+        msgs = []
+        with Baker(lib, on_message=lambda sev, m: msgs.append((sev, m))) as b:
+            inp, tex = W.make_input(b, wl, bake_flags=capi.BAKE_ENABLE_VALIDATION | capi.BAKE_INT_DISABLE_FINE, max_subdivision_level=1)
+            res = b.bake(inp)
+            tex.destroy()
+        out.append((msgs, res))
+    msgs = out[0][0]
+    assert any(sev == capi.SEVERITY_INFO and "unclassifiable triangles" in m for sev, m in msgs)
+    assert any(sev == capi.SEVERITY_PERF_WARNING and "This is unusually large" in m for sev, m in msgs)
+    if len(out) == 2:
+        assert out[0][0] == out[1][0], "validation messages differ from the SDK build"
+        assert out[0][1].diff(out[1][1]) == []
+
+
+def test_unsupported_features_fail_loudly(product_lib):
+    rc, msgs = _attempt(product_lib, lambda d: None, flags=capi.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION)
+    assert rc == capi.NOT_IMPLEMENTED and msgs and "not implemented" in msgs[0][1]
+    rc, msgs = _attempt(product_lib, _set("maxArrayDataSize", 1000))
+    assert rc == capi.NOT_IMPLEMENTED and msgs
+
+
+def test_resident_bake_and_device_result(product_lib):
+    """ommB200StageInputs / BakeResident / GetDeviceResultDesc / DownloadResult give the same bytes as ommCpuBake."""
+    wl = W.config3(num_tris=500, tex_size=256, level=5)
+    with Baker(product_lib) as b:
+        inp, tex = W.make_input(b, wl)
+        want = b.bake(inp)
+        d = inp.to_desc()
+        staged = C.c_void_p()
+        assert product_lib.dll.ommB200StageInputs(b.handle, C.byref(d), C.byref(staged)) == capi.SUCCESS
+        h = C.c_void_p()
+        assert product_lib.dll.ommB200BakeResident(b.handle, staged, None, C.byref(h)) == capi.SUCCESS
+        dev = capi.B200DeviceResultDesc()
+        assert product_lib.dll.ommB200GetDeviceResultDesc(h, C.byref(dev)) == capi.SUCCESS
+        assert dev.arrayDataSize == want.array_data.size and dev.descArrayCount == want.desc_array.size and dev.arrayData
+        assert product_lib.dll.ommB200DownloadResult(h) == capi.SUCCESS
+        p = C.POINTER(capi.CpuBakeResultDesc)()
+        assert product_lib.dll.ommCpuGetBakeResultDesc(h, C.byref(p)) == capi.SUCCESS
+        from omm_b200.baker import _copy_result
+        got = _copy_result(p.contents)
+        product_lib.dll.ommCpuDestroyBakeResult(h)
+        product_lib.dll.ommB200DestroyStagedInputs(staged)
+        tex.destroy()
+    assert got.diff(want) == []
+
+
+def test_user_allocator_is_honoured(product_lib):
+    """All host memory visible through the ABI comes from ommMemoryAllocatorInterface (ref: omm.h:214-232, bake.cpp:123-124)."""
+    live, total = {}, [0]
+    libc = C.CDLL(None)
+    libc.aligned_alloc.restype, libc.aligned_alloc.argtypes = C.c_void_p, [C.c_size_t, C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+
+    def alloc(user, size, align):
+        align = max(int(align), 16)
+        p = libc.aligned_alloc(align, (int(size) + align - 1) // align * align)
+        live[p] = size
+        total[0] += 1
+        return p
+
+    def free(user, p):
+        if p:
+            assert p in live, "free of a pointer the allocator never returned"
+            del live[p]
+            libc.free(p)
+
+    a_cb, f_cb = capi.ALLOCATE_FN(alloc), capi.FREE_FN(free)
+    r_cb = capi.REALLOCATE_FN(lambda user, p, size, align: None)
+    desc = capi.BakerCreationDesc()
+    desc.type = capi.BAKER_CPU
+    desc.memoryAllocatorInterface.allocate, desc.memoryAllocatorInterface.reallocate, desc.memoryAllocatorInterface.free = a_cb, r_cb, f_cb
+    hb = C.c_void_p()
+    assert product_lib.dll.ommCreateBaker(C.byref(desc), C.byref(hb)) == capi.SUCCESS
+    b = Baker.__new__(Baker)
+    b.lib, b.handle, b._cb, b.messages = product_lib, hb.value, None, []
+    wl = W.config3(num_tris=300, tex_size=256, level=5)
+    inp, tex = W.make_input(b, wl)
+    res = b.bake(inp)
+    assert res.array_data.size > 0 and total[0] >= 4
+    tex.destroy()
+    b.destroy()
+    assert live == {}, f"leaked {len(live)} host allocations"
