@@ -275,6 +275,11 @@ static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, Bak
     if (d == 0) return b->log.InvalidArg("input desc was not set");  // ref: bake.cpp:110-113
     if (HandleTagOf(baker) != HandleTag::CpuBaker) return b->log.InvalidArg("Baker was not created as the right type");
     if (d->texture == 0) return b->log.InvalidArg("[Invalid Argument] - ommCpuBakeInputDesc has no texture set");  // ref: bake_cpu_impl.cpp:97-103
+    // ref: bake_cpu_impl.cpp:297-303 -- the SDK looks its kernel up by (format, tiling, addressing mode, filter, pow2) BEFORE it
+    // validates the desc, so an out-of-range addressing mode or filter yields FAILURE without a message.
+    if ((uint32_t)d->runtimeSamplerDesc.addressingMode >= (uint32_t)ommTextureAddressMode_MAX_NUM ||
+        (uint32_t)d->runtimeSamplerDesc.filter >= (uint32_t)ommTextureFilterMode_MAX_NUM)
+        return ommResult_FAILURE;
     const ommResult v = ValidateBakeDesc(b->log, *d);
     if (v != ommResult_SUCCESS) return v;
     const uint32_t flags = (uint32_t)d->bakeFlags;

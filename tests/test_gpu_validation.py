@@ -48,8 +48,6 @@ def _sampler(addr=None, filt=None):
 
 CASES = {
     "alphaMode": (_set("alphaMode", capi.ALPHA_MAX), "[Invalid Argument] - alphaMode is not set"),
-    "addressing": (_sampler(addr=capi.ADDR_MAX), "[Invalid Argument] - runtimeSamplerDesc.addressingMode is not set"),
-    "filter": (_sampler(filt=capi.FILTER_MAX), "[Invalid Argument] - runtimeSamplerDesc.filter is not set"),
     "texCoordFormat": (_set("texCoordFormat", capi.UV_MAX), "[Invalid Argument] - texCoordFormat is not set"),
     "texCoords": (_set("texCoords", None), "[Invalid Argument] - texCoords is not set"),
     "indexFormat": (_set("indexFormat", capi.INDEX_MAX), "[Invalid Argument] - indexFormat is not set"),
@@ -71,6 +69,14 @@ def test_invalid_desc_messages(name, product_lib, checker_lib):
     assert msgs == [(capi.SEVERITY_FATAL, text)]
     if "libomm-lib" in checker_lib.path:
         assert _attempt(checker_lib, mutate) == (rc, msgs)
+
+
+def test_unset_sampler_fields_fail_silently_like_the_sdk(product_lib, checker_lib):
+    """The SDK dispatches on (addressing mode, filter) before validating (ref: bake_cpu_impl.cpp:297-303): FAILURE, no message."""
+    for mutate in (_sampler(addr=capi.ADDR_MAX), _sampler(filt=capi.FILTER_MAX)):
+        assert _attempt(product_lib, mutate) == (capi.FAILURE, [])
+        if "libomm-lib" in checker_lib.path:
+            assert _attempt(checker_lib, mutate) == (capi.FAILURE, [])
 
 
 def test_texture_cutoff_mismatch_message(product_lib, checker_lib):
