@@ -310,9 +310,9 @@ def run_b200(a):
     peaks, peak_kind = measured_peaks()
     work_items, array_bytes, desc_count, my_utris, setup_ms, post_ms = last
     tex_bytes = a.tex * a.tex * 4
-    # algorithmic bytes of one classification launch on this rank: the texture once, one 40-byte item record per work item,
+    # algorithmic bytes of one classification launch on this rank: the texture once, one 32-byte item record per work item,
     # 2 bits written per micro-triangle (DESIGN.md "Kernels")
-    classify_bytes = tex_bytes + 40 * (work_items // world) + my_utris // 4
+    classify_bytes = tex_bytes + 32 * (work_items // world) + my_utris // 4
     cls_ms = sum(classify_ms) / len(classify_ms)
     achieved = classify_bytes / (cls_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "ClassifyKernel", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
