@@ -274,7 +274,7 @@ def run_b200(a):
             step_ms.append(ms)
             classify_ms.append(tm.classifyMs)
             launches += tm.kernelLaunches
-        last = (tm.workItems, tm.arrayDataBytes, tm.descCount, tm.microTriangles, tm.setupMs, tm.postMs)
+        last = (tm.workItems, tm.arrayDataBytes, tm.descCount, tm.microTriangles, tm.setupMs, tm.postMs, tm.itemPostMs, tm.gatherMs)
         lib.dll.ommCpuDestroyBakeResult(h)
     clocks = sampler.stop()
     lib.dll.ommB200DestroyStagedInputs(staged)
@@ -308,7 +308,7 @@ def run_b200(a):
 
     # ---- roofline of the dominant kernel (ClassifyKernel) ----
     peaks, peak_kind = measured_peaks()
-    work_items, array_bytes, desc_count, my_utris, setup_ms, post_ms = last
+    work_items, array_bytes, desc_count, my_utris, setup_ms, post_ms, item_post_ms, gather_ms = last
     tex_bytes = a.tex * a.tex * 4
     # algorithmic bytes of one classification launch on this rank: the texture once, one 32-byte item record per work item,
     # 2 bits written per micro-triangle (DESIGN.md "Kernels")
@@ -332,7 +332,7 @@ def run_b200(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "256 MiB buffer written between steps (outside the timed events)",
                        "work_items": work_items, "array_data_bytes": array_bytes, "desc_count": desc_count,
-                       "path_algorithmic_bytes": path_bytes, "setup_ms": setup_ms, "classify_ms": cls_ms, "post_ms": post_ms,
+                       "path_algorithmic_bytes": path_bytes, "setup_ms": setup_ms, "classify_ms": cls_ms, "post_ms": post_ms, "item_post_ms": item_post_ms, "gather_ms": gather_ms,
                        "sharding": "none" if world == 1 else f"work items split over {world} ranks, 1 NCCL all-gather of state blocks"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -351,6 +351,8 @@ typedef struct ommB200BakeTimings {
     float hostBakeMs;     /* device pipeline incl. the two small read-backs              */
     float hostDownloadMs; /* host allocation + D2H of the result arrays                  */
     float hostTotalMs;    /* whole ommCpuBake call                                       */
+    float itemPostMs;     /* special-index scan + XXH64 of this rank's items (part of postMs) */
+    float gatherMs;       /* NCCL all-gather of state blocks / digests (0 on one GPU; part of postMs) */
 } ommB200BakeTimings;
 
 /* Select the CUDA device used by bakers created afterwards on this thread's process (default: current device). */

@@ -163,6 +163,7 @@ class B200BakeTimings(C.Structure):
         ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64), ("arrayDataBytes", C.c_uint64),
         ("descCount", C.c_uint32), ("reserved", C.c_uint32),
         ("hostStageMs", C.c_float), ("hostBakeMs", C.c_float), ("hostDownloadMs", C.c_float), ("hostTotalMs", C.c_float),
+        ("itemPostMs", C.c_float), ("gatherMs", C.c_float),
     ]
 
 
@@ -202,7 +203,8 @@ def bake_input_desc_default() -> CpuBakeInputDesc:
 
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRODUCT_LIB = os.path.join(REPO_ROOT, "omm_b200", "lib", "libomm-b200.so")
+# OMM_B200_LIB overrides the library path (used to A/B kernel build variants; the default is the in-tree build)
+PRODUCT_LIB = os.environ.get("OMM_B200_LIB") or os.path.join(REPO_ROOT, "omm_b200", "lib", "libomm-b200.so")
 
 # the ABI every library must export (include/omm_b200.h, first half)
 CORE_SYMBOLS = [

@@ -334,10 +334,16 @@ __device__ __forceinline__ uint32_t FindItem(const unsigned long long* __restric
     return lo;
 }
 
-constexpr int kClassifyWarps = 8;  // warps (= units) per block
+#ifndef OMM_CLASSIFY_WARPS
+#define OMM_CLASSIFY_WARPS 4
+#endif
+#ifndef OMM_CLASSIFY_MIN_BLOCKS
+#define OMM_CLASSIFY_MIN_BLOCKS 10
+#endif
+constexpr int kClassifyWarps = OMM_CLASSIFY_WARPS;  // warps (= units) per block
 
 template <class Cfg>
-__global__ void __launch_bounds__(kClassifyWarps * 32) ClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items,
+__global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFY_MIN_BLOCKS) ClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items,
                                                                       const unsigned long long* __restrict__ unitStart,
                                                                       const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
                                                                       unsigned long long unitBegin, unsigned long long unitEnd,
@@ -1016,7 +1022,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     cudaStream_t stream = (cudaStream_t)userStream;
     bool ownStream = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     Scratch scratch{};
     void* cubTemp = nullptr;
     size_t cubTempBytes = 0;
@@ -1064,7 +1070,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         ownStream = true;
     }
     scratch.stream = stream;
-    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
     CUDA_TRY(cudaEventRecord(ev[0], stream));
 
     // ---- parameters ----
@@ -1239,6 +1245,16 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             }
         }
         myMicroTris = microTris;
+        CUDA_TRY(cudaEventRecord(ev[4], stream));  // end of the classification kernels proper
+        CUDA_TRY(scratch.alloc(&digest, W));
+        CUDA_TRY(scratch.alloc(&special, W));
+        if (itemEnd > itemBegin) {
+            // special-index scan + XXH64 of this rank's items (their state words are local already)
+            ItemPostKernel<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
+                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, digest, special);
+            launches++;
+        }
+        CUDA_TRY(cudaEventRecord(ev[5], stream));  // end of the per-item post pass
         if (world > 1) {
             // exact share of micro-triangles classified on this rank
             CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
@@ -1259,6 +1275,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 if (count == 0) continue;
                 uint32_t* seg = stateWords + bounds[r].word;
                 ncclOk = nccl.Broadcast(seg, seg, count, ncclUint32, r, (ncclComm_t)baker->shard.ncclComm, stream) == ncclSuccess;
+                const size_t nItems = bounds[r + 1].item - bounds[r].item;
+                if (ncclOk && nItems) {
+                    ncclOk = nccl.Broadcast(digest + bounds[r].item, digest + bounds[r].item, nItems, ncclUint64, r, (ncclComm_t)baker->shard.ncclComm, stream) ==
+                             ncclSuccess;
+                    ncclOk = ncclOk && nccl.Broadcast(special + bounds[r].item, special + bounds[r].item, nItems, ncclInt32, r,
+                                                      (ncclComm_t)baker->shard.ncclComm, stream) == ncclSuccess;
+                }
             }
             ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
             if (!ncclOk) {
@@ -1273,8 +1296,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     // ---- K5..K7: post ----
     if (W > 0) {
         const uint32_t gridW = (W + TPB - 1) / TPB;
-        CUDA_TRY(scratch.alloc(&digest, W));
-        CUDA_TRY(scratch.alloc(&special, W));
         CUDA_TRY(scratch.alloc(&survivor, W));
         CUDA_TRY(scratch.alloc(&hist, 64));
         CUDA_TRY(scratch.alloc(&sortKeysIn, W));
@@ -1285,9 +1306,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&blockBytes, (size_t)W + 1));
         CUDA_TRY(scratch.alloc(&blockOffset, (size_t)W + 1));
         CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
-        ItemPostKernel<<<(W + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
-                                                        (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, digest, special);
-        launches++;
         const uint64_t cap = NextPow2((uint64_t)W * 2 + 16);
         if (!disableDup) {
             // the UV table (capacity >= 2T+16 >= 2W+16) is reused for the digests
@@ -1382,8 +1400,15 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev[0], ev[1]); tm->setupMs = ms;
-        cudaEventElapsedTime(&ms, ev[1], ev[2]); tm->classifyMs = ms;
-        cudaEventElapsedTime(&ms, ev[2], ev[3]); tm->postMs = ms;
+        if (W > 0) {
+            cudaEventElapsedTime(&ms, ev[1], ev[4]); tm->classifyMs = ms;
+            cudaEventElapsedTime(&ms, ev[4], ev[5]); tm->itemPostMs = ms;
+            cudaEventElapsedTime(&ms, ev[5], ev[2]); tm->gatherMs = ms;
+            cudaEventElapsedTime(&ms, ev[4], ev[3]); tm->postMs = ms;
+        } else {
+            tm->classifyMs = tm->itemPostMs = tm->gatherMs = 0.f;
+            cudaEventElapsedTime(&ms, ev[1], ev[3]); tm->postMs = ms;
+        }
         cudaEventElapsedTime(&ms, ev[0], ev[3]); tm->totalDeviceMs = ms;
         tm->workItems = W;
         tm->kernelLaunches = launches;
@@ -1395,7 +1420,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
 cleanup:
     scratch.freeAll();
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 6; ++i)
         if (ev[i]) cudaEventDestroy(ev[i]);
     if (ownStream) {
         cudaStreamSynchronize(stream);

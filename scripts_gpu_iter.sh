@@ -2,7 +2,7 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -5
-timeout 900 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err
+timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --tris 400000 > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_iter.json'))
