@@ -285,14 +285,6 @@ static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, Bak
     const uint32_t flags = (uint32_t)d->bakeFlags;
     if ((flags & (1u << 7)) && !(flags & (1u << 8)))  // ref: bake_cpu_impl.cpp:718-719
         return b->log.InvalidArg("[Invalid Arg] - EnableAABBTesting can't be used without also setting DisableLevelLineIntersection");
-    if ((flags & ommCpuBakeFlags_EnableNearDuplicateDetection) || (flags & (1u << 10))) {
-        b->log.Log(ommMessageSeverity_Fatal, "[omm-b200] near-duplicate merging (EnableNearDuplicateDetection) is not implemented in this library yet");
-        return ommResult_NOT_IMPLEMENTED;
-    }
-    if (d->maxArrayDataSize != 0xFFFFFFFFu) {
-        b->log.Log(ommMessageSeverity_Fatal, "[omm-b200] maxArrayDataSize budgets (the Compress pass) are not implemented in this library yet");
-        return ommResult_NOT_IMPLEMENTED;
-    }
     *outBaker = b;
     return ommResult_SUCCESS;
 }

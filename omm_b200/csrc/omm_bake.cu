@@ -45,7 +45,7 @@ struct ItemRec {
     uint8_t level;
     uint8_t format;      // ommFormat of the item
     uint8_t degenerate;  // base UV triangle is degenerate (ref: util/geometry.h:44-47)
-    uint8_t pad;
+    uint8_t hashLevel;   // level the item was classified at: the exact-dedup digest always covers 4^hashLevel bytes, also after Compress
 };
 
 struct SetupArgs {
@@ -304,7 +304,7 @@ __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __res
     it.level = (uint8_t)triLevel[t];
     it.format = triFormat[t];
     it.degenerate = triDegenerate[t];
-    it.pad = 0;
+    it.hashLevel = it.level;
     items[w] = it;
     const unsigned long long n = 1ull << (2 * it.level);
     itemUnits[w] = n >= 32 ? n / 32 : 1;
@@ -418,37 +418,39 @@ __device__ __forceinline__ uint64_t Expand3State(uint32_t bits16) {
 
 __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
                                                       const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, float rejectionThreshold,
-                                                      int disableSpecial, uint64_t* __restrict__ digest, int32_t* __restrict__ special) {
+                                                      int disableSpecial, int keepExistingSpecial, uint64_t* __restrict__ digest, int32_t* special) {
     const uint32_t w = itemBegin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= itemEnd) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t level = items[w].level;
-    const uint32_t n = 1u << (2 * level);
+    const uint32_t n = 1u << (2 * level);                       // micro-triangles of the item now (uniformity / rejection test)
+    const uint32_t nHash = 1u << (2 * items[w].hashLevel);      // bytes the SDK's digest covers (>= n, differs only after Compress)
     const uint32_t* words = stateWords + wordStart[w];
     const uint32_t word0 = __ldg(words);
     const uint32_t s0 = word0 & 3u;
+    const uint32_t fullWords = n >> 4;                           // words entirely inside the first n fields
+    const uint32_t headMask = n >= 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u);  // valid fields of word 0 when n < 16
 
     uint64_t h;
     bool allEqual;
     uint32_t known;
-    if (n < 32) {
+    if (nHash < 32) {
         // levels 0..2: 1, 4 or 16 micro-triangles in one word
-        const uint32_t validMask = n == 16 ? 0xFFFFFFFFu : ((1u << (2 * n)) - 1u);
-        allEqual = ((word0 ^ (s0 * 0x55555555u)) & validMask) == 0;
-        known = __popc(~(word0 >> 1) & 0x55555555u & validMask);
+        allEqual = ((word0 ^ (s0 * 0x55555555u)) & headMask) == 0;
+        known = __popc(~(word0 >> 1) & 0x55555555u & headMask);
         const uint64_t lo = Expand3State(word0 & 0xFFFFu), hi = Expand3State(word0 >> 16);
-        h = 42ull + XP5 + (uint64_t)n;
-        if (n == 16) {
+        h = 42ull + XP5 + (uint64_t)nHash;
+        if (nHash == 16) {
             h ^= XxhRound(0, lo); h = Rotl64(h, 27) * XP1 + XP4;
             h ^= XxhRound(0, hi); h = Rotl64(h, 27) * XP1 + XP4;
-        } else if (n == 4) {
+        } else if (nHash == 4) {
             h ^= (lo & 0xFFFFFFFFull) * XP1; h = Rotl64(h, 23) * XP2 + XP3;
         } else {
             h ^= (lo & 0xFFull) * XP5; h = Rotl64(h, 11) * XP1;
         }
         h = XxhAvalanche(h);
     } else {
-        const uint32_t numWords = n >> 4;
+        const uint32_t numWords = nHash >> 4;
         const uint32_t pattern = s0 * 0x55555555u;
         uint32_t diff = 0;
         known = 0;
@@ -456,9 +458,11 @@ __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict_
         const uint32_t j = lane & 3;
         uint64_t acc = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
         for (uint32_t base = 0; base < numWords; base += 32) {
-            const uint32_t mine = (base + lane < numWords) ? __ldg(words + base + lane) : pattern;
-            diff |= mine ^ pattern;
-            if (base + lane < numWords) known += __popc(~(mine >> 1) & 0x55555555u);
+            const uint32_t wi = base + lane;
+            const uint32_t mine = (wi < numWords) ? __ldg(words + wi) : pattern;
+            const uint32_t valid = wi < fullWords ? 0xFFFFFFFFu : ((wi == 0 && n < 16) ? headMask : 0u);
+            diff |= (mine ^ pattern) & valid;
+            known += __popc(~(mine >> 1) & 0x55555555u & valid);
             const uint32_t stripes = min(16u, (numWords - base) >> 1);
             for (uint32_t s = 0; s < stripes; ++s) {
                 const uint32_t wsrc = __shfl_sync(0xFFFFFFFFu, mine, 2 * s + (j >> 1));
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict_
                        v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
         h = Rotl64(v1, 1) + Rotl64(v2, 7) + Rotl64(v3, 12) + Rotl64(v4, 18);
         h = XxhMerge(h, v1); h = XxhMerge(h, v2); h = XxhMerge(h, v3); h = XxhMerge(h, v4);
-        h += (uint64_t)n;
+        h += (uint64_t)nHash;
         h = XxhAvalanche(h);
     }
     if (lane == 0) {
@@ -485,7 +489,8 @@ __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict_
             }
         }
         digest[w] = h;
-        special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
+        // second promotion pass (ref: bake_cpu_impl.cpp:1439-1440): items that already carry a special index are left alone
+        if (!(keepExistingSpecial && special[w] != 0)) special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
     }
 }
 
@@ -539,8 +544,9 @@ __global__ void ItemHistogramAndKeys(const ItemRec* __restrict__ items, const in
     if (threadIdx.x < 26 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
-__global__ void TriangleFinalItems(const uint32_t* __restrict__ triItem, const uint32_t* __restrict__ survivor, const ItemRec* __restrict__ items,
-                                   const int32_t* __restrict__ special, uint32_t triCount, uint32_t* __restrict__ triFinal, uint32_t* __restrict__ hist) {
+__global__ void TriangleFinalItems(const uint32_t* __restrict__ triItem, const uint32_t* __restrict__ survivor, const uint32_t* __restrict__ mergeRoot,
+                                   const uint32_t* __restrict__ survivor2, const ItemRec* __restrict__ items, const int32_t* __restrict__ special,
+                                   uint32_t triCount, uint32_t* __restrict__ triFinal, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[26];
     if (threadIdx.x < 26) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -550,6 +556,7 @@ __global__ void TriangleFinalItems(const uint32_t* __restrict__ triItem, const u
         uint32_t f = kNoItem;
         if (w != kNoItem) {
             f = survivor[w];
+            if (survivor2) f = survivor2[mergeRoot[f]];  // near-duplicate merge, then the second exact dedup
             if (special[f] == 0) atomicAdd(&sh[(items[f].format - 1) * 13 + items[f].level], 1u);
         }
         triFinal[t] = f;
@@ -610,15 +617,17 @@ __global__ void __launch_bounds__(256) WriteDescsAndPack(const uint32_t* __restr
             }
         } else {
             const uint32_t numBytes = n >= 4 ? n >> 2 : 1;
+            const uint32_t byteMask = n >= 4 ? 0xFFu : ((1u << (2 * n)) - 1u);  // level 0: one 2-bit state in the byte
             for (uint32_t b = lane; b < numBytes; b += 32)
-                if (off + b < arrayBytes) dst[b] = (uint8_t)(__ldg(src + (b >> 2)) >> ((b & 3) * 8));
+                if (off + b < arrayBytes) dst[b] = (uint8_t)((__ldg(src + (b >> 2)) >> ((b & 3) * 8)) & byteMask);
         }
     } else {
         // 2-state: one bit per micro-triangle (the state's low bit)
         const uint32_t numBytes = n >= 8 ? n >> 3 : 1;
+        const uint32_t byteMask = n >= 8 ? 0xFFu : ((1u << n) - 1u);  // levels 0/1: 1 or 4 one-bit states in the byte
         for (uint32_t b = lane; b < numBytes; b += 32) {
             const uint32_t bits = CompressEvenBits16(__ldg(src + (b >> 1)));
-            if (off + b < arrayBytes) dst[b] = (uint8_t)(bits >> ((b & 1) * 8));
+            if (off + b < arrayBytes) dst[b] = (uint8_t)((bits >> ((b & 1) * 8)) & byteMask);
         }
     }
 }
@@ -989,6 +998,18 @@ __global__ void SumMicroTriangles(const ItemRec* __restrict__ items, uint32_t it
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(total, v);
 }
 
+// primitives per item after the first exact dedup (input of the host passes)
+__global__ void CountPrimitives(const uint32_t* __restrict__ triItem, const uint32_t* __restrict__ survivor, uint32_t triCount, uint32_t* __restrict__ primCount) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= triCount) return;
+    const uint32_t w = triItem[t];
+    if (w != kNoItem) atomicAdd(&primCount[survivor[w]], 1u);
+}
+__global__ void UpdateItemLevels(ItemRec* __restrict__ items, const uint8_t* __restrict__ levels, uint32_t numItems) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < numItems) items[w].level = levels[w];
+}
+
 __global__ void CountDisabled(const int8_t* __restrict__ triLevel, uint32_t triCount, uint32_t* __restrict__ count) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, t < triCount && triLevel[t] < 0);
@@ -1042,6 +1063,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     uint32_t* stateWords = nullptr;
     uint64_t* digest = nullptr;
     int32_t* special = nullptr;
+    uint32_t *mergeRoot = nullptr, *survivor2 = nullptr;
     uint32_t *survivor = nullptr, *hist = nullptr, *sortKeysIn = nullptr, *sortValsIn = nullptr, *sortKeysOut = nullptr, *sortValsOut = nullptr,
              *descOfItem = nullptr;
     unsigned long long *blockBytes = nullptr, *blockOffset = nullptr;
@@ -1251,7 +1273,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         if (itemEnd > itemBegin) {
             // special-index scan + XXH64 of this rank's items (their state words are local already)
             ItemPostKernel<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
-                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, digest, special);
+                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, digest, special);
             launches++;
         }
         CUDA_TRY(cudaEventRecord(ev[5], stream));  // end of the per-item post pass
@@ -1314,9 +1336,72 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches += 2;
         }
         DigestResolve<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
+        launches++;
+        if (HostPassesNeeded(d)) {
+            // ---- a17 / a18: near-duplicate merge and size-budget compression run on the host (omm_host_passes.cpp) ----
+            uint32_t* primCount = nullptr;
+            uint8_t* levelsDev = nullptr;
+            CUDA_TRY(scratch.alloc(&primCount, W));
+            CUDA_TRY(scratch.alloc(&mergeRoot, W));
+            CUDA_TRY(scratch.alloc(&survivor2, W));
+            CUDA_TRY(scratch.alloc(&levelsDev, W));
+            CUDA_TRY(cudaMemsetAsync(primCount, 0, sizeof(uint32_t) * W, stream));
+            CountPrimitives<<<gridT, TPB, 0, stream>>>(triItem, survivor, T, primCount);
+            launches++;
+            std::vector<ItemRec> hItems(W);
+            std::vector<int32_t> hSpecial(W);
+            std::vector<uint32_t> hPrims(W), hRoot(W), hWords((size_t)totalWords);
+            std::vector<unsigned long long> hWordStart((size_t)W + 1);
+            std::vector<uint8_t> hLevels(W);
+            std::vector<HostPassItem> hp(W);
+            CUDA_TRY(cudaMemcpyAsync(hItems.data(), items, sizeof(ItemRec) * W, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(hSpecial.data(), special, sizeof(int32_t) * W, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(hPrims.data(), primCount, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(hWordStart.data(), wordStart, sizeof(unsigned long long) * ((size_t)W + 1), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(hWords.data(), stateWords, sizeof(uint32_t) * (size_t)totalWords, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            for (uint32_t w = 0; w < W; ++w) {
+                HostPassItem& it = hp[w];
+                it.level = hItems[w].level;
+                it.format = hItems[w].format;
+                it.uv[0] = hItems[w].p0.x; it.uv[1] = hItems[w].p0.y; it.uv[2] = hItems[w].p1.x; it.uv[3] = hItems[w].p1.y;
+                it.uv[4] = hItems[w].p2.x; it.uv[5] = hItems[w].p2.y;
+                it.numPrims = hPrims[w];
+                it.special = hSpecial[w];
+                it.mergedInto = w;
+                it.statesChanged = false;
+            }
+            rc = RunHostPasses(d, hp.data(), W, hWords.data(), hWordStart.data());
+            if (rc != ommResult_SUCCESS) goto cleanup;
+            for (uint32_t w = 0; w < W; ++w) {
+                uint32_t r = w;
+                while (hp[r].mergedInto != r) r = hp[r].mergedInto;
+                hRoot[w] = r;
+                hSpecial[w] = hp[w].special;
+                hLevels[w] = (uint8_t)hp[w].level;
+            }
+            CUDA_TRY(cudaMemcpyAsync(stateWords, hWords.data(), sizeof(uint32_t) * (size_t)totalWords, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(special, hSpecial.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(mergeRoot, hRoot.data(), sizeof(uint32_t) * W, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync(levelsDev, hLevels.data(), W, cudaMemcpyHostToDevice, stream));
+            UpdateItemLevels<<<gridW, TPB, 0, stream>>>(items, levelsDev, W);
+            // ref: bake_cpu_impl.cpp:1969-1971 -- second exact dedup over ALL items with the current states, then the last promotion
+            // (computed first here; the dedup overwrites duplicates with -1 exactly as the serial order does)
+            ItemPostKernel<<<(W + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
+                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, digest, special);
+            launches += 2;
+            if (!disableDup) {
+                FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
+                DigestInsert<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1);
+                launches += 2;
+            }
+            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1, disableDup, survivor2, special);
+            launches++;
+            CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors above must outlive the copies
+        }
         ItemHistogramAndKeys<<<gridW, TPB, 0, stream>>>(items, special, W, hist, sortKeysIn, sortValsIn);
-        TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, items, special, T, triFinal, hist);
-        launches += 3;
+        TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, mergeRoot, survivor2, items, special, T, triFinal, hist);
+        launches += 2;
         {
             size_t tmp = cubTempBytes;
             CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(cubTemp, tmp, sortKeysIn, sortKeysOut, sortValsIn, sortValsOut, (int)W, 0, 32, stream));

@@ -125,6 +125,8 @@ def bake_digests():
     for name in DIGEST_CASES:
         mk, ov = cases[name]
         out[name] = result_digests(PC.run_bake(ref, mk(), **ov))
+    for name, (mk, ov) in PC.sdk_only_cases().items():   # near-duplicate merge / Compress: the port does not restate them
+        out["sdk_only:" + name] = result_digests(PC.run_bake(ref, mk(), **ov))
     return out
 
 

@@ -73,6 +73,28 @@ def cases():
     return c
 
 
+def sdk_only_cases():
+    """Cases for the optional passes the plain-C port does not restate (near-duplicate merge a17, Compress a18): checked
+    against the SDK build only (and its golden digests)."""
+    c = {}
+    hexa = lambda **kw: W.random_mesh(101, 700, tex_kind="blocky", tri_texels=14, max_subdivision_level=3, reuse_frac=0.1, **kw)
+    c["neardup_lsh_blocky"] = (lambda: hexa(bake_flags=A.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION), {})
+    c["neardup_lsh_noise_l4"] = (lambda: W.random_mesh(102, 500, tri_texels=10, max_subdivision_level=4, bake_flags=A.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION,
+                                                       near_duplicate_factor=0.25), {})
+    c["neardup_lsh_mixed_levels"] = (lambda: W.random_mesh(103, 600, tex_kind="circle", tri_texels=30, subdivision_levels=_levels(103, 600, 0, 5),
+                                                           bake_flags=A.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION, unknown_state_promotion=A.PROMOTE_NEAREST), {})
+    c["neardup_bruteforce"] = (lambda: hexa(bake_flags=A.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION | A.BAKE_INT_NEAR_DUP_BRUTE_FORCE), {})
+    c["neardup_lsh_rejection"] = (lambda: hexa(bake_flags=A.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION, rejection_threshold=0.5), {})
+    c["compress_budget_half"] = (lambda: W.random_mesh(104, 300, tri_texels=16, max_subdivision_level=4, max_array_data_size=8000), {})
+    c["compress_budget_tiny"] = (lambda: W.random_mesh(105, 200, tri_texels=16, max_subdivision_level=5, max_array_data_size=600), {})
+    c["compress_budget_not_binding"] = (lambda: W.random_mesh(106, 100, max_subdivision_level=3, max_array_data_size=1 << 20), {})
+    c["compress_and_neardup"] = (lambda: W.random_mesh(107, 400, tex_kind="blocky", tri_texels=14, max_subdivision_level=4, max_array_data_size=5000,
+                                                       bake_flags=A.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION), {})
+    c["compress_disable_dup"] = (lambda: W.random_mesh(108, 200, tri_texels=16, max_subdivision_level=4, max_array_data_size=4000,
+                                                       bake_flags=A.BAKE_DISABLE_DUPLICATE_DETECTION), {})
+    return c
+
+
 def uv_format_cases():
     """UV16_UNORM / UV16_FLOAT / strided UV32 variants of one mesh."""
     out = {}

@@ -31,3 +31,16 @@ def test_product_matches_port_too(product_lib, port_lib):
     from omm_b200 import workloads as W
     wl = W.config3(num_tris=400, tex_size=256, level=5)
     assert PC.run_bake(product_lib, wl).diff(PC.run_bake(port_lib, wl)) == []
+
+
+SDK_ONLY = PC.sdk_only_cases()
+
+
+@pytest.mark.parametrize("name", sorted(SDK_ONLY))
+def test_optional_passes_match_sdk(name, product_lib, ref_lib):
+    """Near-duplicate merge (LSH / brute force) and the Compress budget pass against the SDK build itself."""
+    mk, ov = SDK_ONLY[name]
+    wl = mk()
+    want = PC.run_bake(ref_lib, wl, **ov)
+    got = PC.run_bake(product_lib, wl, **ov)
+    assert got.diff(want) == [], name

@@ -108,13 +108,6 @@ def test_workload_limit_and_validation_messages(product_lib, checker_lib):
         assert out[0][1].diff(out[1][1]) == []
 
 
-def test_unsupported_features_fail_loudly(product_lib):
-    rc, msgs = _attempt(product_lib, lambda d: None, flags=capi.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION)
-    assert rc == capi.NOT_IMPLEMENTED and msgs and "not implemented" in msgs[0][1]
-    rc, msgs = _attempt(product_lib, _set("maxArrayDataSize", 1000))
-    assert rc == capi.NOT_IMPLEMENTED and msgs
-
-
 def test_resident_bake_and_device_result(product_lib):
     """ommB200StageInputs / BakeResident / GetDeviceResultDesc / DownloadResult give the same bytes as ommCpuBake."""
     wl = W.config3(num_tris=500, tex_size=256, level=5)

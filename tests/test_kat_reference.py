@@ -39,6 +39,16 @@ def test_product_reproduces_sdk_known_answers(name, product_lib):
 
 
 @pytest.mark.gpu
+def test_product_circle_merge_similar_kat(product_lib):
+    """ref: test_omm_bake_cpu.cpp:973-986 (Circle with EnableNearDuplicateDetection)."""
+    mk, _, _ = KATS["Circle"]
+    wl = mk()
+    wl.desc["bake_flags"] = capi.BAKE_ENABLE_INTERNAL_THREADS | capi.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION
+    res = PC.run_bake(product_lib, wl)
+    assert K.collect_stats(res) == _expected(dict(totalOpaque=200, totalTransparent=216, totalUnknownTransparent=42, totalUnknownOpaque=54))
+
+
+@pytest.mark.gpu
 def test_product_debug_stats_entry_point(product_lib):
     """ommDebugGetStats of the product agrees with the Python restatement."""
     from omm_b200 import Baker
