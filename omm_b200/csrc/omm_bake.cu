@@ -376,8 +376,167 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFY_MIN_BLOCKS) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K4, load-balanced variant (Linear filter + level-line test + single mip, i.e. the default configuration).
+//
+// Most micro-triangles cover one texel cell, some two to four, a few (coarse levels on big textures) thousands.  In the
+// kernel above the warp then idles through the extra cells of its unluckiest lane.  Here every lane evaluates only the
+// FIRST covered cell of its micro-triangle in place; every further (micro-triangle, cell) pair goes to a per-warp queue in
+// shared memory and is evaluated 32 pairs at a time by whichever lanes are free.  A warp processes kBatchUnits units per
+// batch so that the queue fills.  Coverage counters are sums over visited cells (bake_kernels_cpu.h:317-323, 348-354,
+// 371-372), so the evaluation order is immaterial; the set of visited cells is the reference's (RasterNext).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBatchUnits = 4;
+constexpr int kQueueCap = 64;  // >= 32 left over + 32 pushed per step
+struct WarpQueue {
+    float2 v0[kQueueCap], v1[kQueueCap], v2[kQueueCap];  // micro-triangle vertices (UV space)
+    int cx[kQueueCap], cy[kQueueCap];
+    uint32_t slot[kQueueCap];                             // unit-in-batch * 32 + lane
+    uint32_t above[kBatchUnits * 32], below[kBatchUnits * 32];  // coverage counters per (unit, lane)
+    int8_t fixedState[kBatchUnits * 32];                        // >= 0: decided without fine classification
+    uint32_t itemOf[kBatchUnits], firstOf[kBatchUnits];
+};
+
+template <class Cfg>
+__device__ __forceinline__ void DrainQueue(const BakeParams& P, const DevMip& m, WarpQueue& q, uint32_t head, uint32_t count, uint32_t lane) {
+    if (lane < count) {
+        const uint32_t e = (head + lane) & (kQueueCap - 1);
+        const Tri t = MakeTri(q.v0[e], q.v1[e], q.v2[e]);
+        Coverage c{0u, 0u};
+        LevelLineCell<Cfg, false>(P, m, t, q.cx[e], q.cy[e], c);
+        const uint32_t s = q.slot[e];
+        if (c.above) atomicAdd(&q.above[s], c.above);
+        if (c.below) atomicAdd(&q.below[s], c.below);
+    }
+    __syncwarp();
+}
+
+#ifndef OMM_CLASSIFYQ_MIN_BLOCKS
+#define OMM_CLASSIFYQ_MIN_BLOCKS 8
+#endif
+template <class Cfg>
+__global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS) ClassifyKernelQ(const BakeParams P, const ItemRec* __restrict__ items,
+                                                                       const unsigned long long* __restrict__ unitStart,
+                                                                       const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
+                                                                       unsigned long long unitBegin, unsigned long long unitEnd,
+                                                                       uint32_t* __restrict__ stateWords) {
+    __shared__ WarpQueue sQueues[kClassifyWarps];
+    __shared__ uint32_t sFirstItem;
+    const unsigned long long blockUnit = unitBegin + (unsigned long long)blockIdx.x * (kClassifyWarps * kBatchUnits);
+    if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(unitStart + itemBegin, itemEnd - itemBegin, blockUnit);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long batchUnit = blockUnit + (unsigned long long)warp * kBatchUnits;
+    if (batchUnit >= unitEnd) return;
+    WarpQueue& q = sQueues[warp];
+    const DevMip& m = P.tex.mips[0];
+    const bool earlyOut = P.promotion != ommUnknownStatePromotion_Nearest;
+    for (int i = lane; i < kBatchUnits * 32; i += 32) { q.above[i] = 0; q.below[i] = 0; }
+    __syncwarp();
+
+    uint32_t w = sFirstItem;
+    uint32_t head = 0, count = 0;            // queue state (warp-uniform)
+#pragma unroll 1
+    for (int u = 0; u < kBatchUnits; ++u) {
+        const unsigned long long unit = batchUnit + u;
+        if (unit >= unitEnd) {                                           // warp-uniform
+            if (lane == 0) q.itemOf[u] = kNoItem;
+            continue;
+        }
+        while (w + 1 < itemEnd && __ldg(&unitStart[w + 1]) <= unit) ++w;
+        const ItemRec it = items[w];
+        const uint32_t level = it.level, n = 1u << (2 * level);
+        const uint32_t first = (uint32_t)(unit - __ldg(&unitStart[w])) * 32u;
+        const uint32_t idx = first + lane;
+        if (lane == 0) {
+            q.itemOf[u] = w;
+            q.firstOf[u] = first;
+        }
+        if (it.degenerate) {                                             // warp-uniform: zero-area UV triangles take the serial path
+            q.fixedState[u * 32 + lane] = (int8_t)(idx < n ? ClassifyMicroTriangle<Cfg>(P, it.p0, it.p1, it.p2, true, idx, level) : 0);
+            continue;
+        }
+        bool more = false;
+        uint32_t regAbove = 0, regBelow = 0;
+        Tri st;
+        RasterSetup rs;
+        RasterCursor cur;
+        int fixedState = idx < n ? -1 : 0;
+        if (idx < n) {
+            st = MicroTri(it.p0, it.p1, it.p2, idx, level);
+            int state = ommOpacityState_UnknownOpaque;
+            if (P.useCoarse) {
+                const int cs = CoarseState<Cfg>(P, st);
+                if (cs >= 0) state = cs;
+            }
+            if (state != ommOpacityState_UnknownOpaque) fixedState = state;  // ref: bake_cpu_impl.cpp:861-864
+            else {
+                if (P.cutoff < TexBilinear<Cfg>(P, m, st.p0)) regAbove++;
+                else regBelow++;
+                rs = MakeRasterSetup(st, m.w, m.h, -0.5f);
+                cur = RasterBegin(rs);
+                int fx, fy;
+                more = RasterNext(rs, cur, fx, fy);
+                if (more) {
+                    Coverage c{regAbove, regBelow};
+                    LevelLineCell<Cfg, false>(P, m, st, fx, fy, c);
+                    regAbove = c.above;
+                    regBelow = c.below;
+                }
+            }
+        }
+        q.fixedState[u * 32 + lane] = (int8_t)fixedState;
+        // further covered cells -> queue, one per lane per step; full rounds are drained as soon as they exist
+        while (true) {
+            int ex = 0, ey = 0;
+            if (more && earlyOut && regAbove != 0 && regBelow != 0) more = false;  // state already decided (see ClassifyMicroTriangle)
+            if (more) more = RasterNext(rs, cur, ex, ey);
+            const uint32_t pushMask = __ballot_sync(0xFFFFFFFFu, more);
+            if (pushMask == 0) break;
+            if (more) {
+                const uint32_t e = (head + count + __popc(pushMask & ((1u << lane) - 1u))) & (kQueueCap - 1);
+                q.v0[e] = st.p0; q.v1[e] = st.p1; q.v2[e] = st.p2;
+                q.cx[e] = ex; q.cy[e] = ey;
+                q.slot[e] = (uint32_t)u * 32u + lane;
+            }
+            count += __popc(pushMask);
+            __syncwarp();
+            while (count >= 32) {
+                DrainQueue<Cfg>(P, m, q, head, 32, lane);
+                head = (head + 32) & (kQueueCap - 1);
+                count -= 32;
+            }
+        }
+        if (regAbove) atomicAdd(&q.above[u * 32 + lane], regAbove);
+        if (regBelow) atomicAdd(&q.below[u * 32 + lane], regBelow);
+    }
+    if (count) DrainQueue<Cfg>(P, m, q, head, count, lane);
+    __syncwarp();
+#pragma unroll 1
+    for (int u = 0; u < kBatchUnits; ++u) {
+        const uint32_t item = q.itemOf[u];
+        if (item == kNoItem) continue;
+        const int fixedState = q.fixedState[u * 32 + lane];
+        uint32_t state;
+        if (fixedState >= 0) state = (uint32_t)fixedState;
+        else state = (uint32_t)StateFromCoverage(P, q.above[u * 32 + lane], q.below[u * 32 + lane]);
+        const uint32_t mine = state << (2 * (lane & 15));
+        const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 16 ? mine : 0u);
+        const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, lane >= 16 ? mine : 0u);
+        if (lane == 0) {
+            const uint32_t n = 1u << (2 * items[item].level);
+            uint32_t* dst = stateWords + __ldg(&wordStart[item]) + (q.firstOf[u] >> 4);
+            if (n >= 32) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+            else *dst = lo;
+        }
+    }
+}
+
 typedef void (*ClassifyFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
                            unsigned long long, uint32_t*);
+static bool UseQueueKernel(const BakeParams& P) {
+    return P.filterLinear && !P.disableLevelLine && !P.disableFine && P.tex.mipCount == 1;
+}
 // Picks the compile-time specialisation matching the sampler / texture; every other combination runs the generic kernel.
 static ClassifyFn SelectClassifyKernel(const BakeParams& P) {
     const bool allPow2 = [&] {
@@ -385,6 +544,15 @@ static ClassifyFn SelectClassifyKernel(const BakeParams& P) {
             if (!P.tex.mips[i].isPow2) return false;
         return true;
     }();
+    if (UseQueueKernel(P)) {
+        if (P.tex.isFp32) {
+            if (P.addrMode == ommTextureAddressMode_Wrap && allPow2) return ClassifyKernelQ<KernelCfg<kAddrWrapPow2, true>>;
+            if (P.addrMode == ommTextureAddressMode_Clamp) return ClassifyKernelQ<KernelCfg<kAddrClamp, true>>;
+            return ClassifyKernelQ<KernelCfg<kAddrGeneric, true>>;
+        }
+        if (P.addrMode == ommTextureAddressMode_Wrap && allPow2) return ClassifyKernelQ<KernelCfg<kAddrWrapPow2, false>>;
+        return ClassifyKernelQ<KernelCfg<kAddrGeneric, false>>;
+    }
     if (P.tex.isFp32) {
         if (P.addrMode == ommTextureAddressMode_Wrap && allPow2) return ClassifyKernel<KernelCfg<kAddrWrapPow2, true>>;
         if (P.addrMode == ommTextureAddressMode_Clamp) return ClassifyKernel<KernelCfg<kAddrClamp, true>>;
@@ -1256,13 +1424,14 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         const unsigned long long unitBegin = bounds[rank].unit, unitEnd = bounds[rank + 1].unit;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
         if (itemEnd > itemBegin) {
-            const unsigned long long blocks = (unitEnd - unitBegin + kClassifyWarps - 1) / kClassifyWarps;
+            const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
+            const unsigned long long blocks = (unitEnd - unitBegin + unitsPerBlock - 1) / unitsPerBlock;
             const unsigned long long kMaxGrid = 0x7FFFFFFFull;
             const ClassifyFn classify = SelectClassifyKernel(P);
             for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
                 const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
                 classify<<<(uint32_t)nb, kClassifyWarps * 32, 0, stream>>>(P, items, unitStart, wordStart, itemBegin, itemEnd,
-                                                                          unitBegin + b0 * kClassifyWarps, unitEnd, stateWords);
+                                                                          unitBegin + b0 * unitsPerBlock, unitEnd, stateWords);
                 launches++;
             }
         }

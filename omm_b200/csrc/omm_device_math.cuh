@@ -433,6 +433,33 @@ __device__ __forceinline__ bool RasterTriConservative(const Tri& t, int rw, int 
     return false;
 }
 
+// The same walk as RasterTriConservative, as a resumable iterator: yields the covered cells one at a time in the
+// reference's visiting order (rows bottom-up, each row left to right until the first exit after an entry).
+struct RasterCursor {
+    int x, y;
+    bool wasInside;
+};
+__device__ __forceinline__ RasterCursor RasterBegin(const RasterSetup& r) { return RasterCursor{r.minx, r.miny, false}; }
+__device__ __forceinline__ bool RasterNext(const RasterSetup& r, RasterCursor& c, int& ox, int& oy) {
+    while (c.y < r.maxy) {
+        while (c.x < r.maxx) {
+            if (CellInside(r, c.x, c.y)) {
+                ox = c.x;
+                oy = c.y;
+                c.wasInside = true;
+                ++c.x;
+                return true;
+            }
+            if (c.wasInside) break;
+            ++c.x;
+        }
+        ++c.y;
+        c.x = r.minx;
+        c.wasInside = false;
+    }
+    return false;
+}
+
 // ref: util/cpu_raster.h:486-555 (conservative DDA along a segment)
 template <class F>
 __device__ __forceinline__ bool RasterLineConservative(float2 lp0, float2 lp1, int rw, int rh, float off, F&& f) {
