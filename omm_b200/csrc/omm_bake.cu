@@ -20,6 +20,7 @@
 #include <cmath>
 
 #include "omm_device_math.cuh"
+#include "omm_hier.cuh"
 
 namespace ommb200 {
 
@@ -34,6 +35,7 @@ namespace ommb200 {
     } while (0)
 
 constexpr int kMaxLevel = 12;
+constexpr int kNodeLevels = 6;  // a node of the hierarchical classifier covers at most 4^6 micro-triangles of one work item
 constexpr uint32_t kNoItem = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -285,7 +287,7 @@ __global__ void UvTableResolve(const int8_t* __restrict__ triLevel, const uint64
 __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __restrict__ triLevel, const uint8_t* __restrict__ triFormat,
                            const uint8_t* __restrict__ triDegenerate, const uint32_t* __restrict__ isItem, const uint32_t* __restrict__ itemScan,
                            uint32_t triCount, ItemRec* __restrict__ items, unsigned long long* __restrict__ itemUnits,
-                           unsigned long long* __restrict__ itemWords, uint32_t* __restrict__ levelHist) {
+                           unsigned long long* __restrict__ itemWords, unsigned long long* __restrict__ itemNodes, uint32_t* __restrict__ levelHist) {
     __shared__ uint32_t sh[16];
     if (threadIdx.x < 16) sh[threadIdx.x] = 0;
     __syncthreads();
@@ -309,6 +311,7 @@ __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __res
     const unsigned long long n = 1ull << (2 * it.level);
     itemUnits[w] = n >= 32 ? n / 32 : 1;
     itemWords[w] = n >= 64 ? n / 16 : 4;  // blocks start 16-byte aligned so the warp stores and the pack copies can be vectorised
+    itemNodes[w] = it.level > kNodeLevels ? 1ull << (2 * (it.level - kNodeLevels)) : 1ull;  // see HierClassifyKernel
 }
 
 __global__ void MapTrianglesToItems(const uint32_t* __restrict__ triFirst, const uint32_t* __restrict__ itemScan, uint32_t triCount, uint32_t* __restrict__ triItem) {
@@ -532,9 +535,157 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4, hierarchical variant (Linear filter + level-line test + single mip + no SAT pass: the default configuration).
+//
+// One warp owns a NODE: a sub-triangle of a work item with at most 4^6 micro-triangles (the whole item up to level 6).
+// The warp descends the bird-curve hierarchy breadth-first: regions of 64, 16, 4 and 1 micro-triangles, 32 regions per
+// round, one region per lane.  TestRegion (omm_hier.cuh) proves whole regions to be on one side of the cutoff; failing
+// regions are split through small per-warp work lists in shared memory, and single micro-triangles that still fail get the
+// reference walk (ClassifyMicroTriangle).  States accumulate in a shared-memory block (2 bits per micro-triangle) that is
+// written to HBM once, coalesced.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kHierWarps = 4;
+constexpr int kHierListCap = 64;
+struct HierWarpShared {
+    uint32_t states[256];
+    uint16_t list[4][kHierListCap];  // [0] failing 64-regions, [1] 16-regions, [2] 4-regions, [3] micro-triangles awaiting the reference walk
+};
+
+// write `state` into the micro-triangle range of region `idx` of size 4^e
+__device__ __forceinline__ void HierFill(uint32_t* states, uint32_t e, uint32_t idx, uint32_t state) {
+    if (e == 3) {
+        const uint32_t pat = state * 0x55555555u;
+        *reinterpret_cast<uint4*>(states + 4 * idx) = make_uint4(pat, pat, pat, pat);
+    } else if (e == 2) {
+        states[idx] = state * 0x55555555u;
+    } else if (e == 1) {
+        atomicOr(&states[idx >> 2], (state * 0x55u) << ((idx & 3u) * 8u));
+    } else {
+        atomicOr(&states[idx >> 4], state << ((idx & 15u) * 2u));
+    }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(kHierWarps * 32) HierClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items,
+                                                                     const unsigned long long* __restrict__ nodeStart,
+                                                                     const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
+                                                                     unsigned long long nodeBegin, unsigned long long nodeEnd,
+                                                                     uint32_t* __restrict__ stateWords) {
+    __shared__ __align__(16) HierWarpShared sWarp[kHierWarps];
+    __shared__ uint32_t sFirstItem;
+    const unsigned long long blockNode = nodeBegin + (unsigned long long)blockIdx.x * kHierWarps;
+    if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(nodeStart + itemBegin, itemEnd - itemBegin, blockNode);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long node = blockNode + warp;
+    if (node >= nodeEnd) return;
+    uint32_t w = sFirstItem;
+    while (w + 1 < itemEnd && __ldg(&nodeStart[w + 1]) <= node) ++w;
+    const ItemRec item = items[w];
+    const DevMip& m = P.tex.mips[0];
+    const uint32_t L = item.level;
+    const uint32_t nl = L < (uint32_t)kNodeLevels ? L : (uint32_t)kNodeLevels;        // levels below the node
+    const uint32_t nodeInItem = (uint32_t)(node - __ldg(&nodeStart[w]));               // bird index of the node at level L - nl
+    const uint32_t nMicro = 1u << (2 * nl);
+    HierWarpShared& sh = sWarp[warp];
+    const uint32_t nWords = nMicro >= 16 ? nMicro >> 4 : 1;
+    for (uint32_t i = lane; i < nWords; i += 32) sh.states[i] = 0;
+    __syncwarp();
+
+    const HierItem hi = MakeHierItem(m, item.p0, item.p1, item.p2, L, item.degenerate != 0);
+    const uint32_t sGT = (uint32_t)P.stateGT, sLE = (uint32_t)P.stateLE;
+    uint32_t cnt = 0;  // four warp-uniform list sizes, 8 bits each (each list holds at most 64 entries)
+#define HCNT(i) ((cnt >> (8u * (i))) & 0xFFu)
+    // region of size exponent e, index idx within the node: bird index (nodeInItem << 2(nl-e)) + idx at level L - e
+    const uint32_t e0 = nl < 3 ? nl : 3;
+
+    // test the `active` lanes' regions (size exponent e, node-relative index idx); passing ones are filled, failing ones are pushed
+    auto testAndPush = [&](uint32_t e, uint32_t idx, bool active) {
+        int s = 0;
+        if (active && hi.ok) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
+        if (active && s != 0) HierFill(sh.states, e, idx, s > 0 ? sGT : sLE);
+        const bool fail = active && s == 0;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, fail);
+        const uint32_t li = 3 - e;
+        if (fail) sh.list[li][HCNT(li) + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)idx;
+        cnt += (uint32_t)__popc(mask) << (8u * li);
+        __syncwarp();
+    };
+
+    // initial regions: 4^(nl - e0) of them (64 for a full node: two rounds, at most 64 failures)
+    {
+        const uint32_t nInit = 1u << (2 * (nl - e0));
+        for (uint32_t base = 0; base < nInit; base += 32) testAndPush(e0, base + lane, base + lane < nInit);
+    }
+    // descend: serve the deepest list that can fill a round, else the shallowest non-empty one.  A list grows by at most 32
+    // per round and is served as soon as it holds 8 (regions) / 32 (micro-triangles), so 64 entries are never exceeded.
+    while (cnt != 0) {
+        const uint32_t c0 = HCNT(0), c1 = HCNT(1), c2 = HCNT(2), c3 = HCNT(3);
+        if (c3 >= 32 || (c0 == 0 && c1 == 0 && c2 == 0)) {
+            const uint32_t k = c3 < 32 ? c3 : 32;
+            cnt -= k << 24;
+            if (lane < k) {
+                const uint32_t idx = sh.list[3][c3 - k + lane];
+                const uint32_t st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, item.p0, item.p1, item.p2, item.degenerate != 0, (nodeInItem << (2 * nl)) + idx, L);
+                HierFill(sh.states, 0, idx, st);
+            }
+            __syncwarp();
+            continue;
+        }
+        uint32_t src;
+        if (c2 >= 8 || (c2 > 0 && c0 == 0 && c1 == 0)) src = 2;
+        else if (c1 >= 8 || (c1 > 0 && c0 == 0)) src = 1;
+        else src = 0;  // c0 > 0 here
+        const uint32_t have = HCNT(src);
+        const uint32_t k = have < 8 ? have : 8;
+        cnt -= k << (8u * src);
+        const bool active = (lane >> 2) < k;
+        const uint32_t parent = active ? sh.list[src][have - k + (lane >> 2)] : 0u;
+        __syncwarp();
+        testAndPush(2 - src, parent * 4u + (lane & 3u), active);
+    }
+#undef HCNT
+    __syncwarp();
+    // write the node's state words (item blocks are padded to four words, see BuildItems)
+    uint32_t* dst = stateWords + __ldg(&wordStart[w]) + (unsigned long long)nodeInItem * 256ull;
+    if (nWords >= 4) {
+        for (uint32_t i = lane; i < (nWords >> 2); i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(sh.states)[i];
+    } else if (lane < nWords) {
+        dst[lane] = sh.states[lane];
+    }
+}
+
+typedef void (*HierFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
+                       unsigned long long, uint32_t*);
+// OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
+static int ClassifierOverride() {
+    static const int v = [] {
+        const char* e = getenv("OMM_B200_CLASSIFIER");
+        if (!e) return 0;
+        if (!strcmp(e, "flat")) return 1;
+        if (!strcmp(e, "queue")) return 2;
+        return 0;
+    }();
+    return v;
+}
+static HierFn SelectHierKernel(const BakeParams& P) {
+    if (ClassifierOverride() != 0) return nullptr;
+    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine && !P.useCoarse && P.tex.mipCount == 1)) return nullptr;
+    const bool pow2 = P.tex.mips[0].isPow2 != 0;
+    if (P.tex.isFp32) {
+        if (P.addrMode == ommTextureAddressMode_Wrap && pow2) return HierClassifyKernel<KernelCfg<kAddrWrapPow2, true>>;
+        if (P.addrMode == ommTextureAddressMode_Clamp) return HierClassifyKernel<KernelCfg<kAddrClamp, true>>;
+        return HierClassifyKernel<KernelCfg<kAddrGeneric, true>>;
+    }
+    if (P.addrMode == ommTextureAddressMode_Wrap && pow2) return HierClassifyKernel<KernelCfg<kAddrWrapPow2, false>>;
+    return HierClassifyKernel<KernelCfg<kAddrGeneric, false>>;
+}
 typedef void (*ClassifyFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
                            unsigned long long, uint32_t*);
 static bool UseQueueKernel(const BakeParams& P) {
+    if (ClassifierOverride() == 1) return false;
     return P.filterLinear && !P.disableLevelLine && !P.disableFine && P.tex.mipCount == 1;
 }
 // Picks the compile-time specialisation matching the sampler / texture; every other combination runs the generic kernel.
@@ -1112,7 +1263,7 @@ static NcclApi& Nccl() {
 }
 
 struct ShardBound {
-    unsigned long long unit, word;
+    unsigned long long unit, word, node;
     uint32_t item, pad;
 };
 // First work item of rank r (r = 0..world): items are split where the running unit count crosses r*U/world, so every
@@ -1128,14 +1279,15 @@ __host__ __device__ inline uint32_t ShardFirstItem(const unsigned long long* uni
     }
     return lo;
 }
-__global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart, uint32_t entries, int world,
-                            ShardBound* __restrict__ bounds) {
+__global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart,
+                            const unsigned long long* __restrict__ nodeStart, uint32_t entries, int world, ShardBound* __restrict__ bounds) {
     const int r = threadIdx.x;
     if (r > world) return;
     const uint32_t lo = ShardFirstItem(unitStart, entries, world, r);
     bounds[r].item = lo;
     bounds[r].unit = unitStart[lo];
     bounds[r].word = wordStart[lo];
+    bounds[r].node = nodeStart[lo];
 }
 // host mirror of the partition (same function), exported for the CPU-side multi-rank tests
 ommResult ComputeShardBounds(const unsigned long long* unitStart, uint32_t entries, int world, uint32_t* outFirstItem) {
@@ -1226,7 +1378,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     uint64_t *triKey = nullptr, *tableKeys = nullptr;
     uint32_t *tableVals = nullptr, *triFirst = nullptr, *isItem = nullptr, *itemScan = nullptr, *triItem = nullptr, *triFinal = nullptr;
     ItemRec* items = nullptr;
-    unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr;
+    unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr, *itemNodes = nullptr, *nodeStart = nullptr;
     ShardBound* boundsDev = nullptr;
     uint32_t* stateWords = nullptr;
     uint64_t* digest = nullptr;
@@ -1370,9 +1522,12 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&itemWords, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&unitStart, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&wordStart, (size_t)T + 1));
+        CUDA_TRY(scratch.alloc(&itemNodes, (size_t)T + 1));
+        CUDA_TRY(scratch.alloc(&nodeStart, (size_t)T + 1));
+        CUDA_TRY(cudaMemsetAsync(itemNodes, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
         CUDA_TRY(cudaMemsetAsync(itemUnits, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
         CUDA_TRY(cudaMemsetAsync(itemWords, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
-        BuildItems<<<gridT, TPB, 0, stream>>>(triUV, triLevel, triFormat, triDegenerate, isItem, itemScan, T, items, itemUnits, itemWords, counters + 8);
+        BuildItems<<<gridT, TPB, 0, stream>>>(triUV, triLevel, triFormat, triDegenerate, isItem, itemScan, T, items, itemUnits, itemWords, itemNodes, counters + 8);
         MapTrianglesToItems<<<gridT, TPB, 0, stream>>>(triFirst, itemScan, T, triItem);
         launches += 2;
         {
@@ -1381,9 +1536,11 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemUnits, unitStart, (int)T + 1, stream));
             tmp = cubTempBytes;
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemWords, wordStart, (int)T + 1, stream));
-            launches += 4;
+            tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemNodes, nodeStart, (int)T + 1, stream));
+            launches += 6;
         }
-        ShardBounds<<<1, 96, 0, stream>>>(unitStart, wordStart, T + 1, world, boundsDev);
+        ShardBounds<<<1, 96, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, world, boundsDev);
         launches++;
         CUDA_TRY(cudaMemcpyAsync(countersHost, counters, sizeof(countersHost), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (world + 1), cudaMemcpyDeviceToHost, stream));
@@ -1423,7 +1580,17 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         const uint32_t itemBegin = bounds[rank].item, itemEnd = bounds[rank + 1].item;
         const unsigned long long unitBegin = bounds[rank].unit, unitEnd = bounds[rank + 1].unit;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
-        if (itemEnd > itemBegin) {
+        const HierFn hier = SelectHierKernel(P);
+        if (itemEnd > itemBegin && hier) {
+            const unsigned long long nodeBegin = bounds[rank].node, nodeEnd = bounds[rank + 1].node;
+            const unsigned long long blocks = (nodeEnd - nodeBegin + kHierWarps - 1) / kHierWarps;
+            const unsigned long long kMaxGrid = 0x7FFFFFFFull;
+            for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
+                const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
+                hier<<<(uint32_t)nb, kHierWarps * 32, 0, stream>>>(P, items, nodeStart, wordStart, itemBegin, itemEnd, nodeBegin + b0 * kHierWarps, nodeEnd, stateWords);
+                launches++;
+            }
+        } else if (itemEnd > itemBegin) {
             const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
             const unsigned long long blocks = (unitEnd - unitBegin + unitsPerBlock - 1) / unitsPerBlock;
             const unsigned long long kMaxGrid = 0x7FFFFFFFull;

@@ -7,11 +7,51 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "omm_internal.h"
 
+// Every function of this header compiles for the device AND for the host: the host build (g++ or nvcc's host pass,
+// -ffp-contract=off) is what tests/hier_host_check.cpp links to fuzz the exact shortcuts of omm_hier.cuh against the
+// plain reference walk without a GPU.  It is never part of the product path (the library has no CPU fallback).
+#if defined(__CUDACC__)
+#define OMM_HD __host__ __device__ __forceinline__
+#define OMM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define OMM_HD inline
+#define OMM_HD_NOINLINE inline
+#endif
+
 namespace ommb200 {
+
+OMM_HD float UintAsFloat(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+OMM_HD uint32_t FloatAsUint(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+template <class T>
+OMM_HD T LoadRO(const T* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // ---- bake parameters visible to the kernels ----------------------------------------------------------------------
 struct BakeParams {
@@ -39,14 +79,18 @@ struct Tri {
 constexpr int kTexCoordBorder = 0x7FFFFFFE;  // ref: util/texture.h:22
 
 // (int)float as x86-64 cvttss2si does it: out-of-range and NaN give INT_MIN ("integer indefinite").
-__device__ __forceinline__ int f2i(float f) {
+OMM_HD int f2i(float f) {
+#if defined(__CUDA_ARCH__)
     return (f >= -2147483648.f && f < 2147483648.f) ? __float2int_rz(f) : (int)0x80000000;
+#else
+    return (f >= -2147483648.f && f < 2147483648.f) ? (int)f : (int)0x80000000;
+#endif
 }
-__device__ __forceinline__ float fminStd(float a, float b) { return b < a ? b : a; }  // std::min
-__device__ __forceinline__ float fmaxStd(float a, float b) { return a < b ? b : a; }  // std::max
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+OMM_HD float fminStd(float a, float b) { return b < a ? b : a; }  // std::min
+OMM_HD float fmaxStd(float a, float b) { return a < b ? b : a; }  // std::max
+OMM_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-__device__ __forceinline__ Tri MakeTri(float2 p0, float2 p1, float2 p2) {  // ref: util/geometry.h:63-75
+OMM_HD Tri MakeTri(float2 p0, float2 p1, float2 p2) {  // ref: util/geometry.h:63-75
     Tri t;
     t.p0 = p0; t.p1 = p1; t.p2 = p2;
     t.p0p2 = make_float2(p0.x - p2.x, p0.y - p2.y);
@@ -57,17 +101,21 @@ __device__ __forceinline__ Tri MakeTri(float2 p0, float2 p1, float2 p2) {  // re
     return t;
 }
 
-__device__ __forceinline__ bool TriIsDegenerate(float2 p0, float2 p1, float2 p2) {  // ref: util/geometry.h:44-47
+OMM_HD bool TriIsDegenerate(float2 p0, float2 p1, float2 p2) {  // ref: util/geometry.h:44-47
     const float area = 0.5f * fabsf(p0.x * (p1.y - p2.y) + p1.x * (p2.y - p0.y) + p2.x * (p0.y - p1.y));
     return (double)area < 1e-9;
 }
-__device__ __forceinline__ bool TriIsCCW(float2 p0, float2 p1, float2 p2) {  // ref: util/geometry.h:49-55
+OMM_HD bool TriIsCCW(float2 p0, float2 p1, float2 p2) {  // ref: util/geometry.h:49-55
     const double ax = (double)(p2.x - p0.x), ay = (double)(p2.y - p0.y);
     const double bx = (double)(p1.x - p0.x), by = (double)(p1.y - p0.y);
+#if defined(__CUDA_ARCH__)
     const double nz = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(bx, ay));
+#else
+    const double nz = ax * by - bx * ay;  // both products are exact in double (24-bit x 24-bit significands)
+#endif
     return nz < 0;
 }
-__device__ __forceinline__ bool PointInTri(const Tri& t, float px, float py) {  // ref: util/geometry.h:101-114
+OMM_HD bool PointInTri(const Tri& t, float px, float py) {  // ref: util/geometry.h:101-114
     const float ptp2x = px - t.p2.x, ptp2y = py - t.p2.y;
     const float ptp0x = px - t.p0.x, ptp0y = py - t.p0.y;
     const float s = t.p0p2.x * ptp2y - t.p0p2.y * ptp2x;
@@ -79,7 +127,7 @@ __device__ __forceinline__ bool PointInTri(const Tri& t, float px, float py) {  
 }
 
 // ---- bird curve (ref: util/bird.h:36-118, 170-182) ---------------------------------------------------------------
-__device__ __forceinline__ uint32_t ExtractEvenBits(uint32_t x) {
+OMM_HD uint32_t ExtractEvenBits(uint32_t x) {
     x &= 0x55555555u;
     x = (x | (x >> 1)) & 0x33333333u;
     x = (x | (x >> 2)) & 0x0f0f0f0fu;
@@ -87,12 +135,12 @@ __device__ __forceinline__ uint32_t ExtractEvenBits(uint32_t x) {
     x = (x | (x >> 8)) & 0x0000ffffu;
     return x;
 }
-__device__ __forceinline__ uint32_t PrefixEor(uint32_t x) {
+OMM_HD uint32_t PrefixEor(uint32_t x) {
     x ^= x >> 1; x ^= x >> 2; x ^= x >> 4; x ^= x >> 8;
     return x;
 }
 // Discrete barycentrics of micro-triangle `index`: lattice vertex (iu, iv) of its first corner and orientation.
-__device__ __forceinline__ void Index2DBary(uint32_t index, uint32_t level, uint32_t& iu, uint32_t& iv, bool& upright) {
+OMM_HD void Index2DBary(uint32_t index, uint32_t level, uint32_t& iu, uint32_t& iv, bool& upright) {
     const uint32_t b0 = ExtractEvenBits(index), b1 = ExtractEvenBits(index >> 1);
     const uint32_t fx = PrefixEor(b0), fy = PrefixEor(b0 & ~b1);
     const uint32_t t = fy ^ b1;
@@ -106,18 +154,18 @@ __device__ __forceinline__ void Index2DBary(uint32_t index, uint32_t level, uint
     iu = u; iv = v;
 }
 // ref: util/geometry.h:241-248 -- (p0*b.x + p1*b.y) + p2*b.z with b = (1-u-v, u, v)
-__device__ __forceinline__ float2 InterpUV(float u, float v, float2 p0, float2 p1, float2 p2) {
+OMM_HD float2 InterpUV(float u, float v, float2 p0, float2 p1, float2 p2) {
     const float bx = 1.f - u - v, by = u, bz = v;
     return make_float2(p0.x * bx + p1.x * by + p2.x * bz, p0.y * bx + p1.y * by + p2.y * bz);
 }
-__device__ __forceinline__ Tri MicroTri(float2 p0, float2 p1, float2 p2, uint32_t index, uint32_t level) {
+OMM_HD Tri MicroTri(float2 p0, float2 p1, float2 p2, uint32_t index, uint32_t level) {
     if (level == 0) {
         return MakeTri(InterpUV(0.f, 0.f, p0, p1, p2), InterpUV(1.f, 0.f, p0, p1, p2), InterpUV(0.f, 1.f, p0, p1, p2));
     }
     uint32_t iu, iv;
     bool upright;
     Index2DBary(index, level, iu, iv, upright);
-    const float levelScale = __uint_as_float((127u - level) << 23);
+    const float levelScale = UintAsFloat((127u - level) << 23);
     float du = 1.f * levelScale, dv = 1.f * levelScale;
     const float u = (float)iu * levelScale, v = (float)iv * levelScale;
     if (!upright) { du = -du; dv = -dv; }
@@ -125,13 +173,13 @@ __device__ __forceinline__ Tri MicroTri(float2 p0, float2 p1, float2 p2, uint32_
 }
 
 // ---- texture addressing (ref: util/texture.h:35-91) ----------------------------------------------------------------
-__device__ __forceinline__ int Addr1Generic(int mode, int pow2, int c, int size, int sizeLog2) {
+OMM_HD int Addr1Generic(int mode, int pow2, int c, int size, int sizeLog2) {
     switch (mode) {
     case ommTextureAddressMode_Wrap:
         return pow2 ? (int)((uint32_t)c & (uint32_t)(size - 1)) : (int)((uint32_t)c % (uint32_t)size);
     case ommTextureAddressMode_Mirror:
         if (pow2) {
-            const int a = abs(c) - (c < 0);
+            const int a = (c < 0 ? -c : c) - (c < 0);
             const int flipped = (a >> sizeLog2) & 1;
             const int wrapped = (int)((uint32_t)a & (uint32_t)(size - 1));
             return flipped ? size - wrapped - 1 : wrapped;
@@ -162,31 +210,31 @@ struct KernelCfg {
 };
 
 template <class Cfg>
-__device__ __forceinline__ int Addr1(int mode, int pow2, int c, int size, int sizeLog2) {
+OMM_HD int Addr1(int mode, int pow2, int c, int size, int sizeLog2) {
     if (Cfg::kAddr == kAddrWrapPow2) return (int)((uint32_t)c & (uint32_t)(size - 1));
     if (Cfg::kAddr == kAddrClamp) return clampi(c, 0, size - 1);
     return Addr1Generic(mode, pow2, c, size, sizeLog2);
 }
 
 template <class Cfg>
-__device__ __forceinline__ float TexLoad(const DevTexture& t, const DevMip& m, int x, int y) {  // ref: texture_impl.h:178-202
+OMM_HD float TexLoad(const DevTexture& t, const DevMip& m, int x, int y) {  // ref: texture_impl.h:178-202
     const unsigned long long idx = m.texelOffset + (unsigned long long)((unsigned)x + (unsigned)y * (unsigned)m.w);
-    if (Cfg::kFp32) return __ldg((const float*)t.texels + idx);
-    return (float)__ldg((const uint8_t*)t.texels + idx) * (1.f / 255.f);
+    if (Cfg::kFp32) return LoadRO((const float*)t.texels + idx);
+    return (float)LoadRO((const uint8_t*)t.texels + idx) * (1.f / 255.f);
 }
 // texel (x,y) through address mode + border colour
 template <class Cfg>
-__device__ __forceinline__ float TexFetch(const BakeParams& P, const DevMip& m, int cx, int cy) {
+OMM_HD float TexFetch(const BakeParams& P, const DevMip& m, int cx, int cy) {
     if (Cfg::kAddr == kAddrGeneric && (cx == kTexCoordBorder || cy == kTexCoordBorder)) return P.borderAlpha;
     return TexLoad<Cfg>(P.tex, m, cx, cy);
 }
-__device__ __forceinline__ float GlmLerp(float x, float y, float a) { return x * (1.f - a) + y * a; }
+OMM_HD float GlmLerp(float x, float y, float a) { return x * (1.f - a) + y * a; }
 
 // ref: texture_impl.cpp:261-278 -- run-time bilinear point sample (per-mip pow2 flag).  The SDK reads out of bounds for
 // Border addressing when the footprint leaves the texture; here such texels are borderAlpha (documented deviation on
 // an input the SDK itself cannot process).
 template <class Cfg>
-__device__ __forceinline__ float TexBilinear(const BakeParams& P, const DevMip& m, float2 p) {
+OMM_HD float TexBilinear(const BakeParams& P, const DevMip& m, float2 p) {
     const float px = p.x * (float)m.w - 0.5f, py = p.y * (float)m.h - 0.5f;
     const float fx = floorf(px), fy = floorf(py);
     const int ix = f2i(fx), iy = f2i(fy);
@@ -203,7 +251,7 @@ __device__ __forceinline__ float TexBilinear(const BakeParams& P, const DevMip& 
 }
 
 // ---- coverage -> state (ref: bake_kernels_cpu.h:25-61) -------------------------------------------------------------
-__device__ __forceinline__ int StateFromCoverage(const BakeParams& P, uint32_t above, uint32_t below) {
+OMM_HD int StateFromCoverage(const BakeParams& P, uint32_t above, uint32_t below) {
     if (above != 0 && below != 0) {
         if (P.globalFormat == ommFormat_OC1_4_State) {
             if (P.promotion == ommUnknownStatePromotion_ForceOpaque) return ommOpacityState_UnknownOpaque;
@@ -217,16 +265,16 @@ __device__ __forceinline__ int StateFromCoverage(const BakeParams& P, uint32_t a
     if (above == 0) return P.stateLE;
     return P.stateGT;
 }
-__device__ __forceinline__ bool IsUnknownState(int s) { return s == ommOpacityState_UnknownOpaque || s == ommOpacityState_UnknownTransparent; }
+OMM_HD bool IsUnknownState(int s) { return s == ommOpacityState_UnknownOpaque || s == ommOpacityState_UnknownTransparent; }
 
 // ---- level-line test (ref: bake_kernels_cpu.h:115-238) -------------------------------------------------------------
-__device__ __forceinline__ bool IsZero(float v, float eps) { return v < eps && v > -eps; }
-__device__ __forceinline__ float Len2(float x, float y) { return sqrtf(x * x + y * y); }
-__device__ __forceinline__ bool InUnitSquare(float x, float y) { return x >= 0.f && x <= 1.f && y >= 0.f && y <= 1.f; }
+OMM_HD bool IsZero(float v, float eps) { return v < eps && v > -eps; }
+OMM_HD float Len2(float x, float y) { return sqrtf(x * x + y * y); }
+OMM_HD bool InUnitSquare(float x, float y) { return x >= 0.f && x <= 1.f && y >= 0.f && y <= 1.f; }
 
 // |p - p0| + |p - p1| - |p1 - p0| within 1e-5 (ref: bake_kernels_cpu.h:115-133).  The segment length is only ever used
 // here, so it is computed on demand (the reference computes it eagerly; the value is the same).
-__device__ __forceinline__ bool PointOnEdge(float2 p0, float2 p1, float x, float y) {
+OMM_HD bool PointOnEdge(float2 p0, float2 p1, float x, float y) {
     const float length = Len2(p1.x - p0.x, p1.y - p0.y);
     const float l = Len2(x - p0.x, y - p0.y) + Len2(x - p1.x, y - p1.y) - length;
     return IsZero(l, 1e-5f);
@@ -238,7 +286,7 @@ __device__ __forceinline__ bool PointOnEdge(float2 p0, float2 p1, float x, float
 //   * x >= 0 fails when n and c0 have strictly opposite signs, except when the quotient underflows to -0 (which compares
 //     >= 0): that needs |n| <= 2^-150 |c0|, excluded here by requiring |n| > 2^-100.
 // "true" means "cannot be decided cheaply or is inside": the caller then evaluates the reference expression itself.
-__device__ __forceinline__ bool QuotientMayBeInUnitRange(float n, float c0) {
+OMM_HD bool QuotientMayBeInUnitRange(float n, float c0) {
     const bool le1 = c0 > 0.f ? (n <= c0) : (n >= c0);
     if (!le1) return false;                       // also rejects NaN numerators, like the reference's (x <= 1.f)
     const bool oppositeSigns = (n > 0.f && c0 < 0.f) || (n < 0.f && c0 > 0.f);
@@ -247,7 +295,7 @@ __device__ __forceinline__ bool QuotientMayBeInUnitRange(float n, float c0) {
 }
 
 // h = (a - cutoff, b, c, d); locals named as in the reference (ref: bake_kernels_cpu.h:144-238).
-__device__ __noinline__ bool EdgeHyperbola(float2 p0, float2 p1, float hx, float hy, float hz, float hw) {
+OMM_HD_NOINLINE bool EdgeHyperbola(float2 p0, float2 p1, float hx, float hy, float hz, float hw) {
     if (p0.x > p1.x) { const float2 t = p0; p0 = p1; p1 = t; }
     const float a = hx, b = hy, c = hz, d = hw;
     const float k_denum = p1.x - p0.x;
@@ -301,7 +349,7 @@ struct Coverage {
 
 // ref: bake_kernels_cpu.h:241-399.  `tri` is the micro-triangle in UV space (original winding).
 template <class Cfg, bool kDegenerate>
-__device__ __forceinline__ void LevelLineCell(const BakeParams& P, const DevMip& m, const Tri& tri, int px, int py, Coverage& cov) {
+OMM_HD void LevelLineCell(const BakeParams& P, const DevMip& m, const Tri& tri, int px, int py, Coverage& cov) {
     const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
     const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
     const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
@@ -350,7 +398,7 @@ __device__ __forceinline__ void LevelLineCell(const BakeParams& P, const DevMip&
 
 // ref: bake_kernels_cpu.h:404-452 (only reachable through internal flag bits 7/8)
 template <class Cfg>
-__device__ __forceinline__ void ConservativeBilinearCell(const BakeParams& P, const DevMip& m, int px, int py, Coverage& cov) {
+OMM_HD void ConservativeBilinearCell(const BakeParams& P, const DevMip& m, int px, int py, Coverage& cov) {
     const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
     const int ix = f2i(pfx), iy = f2i(pfy);
     const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, ix, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, iy, m.h, m.log2h);
@@ -363,7 +411,7 @@ __device__ __forceinline__ void ConservativeBilinearCell(const BakeParams& P, co
 }
 // ref: bake_cpu_impl.cpp:994-1009
 template <class Cfg>
-__device__ __forceinline__ void NearestCell(const BakeParams& P, const DevMip& m, int px, int py, Coverage& cov) {
+OMM_HD void NearestCell(const BakeParams& P, const DevMip& m, int px, int py, Coverage& cov) {
     const int cx = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), cy = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
     const float alpha = TexFetch<Cfg>(P, m, cx, cy);
     if (P.cutoff < alpha) cov.above += 1;
@@ -374,14 +422,14 @@ __device__ __forceinline__ void NearestCell(const BakeParams& P, const DevMip& m
 struct EdgeFn {
     float nx, ny, c;
 };
-__device__ __forceinline__ EdgeFn MakeEdgeFn(float2 p, float2 q) {  // ref: util/cpu_raster.h:26-29
+OMM_HD EdgeFn MakeEdgeFn(float2 p, float2 q) {  // ref: util/cpu_raster.h:26-29
     EdgeFn e;
     e.nx = q.y - p.y;
     e.ny = p.x - q.x;
     e.c = -(e.nx * p.x + e.ny * p.y);
     return e;
 }
-__device__ __forceinline__ float EvalEdgeCons(const EdgeFn& e, float sx, float sy) {  // ref: util/cpu_raster.h:46-51, ext=(1,1)
+OMM_HD float EvalEdgeCons(const EdgeFn& e, float sx, float sy) {  // ref: util/cpu_raster.h:46-51, ext=(1,1)
     const float ev = (e.nx * sx + e.ny * sy) + e.c;
     const float bx = e.nx > 0 ? 0.f : e.nx;
     const float by = e.ny > 0 ? 0.f : e.ny;
@@ -393,7 +441,7 @@ struct RasterSetup {
     EdgeFn e0, e1, e2;
     int minx, miny, maxx, maxy;
 };
-__device__ __forceinline__ RasterSetup MakeRasterSetup(const Tri& t_, int rw, int rh, float off) {
+OMM_HD RasterSetup MakeRasterSetup(const Tri& t_, int rw, int rh, float off) {
     const bool ccw = TriIsCCW(t_.p0, t_.p1, t_.p2);
     const float rfx = (float)rw, rfy = (float)rh;
     const float2 a = make_float2(t_.p0.x * rfx + off, t_.p0.y * rfy + off);
@@ -410,7 +458,7 @@ __device__ __forceinline__ RasterSetup MakeRasterSetup(const Tri& t_, int rw, in
     r.e2 = MakeEdgeFn(q2, q0);
     return r;
 }
-__device__ __forceinline__ bool CellInside(const RasterSetup& r, int x, int y) {
+OMM_HD bool CellInside(const RasterSetup& r, int x, int y) {
     const float sx = (float)x, sy = (float)y;
     return EvalEdgeCons(r.e0, sx, sy) < 0.f && EvalEdgeCons(r.e1, sx, sy) < 0.f && EvalEdgeCons(r.e2, sx, sy) < 0.f;
 }
@@ -418,7 +466,7 @@ __device__ __forceinline__ bool CellInside(const RasterSetup& r, int x, int y) {
 // Serial over-conservative raster with the reference's row scan ("stop the row at the first exit after an entry").
 // f(x, y) returns true to abort the whole raster (used for the exact early-out, see ClassifyMicroTriangle).
 template <class F>
-__device__ __forceinline__ bool RasterTriConservative(const Tri& t, int rw, int rh, float off, F&& f) {
+OMM_HD bool RasterTriConservative(const Tri& t, int rw, int rh, float off, F&& f) {
     const RasterSetup r = MakeRasterSetup(t, rw, rh, off);
     for (int y = r.miny; y < r.maxy; ++y) {
         bool wasInside = false;
@@ -439,8 +487,8 @@ struct RasterCursor {
     int x, y;
     bool wasInside;
 };
-__device__ __forceinline__ RasterCursor RasterBegin(const RasterSetup& r) { return RasterCursor{r.minx, r.miny, false}; }
-__device__ __forceinline__ bool RasterNext(const RasterSetup& r, RasterCursor& c, int& ox, int& oy) {
+OMM_HD RasterCursor RasterBegin(const RasterSetup& r) { return RasterCursor{r.minx, r.miny, false}; }
+OMM_HD bool RasterNext(const RasterSetup& r, RasterCursor& c, int& ox, int& oy) {
     while (c.y < r.maxy) {
         while (c.x < r.maxx) {
             if (CellInside(r, c.x, c.y)) {
@@ -462,7 +510,7 @@ __device__ __forceinline__ bool RasterNext(const RasterSetup& r, RasterCursor& c
 
 // ref: util/cpu_raster.h:486-555 (conservative DDA along a segment)
 template <class F>
-__device__ __forceinline__ bool RasterLineConservative(float2 lp0, float2 lp1, int rw, int rh, float off, F&& f) {
+OMM_HD bool RasterLineConservative(float2 lp0, float2 lp1, int rw, int rh, float off, F&& f) {
     const float rfx = (float)rw, rfy = (float)rh;
     float2 p0 = make_float2(lp0.x * rfx + off, lp0.y * rfy + off);
     float2 p1 = make_float2(lp1.x * rfx + off, lp1.y * rfy + off);
@@ -471,7 +519,7 @@ __device__ __forceinline__ bool RasterLineConservative(float2 lp0, float2 lp1, i
     int x = f2i(floorf(p0.x)), y = f2i(floorf(p0.y));
     const int stepX = (dx > 0) ? 1 : ((dx < 0) ? -1 : 0);
     const int stepY = (dy > 0) ? 1 : ((dy < 0) ? -1 : 0);
-    const float inf = __int_as_float(0x7f800000);
+    const float inf = UintAsFloat(0x7f800000u);
     const float tDeltaX = (stepX != 0) ? 1.f / fabsf(dx) : inf;
     const float tDeltaY = (stepY != 0) ? 1.f / fabsf(dy) : inf;
     float tMaxX = inf, tMaxY = inf;
@@ -491,7 +539,7 @@ __device__ __forceinline__ bool RasterLineConservative(float2 lp0, float2 lp1, i
 // ---- coarse SAT classification of one micro-triangle (ref: bake_cpu_impl.cpp:749-801) ----------------------------
 // returns -1 when the coarse pass leaves the micro-triangle untouched, else the state it sets.
 template <class Cfg>
-__device__ __forceinline__ int CoarseState(const BakeParams& P, const Tri& st) {
+OMM_HD int CoarseState(const BakeParams& P, const Tri& st) {
     const DevMip& m = P.tex.mips[0];
     if (f2i(st.aabb_s.x) != f2i(st.aabb_e.x) || f2i(st.aabb_s.y) != f2i(st.aabb_e.y)) return -1;
     const float fsx = st.aabb_s.x * (float)m.w - 0.5f, fsy = st.aabb_s.y * (float)m.h - 0.5f;
@@ -506,10 +554,10 @@ __device__ __forceinline__ int CoarseState(const BakeParams& P, const Tri& st) {
     const uint32_t area = (uint32_t)((ex - sx + 1) * (ey - sy + 1));
     const uint32_t* sat = P.tex.sat + m.satOffset;
     const int sx1 = sx - 1, sy1 = sy - 1;  // ref: texture_impl.h:108-125
-    const uint32_t A = (sx1 >= 0 && sy1 >= 0) ? __ldg(sat + sx1 + (size_t)sy1 * m.w) : 0;
-    const uint32_t B = (sy1 >= 0) ? __ldg(sat + ex + (size_t)sy1 * m.w) : 0;
-    const uint32_t C = (sx1 >= 0) ? __ldg(sat + sx1 + (size_t)ey * m.w) : 0;
-    const uint32_t D = __ldg(sat + ex + (size_t)ey * m.w);
+    const uint32_t A = (sx1 >= 0 && sy1 >= 0) ? LoadRO(sat + sx1 + (size_t)sy1 * m.w) : 0;
+    const uint32_t B = (sy1 >= 0) ? LoadRO(sat + ex + (size_t)sy1 * m.w) : 0;
+    const uint32_t C = (sx1 >= 0) ? LoadRO(sat + sx1 + (size_t)ey * m.w) : 0;
+    const uint32_t D = LoadRO(sat + ex + (size_t)ey * m.w);
     const uint32_t sa = D + A - B - C;
     if (sa == 0) return P.stateLE;
     if (sa == area) return P.stateGT;
@@ -521,7 +569,7 @@ __device__ __forceinline__ int CoarseState(const BakeParams& P, const Tri& st) {
 // non-zero (bake_kernels_cpu.h:27-50), counters never decrease, and every later mip only adds to them, so the walk can
 // stop the moment both are non-zero.  Under Nearest promotion the counts matter and the full walk is done.
 template <class Cfg>
-__device__ __forceinline__ int ClassifyMicroTriangle(const BakeParams& P, float2 b0, float2 b1, float2 b2, bool baseDegenerate, uint32_t index,
+OMM_HD int ClassifyMicroTriangle(const BakeParams& P, float2 b0, float2 b1, float2 b2, bool baseDegenerate, uint32_t index,
                                                     uint32_t level) {
     const Tri st = MicroTri(b0, b1, b2, index, level);
     int state = ommOpacityState_UnknownOpaque;

@@ -1,0 +1,226 @@
+// omm_hier.cuh -- exact hierarchical shortcuts for the Linear / level-line classifier (default configuration).
+//
+// The reference decides the state of a micro-triangle t from three kinds of evidence (ref: bake_cpu_impl.cpp:861-908,
+// bake_kernels_cpu.h:241-399):   (1) the bilinear sample at t.p0,   (2) the texel centres that lie inside t,
+// (3) intersections of t's edges with the level line  alpha = cutoff  inside every bilinear cell the conservative raster
+// visits.  A REGION is a sub-triangle of the bird curve (4^e consecutive micro-triangles, e = 0 is one micro-triangle).
+// TestRegion() below proves, for a whole region at once, that all three kinds of evidence can only ever vote for ONE side
+// s of the cutoff; then every micro-triangle of the region ends with coverage (s-counter > 0, other counter == 0) and its
+// state is stateGT / stateLE whatever the promotion mode.  When the proof does not go through the region is split, and
+// single micro-triangles that still fail are evaluated by the reference walk (ClassifyMicroTriangle).  The shortcut never
+// changes a result: it only skips arithmetic whose outcome is known.
+//
+// Notation.  u = 2^-24 (unit round-off), W x H = texture size.  "r-space" = texel space after the raster offset:
+// r(p) = fl(fl(p.x*W) - 0.5) -- the very expression of the rasterizer (cpu_raster.h:287-291) and of the bilinear sampler
+// (texture_impl.cpp:263).  Cell (cx, cy) has its corners on the texel centres; cell-local coordinates are q = r - (cx, cy)
+// (the kernel computes fl(fl(W*p.x) - (cx + 0.5)), bake_kernels_cpu.h:356-358), so the cell is [0,1]^2 and the bilinear
+// patch is  h(x,y) = a' + b x + c y + d x y  with the float coefficients of bake_kernels_cpu.h:330-340 (a' = a - cutoff).
+//
+// (A) Enclosure.  Every lattice vertex of the region is a convex combination of the region's three corner vertices in real
+//     arithmetic; the float evaluation of InterpolateTriangleUV (3 products, 2 sums) is off by <= 3.01 u Pmax, the products
+//     with W and the offsets add <= 2 u (W Pmax + 1).  With eps = 16 u (max(W,H) Pmax + 2) every vertex of every
+//     micro-triangle of the region has r within [lo, hi] = [min corner r - eps, max corner r + eps] (for a single
+//     micro-triangle the corners ARE the vertices and eps = 4 u (...) only covers r-versus-q rounding).
+//     Footprint F = cells floor(lo) .. floor(hi): a superset of the raster's cells [floor(min r), ceil(max r) - 1] and of the
+//     cell floor(r(p0)) of the bilinear sample.
+// (B) Edge test.  TestEdgeHyperbolaIntersection returns true only with a point (x^, y^) that passed InUnitSquare and
+//     PointOnEdge.  PointOnEdge bounds |p-p0| + |p-p1| by L + 1e-5 (+ rounding), an ellipse that stays within
+//     delta = sqrt(e(2L+e))/2 + e, e = 1.001e-5 + 16 u L, of the segment; hence (x^, y^) lies in
+//     B = [lo - c - delta, hi - c + delta] intersected with [0,1]^2.  Backward error analysis of the three branches
+//     (vertical / linear / quadratic, bake_kernels_cpu.h:157-236) gives |h(x^, y^)| <= R with
+//        R = 4.01e-6 + 16 u T + 32 u (Gmax + |cutoff|) + 2.1 u max_K (c K + d M(K) + b)^2 / (d K),
+//        T = |a'| + |b| + (|c| + |d|)(K + M + 1),   K = |k^| (edge slope),  M = |m^| <= Qy + Qx K,  Q = max |q|,
+//     where the last term is only present when |d K| can reach 1e-6 (the quadratic branch) and K ranges over the slopes
+//     the region's edges can have (three direction classes per work item, see MakeHierItem; the function of K is convex, so
+//     the maximum is at an end of the range).  A bilinear function attains its extrema over the rectangle B at B's corners,
+//     so  min over B's corners of s h > R  proves that no edge of the region can report an intersection in this cell.
+//     The 3e-6 inside the constant also settles the "flat patch" branch (|b|,|c|,|d| < 1e-6 => sign(a') = s), and the
+//     32 u (Gmax + |cutoff|) term the difference between h and the sampler's lerp form, so the bilinear sample at p0, whose
+//     (wx, wy) lies in the B of its cell, votes s as well.
+// (C) Texel centres.  A cell corner whose texel is on side s can only vote s.  A corner on the other side must be provably
+//     outside every micro-triangle of the region as PointInTriangle evaluates it: each of its three edge functions is
+//     computed with relative error <= 4.1 u of |e||P - A|, the three real values sum to twice the area, and for a point at
+//     distance rho from the triangle the most negative one is >= kappa^2 emax rho / 2 (kappa = 2 Area / emax^2); so
+//     rho >= 5 * 4.1 u / kappa^2 * diam makes two of them reliably opposite in sign, which makes the function return false
+//     whatever the third one does.  In r-space: the corner is separated from [lo, hi] by pit = rho W + eps in x or y.
+//
+// Everything here compiles for host and device (see omm_device_math.cuh); tests/hier_host_check.cpp fuzzes TestRegion
+// against the reference walk on the CPU, the GPU parity suite does the same through the library.
+#pragma once
+
+#include "omm_device_math.cuh"
+
+namespace ommb200 {
+
+constexpr float kUnitRoundoff = 5.9604645e-8f;  // 2^-24
+constexpr int kHierMaxCells = 16;               // a region whose footprint is larger is split instead
+
+struct HierItem {
+    float2 p0, p1, p2;
+    uint32_t level;
+    float epsRegion, epsSingle;  // r-space enclosure slack (A)
+    float deltaEdge;             // PointOnEdge pad (B)
+    float kmin[3], kmax[3];      // slope range of the three edge direction classes (B)
+    float pitX, pitY;            // r-space separation that makes PointInTriangle provably false (C); +inf = unavailable
+    int ok;                      // shortcuts applicable to this work item at all
+};
+
+OMM_HD float UlpOf(float x) {  // x >= 2^-100
+    return UintAsFloat((FloatAsUint(x) & 0x7F800000u) - (23u << 23));
+}
+
+OMM_HD HierItem MakeHierItem(const DevMip& m, float2 p0, float2 p1, float2 p2, uint32_t level, bool degenerate) {
+    const float u = kUnitRoundoff;
+    const float inf = UintAsFloat(0x7f800000u);
+    HierItem it;
+    it.p0 = p0; it.p1 = p1; it.p2 = p2;
+    it.level = level;
+    const float W = (float)m.w, H = (float)m.h;
+    const float S = W > H ? W : H;
+    const float Pmax = fmaxf(fmaxf(fmaxf(fabsf(p0.x), fabsf(p0.y)), fmaxf(fabsf(p1.x), fabsf(p1.y))), fmaxf(fabsf(p2.x), fabsf(p2.y)));
+    const float ext = S * Pmax;
+    it.ok = !degenerate && (ext < 1048576.f);  // NaN / Inf coordinates fail the comparison
+    it.epsSingle = 4.f * u * (ext + 2.f);
+    it.epsRegion = 16.f * u * (ext + 2.f);
+    const float scale = UintAsFloat((127u - level) << 23);
+    const float2 e[3] = {make_float2(p1.x - p0.x, p1.y - p0.y), make_float2(p2.x - p0.x, p2.y - p0.y), make_float2(p2.x - p1.x, p2.y - p1.y)};
+    float gmax = 0.f, lmax = 0.f, emax2 = 0.f, emin2 = inf;
+    float ax[3], ay[3];
+    for (int j = 0; j < 3; ++j) {
+        ax[j] = fabsf(W * e[j].x * scale);
+        ay[j] = fabsf(H * e[j].y * scale);
+        gmax = fmaxf(gmax, fmaxf(ax[j], ay[j]));
+        lmax = fmaxf(lmax, sqrtf(ax[j] * ax[j] + ay[j] * ay[j]));
+        const float l2 = e[j].x * e[j].x + e[j].y * e[j].y;
+        emax2 = fmaxf(emax2, l2);
+        emin2 = fminf(emin2, l2);
+    }
+    const float eta = it.epsRegion * 1.01f + 8.f * u * gmax;  // |computed edge component - ideal| (two vertices, float g)
+    const float Lmax = lmax * (1.f + 8.f * u) + 2.f * eta;
+    const float epsEff = 1.001e-5f + 16.f * u * Lmax;
+    it.deltaEdge = (0.5f * sqrtf(epsEff * (2.f * Lmax + epsEff)) + epsEff) * 1.01f;
+    // Floats of magnitude >= 16 are multiples of tau = ulp >= 2^-19 > 1e-6 and their differences with the cell centre and
+    // with each other are exact (Sterbenz), so a non-zero k_denum of a steep edge is at least tau.
+    const float x0 = W * p0.x, x1 = W * p1.x, x2 = W * p2.x;
+    const float xlo = fminf(fminf(x0, x1), x2), xhi = fmaxf(fmaxf(x0, x1), x2);
+    const float amin = (xlo > 0.f ? xlo : (xhi < 0.f ? -xhi : 0.f)) - 2.f;
+    const float tau = amin >= 16.f ? UlpOf(amin) : 0.f;
+    for (int j = 0; j < 3; ++j) {
+        const float lowNum = ay[j] - eta;
+        it.kmin[j] = (lowNum > 0.f ? lowNum : 0.f) / (ax[j] + eta) * (1.f - 8.f * u);
+        if (ax[j] > 2.f * eta) it.kmax[j] = (ay[j] + eta) / (ax[j] - eta) * (1.f + 8.f * u);
+        else it.kmax[j] = (ay[j] + eta) / fmaxf(9.9e-7f, tau) * (1.f + 8.f * u);
+    }
+    // (C): shape factor of the base triangle; micro-triangles are similar to it up to the vertex rounding `pr`
+    it.pitX = it.pitY = inf;
+    const float area2 = fabsf(e[0].x * e[1].y - e[0].y * e[1].x);
+    const float kappa = area2 / emax2;
+    const float eminT = sqrtf(emin2) * scale;
+    const float pr = (6.02f * u * Pmax) / eminT;
+    if (kappa >= 0.01f && pr <= kappa * 0.0625f) {
+        const float kEff = 0.7f * kappa;
+        const float rho0 = (5.f * 4.1f * u / (kEff * kEff)) * sqrtf(emax2) * scale * (1.f + pr) * 1.01f;
+        it.pitX = rho0 * W + it.epsRegion;
+        it.pitY = rho0 * H + it.epsRegion;
+    }
+    if (!(kappa >= 0.f)) it.ok = 0;  // NaN guard
+    return it;
+}
+
+// Upper bound test of (B): returns true when `margin` (= min over B's corners of s*h, as computed in float) provably
+// exceeds R for every edge slope the work item can have.  al..de = |a'|,|b|,|c|,|d|; qx,qy = max |cell-local coordinate|.
+OMM_HD bool MarginBeatsEdgeBound(const HierItem& it, float margin, float al, float be, float ga, float de, float gmaxAbs, float cutoffAbs, float qx,
+                                 float qy) {
+    const float u = kUnitRoundoff;
+    float kAll = fmaxf(fmaxf(it.kmax[0], it.kmax[1]), it.kmax[2]);
+    const float mAll = (qy + qx * kAll) * (1.f + 4.f * u);
+    const float T = al + be + (ga + de) * (kAll + mAll + 1.f);
+    const float lin = 4.01e-6f + 16.f * u * T + 32.f * u * (gmaxAbs + cutoffAbs);
+    const float rem = margin - lin;
+    if (!(rem > 0.f)) return false;
+    // quadratic branch: needs |d k| >= 1e-6.  2.1 u (ga K + de M(K) + be)^2 <= rem * de * K (1 - 4u)  at both ends of the range
+    const float k0 = 9.9e-7f / (de * (1.f + 4.f * u));  // +inf when d == 0: no quadratic branch
+    bool ok = true;
+    for (int j = 0; j < 3; ++j) {
+        const float klo = fmaxf(it.kmin[j], k0), khi = it.kmax[j];
+        if (!(klo <= khi)) continue;
+        const float c1lo = (ga * klo + de * (qy + qx * klo) + be) * (1.f + 8.f * u);
+        const float c1hi = (ga * khi + de * (qy + qx * khi) + be) * (1.f + 8.f * u);
+        ok = ok && (2.1f * u * c1lo * c1lo < rem * (de * klo * (1.f - 8.f * u)));
+        ok = ok && (2.1f * u * c1hi * c1hi < rem * (de * khi * (1.f - 8.f * u)));
+    }
+    return ok;
+}
+
+// Returns +1 / -1 when every micro-triangle of the region (bird index `index` at subdivision level `regionLevel` of the
+// work item; regionLevel == it.level means a single micro-triangle) is provably on that side of the cutoff, 0 otherwise.
+template <class Cfg>
+OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, uint32_t regionLevel) {
+    const Tri rt = MicroTri(it.p0, it.p1, it.p2, index, regionLevel);
+    const float W = (float)m.w, H = (float)m.h;
+    const float eps = regionLevel == it.level ? it.epsSingle : it.epsRegion;
+    const float r0x = rt.p0.x * W + -0.5f, r0y = rt.p0.y * H + -0.5f;
+    const float r1x = rt.p1.x * W + -0.5f, r1y = rt.p1.y * H + -0.5f;
+    const float r2x = rt.p2.x * W + -0.5f, r2y = rt.p2.y * H + -0.5f;
+    const float lox = fminf(fminf(r0x, r1x), r2x) - eps, loy = fminf(fminf(r0y, r1y), r2y) - eps;
+    const float hix = fmaxf(fmaxf(r0x, r1x), r2x) + eps, hiy = fmaxf(fmaxf(r0y, r1y), r2y) + eps;
+    if (!(lox > -2097152.f && loy > -2097152.f && hix < 2097152.f && hiy < 2097152.f)) return 0;
+    const int cx0 = (int)floorf(lox), cy0 = (int)floorf(loy), cx1 = (int)floorf(hix), cy1 = (int)floorf(hiy);
+    if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kHierMaxCells) return 0;
+    const float delta = it.deltaEdge;
+    const float cutoffAbs = fabsf(P.cutoff);
+    int sAll = 0;
+    for (int cy = cy0; cy <= cy1; ++cy) {
+        const int y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy, m.h, m.log2h), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy + 1, m.h, m.log2h);
+        const float fy = (float)cy;
+        const float by0 = fmaxf(0.f, loy - fy - delta), by1 = fminf(1.f, hiy - fy + delta);
+        const float qy = fmaxf(fabsf(loy - fy), fabsf(hiy - fy)) + delta;
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx, m.w, m.log2w), x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx + 1, m.w, m.log2w);
+            // (c00, c01, c11, c10) as the reference gathers them
+            const float gx = TexFetch<Cfg>(P, m, x0, y0);
+            const float gy = TexFetch<Cfg>(P, m, x0, y1);
+            const float gz = TexFetch<Cfg>(P, m, x1, y1);
+            const float gw = TexFetch<Cfg>(P, m, x1, y0);
+            const float a = gx - P.cutoff;
+            const float b = gw - gx;
+            const float c = gy - gx;
+            const float d = gx + gz - gy - gw;
+            const float fx = (float)cx;
+            const float bx0 = fmaxf(0.f, lox - fx - delta), bx1 = fminf(1.f, hix - fx + delta);
+            const float qx = fmaxf(fabsf(lox - fx), fabsf(hix - fx)) + delta;
+            // h at the four corners of B
+            const float e0 = a + b * bx0, e1 = a + b * bx1;
+            const float f0 = c + d * bx0, f1 = c + d * bx1;
+            const float h00 = e0 + f0 * by0, h01 = e0 + f0 * by1, h10 = e1 + f1 * by0, h11 = e1 + f1 * by1;
+            const float mn = fminf(fminf(h00, h01), fminf(h10, h11)), mx = fmaxf(fmaxf(h00, h01), fmaxf(h10, h11));
+            int s;
+            float margin;
+            if (mn > 0.f) { s = 1; margin = mn; }
+            else if (mx < 0.f) { s = -1; margin = -mx; }
+            else return 0;
+            if (sAll != 0 && sAll != s) return 0;
+            sAll = s;
+            // (C) texel centres on the other side must be out of reach of PointInTriangle
+            const bool want = s > 0;
+            const bool o0 = P.cutoff < gx, o1 = P.cutoff < gy, o2 = P.cutoff < gz, o3 = P.cutoff < gw;
+            if (o0 != want || o1 != want || o2 != want || o3 != want) {
+                const bool farL = lox - fx >= it.pitX;             // corners with local x = 0 are left of the region
+                const bool farR = (fx + 1.f) - hix >= it.pitX;     // corners with local x = 1 are right of it
+                const bool farB = loy - fy >= it.pitY;
+                const bool farT = (fy + 1.f) - hiy >= it.pitY;
+                // corner 0 = (0,0), 1 = (0,1), 2 = (1,1), 3 = (1,0); a corner at local x = 1 is also "left of the region" when the
+                // region starts beyond it, i.e. lox - (fx + 1) >= pit, which implies farL; the four flags below are the cheap subset.
+                if (o0 != want && !(farL || farB)) return 0;
+                if (o1 != want && !(farL || farT)) return 0;
+                if (o2 != want && !(farR || farT)) return 0;
+                if (o3 != want && !(farR || farB)) return 0;
+            }
+            const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
+            if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, cutoffAbs, qx, qy)) return 0;
+        }
+    }
+    return sAll;
+}
+
+}  // namespace ommb200

@@ -1,0 +1,105 @@
+// hier_host_check.cpp -- TEST INFRASTRUCTURE.  Host build (g++, -ffp-contract=off) of the classifier arithmetic in
+// omm_b200/csrc/omm_device_math.cuh + omm_hier.cuh.  For one work item it runs the hierarchical descent of
+// HierClassifyKernel serially and compares every micro-triangle's state with the plain reference walk
+// (ClassifyMicroTriangle, itself parity-tested against the SDK build on the GPU).  Used by tests/test_hier_host.py to fuzz
+// the exact shortcuts (TestRegion) without a GPU.  Never linked into libomm-b200.so.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../omm_b200/csrc/omm_hier.cuh"
+
+using namespace ommb200;
+
+struct HierCheckStats {
+    uint64_t microTriangles;
+    uint64_t mismatches;
+    uint64_t tests[4];   // region tests at size exponent 3,2,1,0
+    uint64_t passes[4];
+    uint64_t fullEvals;
+    uint64_t firstBadItem, firstBadIndex;
+    int32_t firstBadGot, firstBadWant;
+};
+
+template <class Cfg>
+static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, uint32_t nodeInItem, uint32_t nl, uint32_t e, uint32_t idx, uint8_t* states,
+                    HierCheckStats* st, const float2* uv, bool degenerate) {
+    const uint32_t L = hi.level;
+    int s = 0;
+    st->tests[3 - e]++;
+    if (hi.ok) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
+    if (s != 0) {
+        st->passes[3 - e]++;
+        const uint32_t n = 1u << (2 * e);
+        for (uint32_t i = 0; i < n; ++i) states[idx * n + i] = (uint8_t)(s > 0 ? P.stateGT : P.stateLE);
+        return;
+    }
+    if (e == 0) {
+        st->fullEvals++;
+        states[idx] = (uint8_t)ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, (nodeInItem << (2 * nl)) + idx, L);
+        return;
+    }
+    for (uint32_t k = 0; k < 4; ++k) Descend<Cfg>(P, m, hi, nodeInItem, nl, e - 1, idx * 4 + k, states, st, uv, degenerate);
+}
+
+template <class Cfg>
+static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* levels, uint32_t numItems, HierCheckStats* st) {
+    const DevMip& m = P.tex.mips[0];
+    std::vector<uint8_t> states(4096);
+    for (uint32_t it = 0; it < numItems; ++it) {
+        const float2 uv[3] = {make_float2(uvs[6 * it], uvs[6 * it + 1]), make_float2(uvs[6 * it + 2], uvs[6 * it + 3]), make_float2(uvs[6 * it + 4], uvs[6 * it + 5])};
+        const uint32_t L = levels[it];
+        const bool degenerate = TriIsDegenerate(uv[0], uv[1], uv[2]);
+        const HierItem hi = MakeHierItem(m, uv[0], uv[1], uv[2], L, degenerate);
+        const uint32_t nl = L < 6 ? L : 6;
+        const uint32_t nodes = L > 6 ? 1u << (2 * (L - 6)) : 1u;
+        const uint32_t e0 = nl < 3 ? nl : 3;
+        for (uint32_t node = 0; node < nodes; ++node) {
+            const uint32_t nInit = 1u << (2 * (nl - e0));
+            for (uint32_t r = 0; r < nInit; ++r) Descend<Cfg>(P, m, hi, node, nl, e0, r, states.data(), st, uv, degenerate);
+            const uint32_t n = 1u << (2 * nl);
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t index = (node << (2 * nl)) + i;
+                const int want = ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L);
+                st->microTriangles++;
+                if (want != (int)states[i]) {
+                    if (st->mismatches == 0) {
+                        st->firstBadItem = it;
+                        st->firstBadIndex = index;
+                        st->firstBadGot = states[i];
+                        st->firstBadWant = want;
+                    }
+                    st->mismatches++;
+                }
+            }
+        }
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int hier_host_check(const void* texels, int isFp32, int w, int h, int addrMode, float borderAlpha,
+                                                                      float cutoff, int stateGT, int stateLE, int format, int promotion, const float* uvs,
+                                                                      const uint8_t* levels, uint32_t numItems, HierCheckStats* st) {
+    memset(st, 0, sizeof(*st));
+    BakeParams P{};
+    P.tex.texels = texels;
+    P.tex.sat = nullptr;
+    P.tex.isFp32 = isFp32;
+    P.tex.mipCount = 1;
+    DevMip& m = P.tex.mips[0];
+    m.w = w; m.h = h;
+    m.log2w = __builtin_ctz((unsigned)w); m.log2h = __builtin_ctz((unsigned)h);
+    m.isPow2 = (w & (w - 1)) == 0 && (h & (h - 1)) == 0;
+    m.rcpw = 1.f / (float)w; m.rcph = 1.f / (float)h;
+    m.texelOffset = 0; m.satOffset = 0;
+    P.addrMode = addrMode;
+    P.filterLinear = 1;
+    P.borderAlpha = borderAlpha;
+    P.cutoff = cutoff;
+    P.stateGT = stateGT; P.stateLE = stateLE;
+    P.globalFormat = format;
+    P.promotion = promotion;
+    P.pow2Mip0 = m.isPow2;
+    if (isFp32) CheckItems<KernelCfg<kAddrGeneric, true>>(P, uvs, levels, numItems, st);
+    else CheckItems<KernelCfg<kAddrGeneric, false>>(P, uvs, levels, numItems, st);
+    return st->mismatches == 0 ? 0 : 1;
+}
