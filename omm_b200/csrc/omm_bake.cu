@@ -550,7 +550,7 @@ constexpr int kHierWarps = 4;
 constexpr int kHierListCap = 64;
 struct HierWarpShared {
     uint32_t states[256];
-    uint16_t list[4][kHierListCap];  // [0] failing 64-regions, [1] 16-regions, [2] 4-regions, [3] micro-triangles awaiting the reference walk
+    uint16_t list[3][kHierListCap];  // failing regions of 64, 16 and 4 micro-triangles (node-relative region indices)
 };
 
 // write `state` into the micro-triangle range of region `idx` of size 4^e
@@ -567,98 +567,143 @@ __device__ __forceinline__ void HierFill(uint32_t* states, uint32_t e, uint32_t 
     }
 }
 
+// Items the shortcuts do not cover (zero-area UV triangles, non-finite or huge coordinates): the generic reference walk.
+// Reads the bake parameters from their copy in global memory (a reference to the kernel parameter would force a 1 KB
+// per-thread stack copy of it).
+template <class Cfg>
+__device__ __noinline__ uint32_t HierSlowPath(const BakeParams* __restrict__ Pg, float2 p0, float2 p1, float2 p2, bool degenerate, uint32_t index, uint32_t level) {
+    return (uint32_t)ClassifyMicroTriangle<Cfg>(*Pg, p0, p1, p2, degenerate, index, level);
+}
+
+// Persistent warps: every warp draws nodes from a global counter until none are left (work per node varies by two orders
+// of magnitude between uniform and level-line-crossed triangles).
 template <class Cfg>
 __global__ void __launch_bounds__(kHierWarps * 32) HierClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items,
                                                                      const unsigned long long* __restrict__ nodeStart,
                                                                      const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
                                                                      unsigned long long nodeBegin, unsigned long long nodeEnd,
+                                                                     unsigned long long* __restrict__ nodeCounter, const BakeParams* __restrict__ Pglobal,
                                                                      uint32_t* __restrict__ stateWords) {
     __shared__ __align__(16) HierWarpShared sWarp[kHierWarps];
-    __shared__ uint32_t sFirstItem;
-    const unsigned long long blockNode = nodeBegin + (unsigned long long)blockIdx.x * kHierWarps;
-    if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(nodeStart + itemBegin, itemEnd - itemBegin, blockNode);
-    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long node = blockNode + warp;
-    if (node >= nodeEnd) return;
-    uint32_t w = sFirstItem;
-    while (w + 1 < itemEnd && __ldg(&nodeStart[w + 1]) <= node) ++w;
-    const ItemRec item = items[w];
-    const DevMip& m = P.tex.mips[0];
-    const uint32_t L = item.level;
-    const uint32_t nl = L < (uint32_t)kNodeLevels ? L : (uint32_t)kNodeLevels;        // levels below the node
-    const uint32_t nodeInItem = (uint32_t)(node - __ldg(&nodeStart[w]));               // bird index of the node at level L - nl
-    const uint32_t nMicro = 1u << (2 * nl);
     HierWarpShared& sh = sWarp[warp];
-    const uint32_t nWords = nMicro >= 16 ? nMicro >> 4 : 1;
-    for (uint32_t i = lane; i < nWords; i += 32) sh.states[i] = 0;
-    __syncwarp();
-
-    const HierItem hi = MakeHierItem(m, item.p0, item.p1, item.p2, L, item.degenerate != 0);
+    const DevMip& m = P.tex.mips[0];
     const uint32_t sGT = (uint32_t)P.stateGT, sLE = (uint32_t)P.stateLE;
-    uint32_t cnt = 0;  // four warp-uniform list sizes, 8 bits each (each list holds at most 64 entries)
-#define HCNT(i) ((cnt >> (8u * (i))) & 0xFFu)
-    // region of size exponent e, index idx within the node: bird index (nodeInItem << 2(nl-e)) + idx at level L - e
-    const uint32_t e0 = nl < 3 ? nl : 3;
+    const unsigned long long firstNodeOfShard = __ldg(&nodeStart[itemBegin]);
 
-    // test the `active` lanes' regions (size exponent e, node-relative index idx); passing ones are filled, failing ones are pushed
-    auto testAndPush = [&](uint32_t e, uint32_t idx, bool active) {
-        int s = 0;
-        if (active && hi.ok) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
-        if (active && s != 0) HierFill(sh.states, e, idx, s > 0 ? sGT : sLE);
-        const bool fail = active && s == 0;
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, fail);
-        const uint32_t li = 3 - e;
-        if (fail) sh.list[li][HCNT(li) + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)idx;
-        cnt += (uint32_t)__popc(mask) << (8u * li);
-        __syncwarp();
-    };
-
-    // initial regions: 4^(nl - e0) of them (64 for a full node: two rounds, at most 64 failures)
-    {
-        const uint32_t nInit = 1u << (2 * (nl - e0));
-        for (uint32_t base = 0; base < nInit; base += 32) testAndPush(e0, base + lane, base + lane < nInit);
-    }
-    // descend: serve the deepest list that can fill a round, else the shallowest non-empty one.  A list grows by at most 32
-    // per round and is served as soon as it holds 8 (regions) / 32 (micro-triangles), so 64 entries are never exceeded.
-    while (cnt != 0) {
-        const uint32_t c0 = HCNT(0), c1 = HCNT(1), c2 = HCNT(2), c3 = HCNT(3);
-        if (c3 >= 32 || (c0 == 0 && c1 == 0 && c2 == 0)) {
-            const uint32_t k = c3 < 32 ? c3 : 32;
-            cnt -= k << 24;
-            if (lane < k) {
-                const uint32_t idx = sh.list[3][c3 - k + lane];
-                const uint32_t st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, item.p0, item.p1, item.p2, item.degenerate != 0, (nodeInItem << (2 * nl)) + idx, L);
-                HierFill(sh.states, 0, idx, st);
-            }
-            __syncwarp();
-            continue;
+    while (true) {
+        unsigned long long node = 0;
+        if (lane == 0) node = atomicAdd(nodeCounter, 1ull);
+        node = __shfl_sync(0xFFFFFFFFu, node, 0) + nodeBegin;
+        if (node >= nodeEnd) break;
+        // item of the node: every item has at least one node, so the item index is at most itemBegin + (node - first node)
+        uint32_t w;
+        {
+            const unsigned long long guess = (unsigned long long)itemBegin + (node - firstNodeOfShard);
+            w = guess < (unsigned long long)(itemEnd - 1) ? (uint32_t)guess : itemEnd - 1;
+            if (__ldg(&nodeStart[w]) > node) w = itemBegin + FindItem(nodeStart + itemBegin, w - itemBegin, node);
         }
-        uint32_t src;
-        if (c2 >= 8 || (c2 > 0 && c0 == 0 && c1 == 0)) src = 2;
-        else if (c1 >= 8 || (c1 > 0 && c0 == 0)) src = 1;
-        else src = 0;  // c0 > 0 here
-        const uint32_t have = HCNT(src);
-        const uint32_t k = have < 8 ? have : 8;
-        cnt -= k << (8u * src);
-        const bool active = (lane >> 2) < k;
-        const uint32_t parent = active ? sh.list[src][have - k + (lane >> 2)] : 0u;
+        const ItemRec item = items[w];
+        const uint32_t L = item.level;
+        const uint32_t nl = L < (uint32_t)kNodeLevels ? L : (uint32_t)kNodeLevels;  // levels below the node
+        const uint32_t nodeInItem = (uint32_t)(node - __ldg(&nodeStart[w]));          // bird index of the node at level L - nl
+        const uint32_t nMicro = 1u << (2 * nl);
+        const uint32_t nWords = nMicro >= 16 ? nMicro >> 4 : 1;
+        for (uint32_t i = lane; i < nWords; i += 32) sh.states[i] = 0;
         __syncwarp();
-        testAndPush(2 - src, parent * 4u + (lane & 3u), active);
-    }
+
+        const HierItem hi = MakeHierItem(m, item.p0, item.p1, item.p2, L, item.degenerate != 0);
+        uint32_t cnt = 0;  // three warp-uniform list sizes, 8 bits each
+#define HCNT(i) ((cnt >> (8u * (i))) & 0xFFu)
+        // initial regions: size exponent e0 = min(nl, 3), 4^(nl - e0) of them; a level-0 item is a single leaf
+        const uint32_t e0 = nl < 3 ? nl : 3;
+        uint32_t nInit = nl == 0 ? 0u : 1u << (2 * (nl - e0));
+        uint32_t initDone = 0;
+        if (nl == 0 || !hi.ok) {
+            // no region tests: seed the leaf list with every 4-region (items the shortcuts do not cover are rare and small)
+            nInit = 0;
+            if (nl <= 1) {
+                if (lane == 0) sh.list[2][0] = 0;
+                cnt = 1u << 16;
+            }
+        }
+        const bool seedLeaves = !hi.ok && nl >= 2;
+        uint32_t seedNext = 0;  // next 4-region to seed when the whole node takes the slow path
+        const uint32_t seedCount = nMicro >> 2;
+
+        // Serve the deepest list that can fill a round, else the shallowest source.  A list grows by at most 32 per round and is
+        // served as soon as it holds 8 entries, so it never exceeds 40.
+        while (true) {
+            const uint32_t c0 = HCNT(0), c1 = HCNT(1), c2 = HCNT(2);
+            const bool moreInit = initDone < nInit;
+            if (seedLeaves && c2 == 0 && seedNext < seedCount) {
+                if (lane < 8 && seedNext + lane < seedCount) sh.list[2][lane] = (uint16_t)(seedNext + lane);
+                const uint32_t k = seedCount - seedNext < 8 ? seedCount - seedNext : 8;
+                seedNext += k;
+                cnt += k << 16;
+                __syncwarp();
+                continue;
+            }
+            if (c2 >= 8 || (c2 > 0 && c1 == 0 && c0 == 0 && !moreInit)) {
+                // leaf round: 8 failing 4-regions = 32 micro-triangles
+                const uint32_t k = c2 < 8 ? c2 : 8;
+                cnt -= k << 16;
+                const uint32_t idx = ((lane >> 2) < k ? (uint32_t)sh.list[2][c2 - k + (lane >> 2)] : 0u) * 4u + (lane & 3u);
+                if ((lane >> 2) < k && idx < nMicro) {
+                    const uint32_t index = (nodeInItem << (2 * nl)) + idx;
+                    const uint32_t st = hi.ok ? (uint32_t)LeafClassify<Cfg>(P, m, hi, index) : HierSlowPath<Cfg>(Pglobal, item.p0, item.p1, item.p2, item.degenerate != 0, index, L);
+                    HierFill(sh.states, 0, idx, st);
+                }
+                __syncwarp();
+                continue;
+            }
+            uint32_t e, idx;
+            bool active;
+            if (c1 >= 8 || (c1 > 0 && c0 == 0 && !moreInit)) {
+                const uint32_t k = c1 < 8 ? c1 : 8;
+                cnt -= k << 8;
+                active = (lane >> 2) < k;
+                idx = (active ? (uint32_t)sh.list[1][c1 - k + (lane >> 2)] : 0u) * 4u + (lane & 3u);
+                e = 1;
+            } else if (c0 >= 8 || (c0 > 0 && !moreInit)) {
+                const uint32_t k = c0 < 8 ? c0 : 8;
+                cnt -= k;
+                active = (lane >> 2) < k;
+                idx = (active ? (uint32_t)sh.list[0][c0 - k + (lane >> 2)] : 0u) * 4u + (lane & 3u);
+                e = 2;
+            } else if (moreInit) {
+                e = e0;
+                idx = initDone + lane;
+                active = idx < nInit;
+                initDone += 32;
+            } else
+                break;
+            __syncwarp();
+            int s = 0;
+            if (active) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
+            if (active && s != 0) HierFill(sh.states, e, idx, s > 0 ? sGT : sLE);
+            const bool fail = active && s == 0;
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, fail);
+            const uint32_t li = 3 - e;  // e = 3, 2, 1 -> list 0, 1, 2
+            if (fail) sh.list[li][HCNT(li) + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)idx;
+            cnt += (uint32_t)__popc(mask) << (8u * li);
+            __syncwarp();
+        }
 #undef HCNT
-    __syncwarp();
-    // write the node's state words (item blocks are padded to four words, see BuildItems)
-    uint32_t* dst = stateWords + __ldg(&wordStart[w]) + (unsigned long long)nodeInItem * 256ull;
-    if (nWords >= 4) {
-        for (uint32_t i = lane; i < (nWords >> 2); i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(sh.states)[i];
-    } else if (lane < nWords) {
-        dst[lane] = sh.states[lane];
+        __syncwarp();
+        // write the node's state words (item blocks are padded to four words, see BuildItems)
+        uint32_t* dst = stateWords + __ldg(&wordStart[w]) + (unsigned long long)nodeInItem * 256ull;
+        if (nWords >= 4) {
+            for (uint32_t i = lane; i < (nWords >> 2); i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(sh.states)[i];
+        } else if (lane < nWords) {
+            dst[lane] = sh.states[lane];
+        }
+        __syncwarp();
     }
 }
 
 typedef void (*HierFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
-                       unsigned long long, uint32_t*);
+                       unsigned long long, unsigned long long*, const BakeParams*, uint32_t*);
 // OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
 static int ClassifierOverride() {
     static const int v = [] {
@@ -1583,13 +1628,19 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         const HierFn hier = SelectHierKernel(P);
         if (itemEnd > itemBegin && hier) {
             const unsigned long long nodeBegin = bounds[rank].node, nodeEnd = bounds[rank + 1].node;
-            const unsigned long long blocks = (nodeEnd - nodeBegin + kHierWarps - 1) / kHierWarps;
-            const unsigned long long kMaxGrid = 0x7FFFFFFFull;
-            for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
-                const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
-                hier<<<(uint32_t)nb, kHierWarps * 32, 0, stream>>>(P, items, nodeStart, wordStart, itemBegin, itemEnd, nodeBegin + b0 * kHierWarps, nodeEnd, stateWords);
-                launches++;
-            }
+            // persistent grid: as many blocks as fit on the device at once
+            int perSm = 0, sms = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, hier, kHierWarps * 32, 0));
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
+            const unsigned long long want = (nodeEnd - nodeBegin + kHierWarps - 1) / kHierWarps;
+            const unsigned long long grid = std::min<unsigned long long>(want, (unsigned long long)std::max(perSm, 1) * (unsigned long long)std::max(sms, 1));
+            BakeParams* paramsDev = nullptr;
+            CUDA_TRY(scratch.alloc(&paramsDev, 1));
+            CUDA_TRY(cudaMemcpyAsync(paramsDev, &P, sizeof(BakeParams), cudaMemcpyHostToDevice, stream));  // pageable source: staged before the call returns
+            CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
+            hier<<<(uint32_t)grid, kHierWarps * 32, 0, stream>>>(P, items, nodeStart, wordStart, itemBegin, itemEnd, nodeBegin, nodeEnd, workloadDev, paramsDev,
+                                                                 stateWords);
+            launches++;
         } else if (itemEnd > itemBegin) {
             const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
             const unsigned long long blocks = (unitEnd - unitBegin + unitsPerBlock - 1) / unitsPerBlock;

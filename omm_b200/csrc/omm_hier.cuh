@@ -223,4 +223,105 @@ OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, 
     return sAll;
 }
 
+
+// ---- leaf: one micro-triangle, the reference walk with two exact skips ------------------------------------------------
+// (D) Per-cell edge filter.  q0,q1,q2 are the reference's own cell-local vertex coordinates.  A reported intersection lies
+//     within delta of one of the three segments (B), at a point of the unit square where |h| <= R.  Along a segment h is a
+//     quadratic g(t) with second-order coefficient A2 = d ex ey, so g stays within |A2|/4 of the chord between its end
+//     values; moving delta away from the segment changes h by at most delta (|b| + |c| + |d|(Qx + Qy)).  Hence, when the
+//     three vertex values have one sign s and
+//        min_i |h(q_i)| - max_j |A2_j| / 4 - 3 delta (|b| + |c| + |d|(Qx + Qy)) - 8 u (|a'| + |b| Qx + |c| Qy + |d| Qx Qy)  >  R
+//     (the last term covers the float evaluation of h(q_i)), none of the three tests can succeed and they are skipped.
+// (E) Votes that cannot matter.  Unless the promotion is Nearest the state depends only on which counters are non-zero
+//     (bake_kernels_cpu.h:27-50).  In a cell whose four texels are on side s, where side s has been voted already and the
+//     edge filter holds, the corner and flat-patch branches can only vote s again: the whole cell is skipped.
+template <class Cfg>
+OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, const Tri& tri, int px, int py, Coverage& cov, bool countsMatter) {
+    const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
+    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
+    const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
+    const float gx = TexFetch<Cfg>(P, m, x0, y0);
+    const float gy = TexFetch<Cfg>(P, m, x0, y1);
+    const float gz = TexFetch<Cfg>(P, m, x1, y1);
+    const float gw = TexFetch<Cfg>(P, m, x1, y0);
+    const float a = gx;
+    const float b = gw - gx;
+    const float c = gy - gx;
+    const float d = gx + gz - gy - gw;
+    const float sx = (float)m.w, sy = (float)m.h;
+    const float h0 = a - P.cutoff;
+    const float2 q0 = make_float2(sx * tri.p0.x - pfx, sy * tri.p0.y - pfy);
+    const float2 q1 = make_float2(sx * tri.p1.x - pfx, sy * tri.p1.y - pfy);
+    const float2 q2 = make_float2(sx * tri.p2.x - pfx, sy * tri.p2.y - pfy);
+    const bool o0 = P.cutoff < gx, o1 = P.cutoff < gy, o2 = P.cutoff < gz, o3 = P.cutoff < gw;
+
+    // (D) edge filter
+    bool edgesCannotHit = false;
+    int s = 0;
+    {
+        const float v0 = (h0 + b * q0.x) + (c + d * q0.x) * q0.y;
+        const float v1 = (h0 + b * q1.x) + (c + d * q1.x) * q1.y;
+        const float v2 = (h0 + b * q2.x) + (c + d * q2.x) * q2.y;
+        if (v0 > 0.f && v1 > 0.f && v2 > 0.f) s = 1;
+        else if (v0 < 0.f && v1 < 0.f && v2 < 0.f) s = -1;
+        if (s != 0 && it.ok) {
+            const float al = fabsf(h0), be = fabsf(b), ga = fabsf(c), de = fabsf(d);
+            const float qx = fmaxf(fmaxf(fabsf(q0.x), fabsf(q1.x)), fabsf(q2.x)) + it.deltaEdge;
+            const float qy = fmaxf(fmaxf(fabsf(q0.y), fabsf(q1.y)), fabsf(q2.y)) + it.deltaEdge;
+            const float e01 = fabsf((q1.x - q0.x) * (q1.y - q0.y)), e12 = fabsf((q2.x - q1.x) * (q2.y - q1.y)), e20 = fabsf((q0.x - q2.x) * (q0.y - q2.y));
+            const float sag = 0.2525f * de * fmaxf(fmaxf(e01, e12), e20);
+            const float pad = 3.f * it.deltaEdge * (be + ga + de * (qx + qy)) + 8.f * kUnitRoundoff * (al + be * qx + ga * qy + de * qx * qy);
+            const float margin = fminf(fminf(fabsf(v0), fabsf(v1)), fabsf(v2)) - sag - pad;
+            const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
+            edgesCannotHit = MarginBeatsEdgeBound(it, margin, al, be, ga, de, gmaxAbs, fabsf(P.cutoff), qx, qy);
+        }
+    }
+    // (E)
+    if (edgesCannotHit && !countsMatter) {
+        const bool want = s > 0;
+        if (o0 == want && o1 == want && o2 == want && o3 == want && (want ? cov.above : cov.below) != 0) return;
+    }
+    {
+        const float ipx = pfx * m.rcpw, ipy = pfy * m.rcph;
+        const bool in0 = PointInTri(tri, ipx, ipy);
+        const bool in1 = PointInTri(tri, ipx + 0.0f, ipy + m.rcph);
+        const bool in2 = PointInTri(tri, ipx + m.rcpw, ipy + m.rcph);
+        const bool in3 = PointInTri(tri, ipx + m.rcpw, ipy + 0.0f);
+        const bool isOpaque = (in0 && o0) || (in1 && o1) || (in2 && o2) || (in3 && o3);
+        const bool isTransparent = (in0 && !o0) || (in1 && !o1) || (in2 && !o2) || (in3 && !o3);
+        if (isOpaque) cov.above += 1;
+        if (isTransparent) cov.below += 1;
+        if (isOpaque && isTransparent) return;
+    }
+    if (IsZero(b, 1e-6f) && IsZero(c, 1e-6f) && IsZero(d, 1e-6f)) {
+        if (P.cutoff < a) cov.above += 1;
+        else cov.below += 1;
+        return;
+    }
+    if (edgesCannotHit) return;
+    if (EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d)) {
+        cov.above += 1;
+        cov.below += 1;
+    }
+}
+
+// One micro-triangle of a non-degenerate work item, Linear filter, level-line test, single mip, no SAT pass
+// (ref: bake_cpu_impl.cpp:861-908 with ResampleFine's Normal path).
+template <class Cfg>
+OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index) {
+    const Tri st = MicroTri(it.p0, it.p1, it.p2, index, it.level);
+    Coverage cov{0u, 0u};
+    const bool countsMatter = P.promotion == ommUnknownStatePromotion_Nearest;
+    if (P.cutoff < TexBilinear<Cfg>(P, m, st.p0)) cov.above++;
+    else cov.below++;
+    const RasterSetup rs = MakeRasterSetup(st, m.w, m.h, -0.5f);
+    RasterCursor cur = RasterBegin(rs);
+    int x, y;
+    while (RasterNext(rs, cur, x, y)) {
+        LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter);
+        if (!countsMatter && cov.above != 0 && cov.below != 0) break;  // exact early-out, see ClassifyMicroTriangle
+    }
+    return StateFromCoverage(P, cov.above, cov.below);
+}
+
 }  // namespace ommb200

@@ -25,6 +25,12 @@ template <class Cfg>
 static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, uint32_t nodeInItem, uint32_t nl, uint32_t e, uint32_t idx, uint8_t* states,
                     HierCheckStats* st, const float2* uv, bool degenerate) {
     const uint32_t L = hi.level;
+    if (e == 0) {  // leaves: the reference walk with the exact skips of LeafCell (slow path for items the shortcuts do not cover)
+        st->fullEvals++;
+        const uint32_t index = (nodeInItem << (2 * nl)) + idx;
+        states[idx] = (uint8_t)(hi.ok ? LeafClassify<Cfg>(P, m, hi, index) : ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L));
+        return;
+    }
     int s = 0;
     st->tests[3 - e]++;
     if (hi.ok) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
@@ -32,11 +38,6 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, ui
         st->passes[3 - e]++;
         const uint32_t n = 1u << (2 * e);
         for (uint32_t i = 0; i < n; ++i) states[idx * n + i] = (uint8_t)(s > 0 ? P.stateGT : P.stateLE);
-        return;
-    }
-    if (e == 0) {
-        st->fullEvals++;
-        states[idx] = (uint8_t)ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, (nodeInItem << (2 * nl)) + idx, L);
         return;
     }
     for (uint32_t k = 0; k < 4; ++k) Descend<Cfg>(P, m, hi, nodeInItem, nl, e - 1, idx * 4 + k, states, st, uv, degenerate);
