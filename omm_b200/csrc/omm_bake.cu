@@ -35,7 +35,6 @@ namespace ommb200 {
     } while (0)
 
 constexpr int kMaxLevel = 12;
-constexpr int kNodeLevels = 6;  // a node of the hierarchical classifier covers at most 4^6 micro-triangles of one work item
 constexpr uint32_t kNoItem = 0xFFFFFFFFu;
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -311,7 +310,7 @@ __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __res
     const unsigned long long n = 1ull << (2 * it.level);
     itemUnits[w] = n >= 32 ? n / 32 : 1;
     itemWords[w] = n >= 64 ? n / 16 : 4;  // blocks start 16-byte aligned so the warp stores and the pack copies can be vectorised
-    itemNodes[w] = it.level > kNodeLevels ? 1ull << (2 * (it.level - kNodeLevels)) : 1ull;  // see HierClassifyKernel
+    itemNodes[w] = it.level > 3 ? 1ull << (2 * (it.level - 3)) : 1ull;  // initial regions of the hierarchical classifier (HierTestInitial)
 }
 
 __global__ void MapTrianglesToItems(const uint32_t* __restrict__ triFirst, const uint32_t* __restrict__ itemScan, uint32_t triCount, uint32_t* __restrict__ triItem) {
@@ -539,171 +538,160 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS)
 // ---------------------------------------------------------------------------------------------------------------------
 // K4, hierarchical variant (Linear filter + level-line test + single mip + no SAT pass: the default configuration).
 //
-// One warp owns a NODE: a sub-triangle of a work item with at most 4^6 micro-triangles (the whole item up to level 6).
-// The warp descends the bird-curve hierarchy breadth-first: regions of 64, 16, 4 and 1 micro-triangles, 32 regions per
-// round, one region per lane.  TestRegion (omm_hier.cuh) proves whole regions to be on one side of the cutoff; failing
-// regions are split through small per-warp work lists in shared memory, and single micro-triangles that still fail get the
-// reference walk (ClassifyMicroTriangle).  States accumulate in a shared-memory block (2 bits per micro-triangle) that is
-// written to HBM once, coalesced.
+// Level-synchronous descent of the bird-curve hierarchy with work lists in HBM:
+//   HierPrepare       per work item: the constants of the exact shortcuts (HierItem, omm_hier.cuh)
+//   HierTestInitial   one thread per INITIAL region (64 micro-triangles; the whole item below level 3): TestRegion proves the
+//                     region to be on one side of the cutoff -> its state words are filled; else the region goes to a list
+//   HierTestList      one thread per child (16, then 4 micro-triangles) of every listed region: same test, next list
+//   HierLeaves        one thread per micro-triangle of every listed 4-region: the reference walk with the exact skips of
+//                     LeafCell; four lanes assemble the byte of their 4-region
+// Every kernel is small and homogeneous (no divergence between phases, full occupancy); a list entry is (item, region index).
+// The lists are sized for the worst case (every test fails) of one CHUNK of initial regions; a bake is a sequence of chunks.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kHierWarps = 4;
-constexpr int kHierListCap = 64;
-struct HierWarpShared {
-    uint32_t states[256];
-    uint16_t list[3][kHierListCap];  // failing regions of 64, 16 and 4 micro-triangles (node-relative region indices)
+constexpr uint32_t kHierChunkRegions = 8u << 20;  // initial regions per chunk: lists of 8M + 32M + 128M entries (1.3 GiB) at most
+struct HierLists {
+    unsigned long long* q[3];   // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
+    unsigned long long* count;  // [3]
 };
 
-// write `state` into the micro-triangle range of region `idx` of size 4^e
-__device__ __forceinline__ void HierFill(uint32_t* states, uint32_t e, uint32_t idx, uint32_t state) {
-    if (e == 3) {
-        const uint32_t pat = state * 0x55555555u;
-        *reinterpret_cast<uint4*>(states + 4 * idx) = make_uint4(pat, pat, pat, pat);
-    } else if (e == 2) {
-        states[idx] = state * 0x55555555u;
-    } else if (e == 1) {
-        atomicOr(&states[idx >> 2], (state * 0x55u) << ((idx & 3u) * 8u));
-    } else {
-        atomicOr(&states[idx >> 4], state << ((idx & 15u) * 2u));
+__global__ void HierPrepare(const BakeParams P, const ItemRec* __restrict__ items, uint32_t itemBegin, uint32_t itemEnd, HierItem* __restrict__ hierItems) {
+    const uint32_t w = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= itemEnd) return;
+    const ItemRec it = items[w];
+    hierItems[w] = MakeHierItem(P.tex.mips[0], it.p0, it.p1, it.p2, it.level, it.degenerate != 0);
+}
+
+__device__ __forceinline__ HierItem LoadHierItem(const HierItem* __restrict__ p) {
+    HierItem hi;
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4* dst = reinterpret_cast<uint4*>(&hi);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);
+    return hi;
+}
+
+// warp-aggregated append of (item, idx) for the lanes with `push`
+__device__ __forceinline__ void HierAppend(unsigned long long* __restrict__ list, unsigned long long* __restrict__ count, bool push, uint32_t item, uint32_t idx) {
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, push);
+    if (mask == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)(__ffs(mask) - 1)) base = atomicAdd(count, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(mask) - 1);
+    if (push) list[base + __popc(mask & ((1u << lane) - 1u))] = ((unsigned long long)item << 32) | idx;
+}
+
+// state words of region `idx` (size exponent e) of an item whose block starts at `words`
+__device__ __forceinline__ void HierFillGlobal(uint32_t* __restrict__ words, uint32_t e, uint32_t idx, uint32_t state) {
+    const uint32_t pat = state * 0x55555555u;
+    if (e == 3) reinterpret_cast<uint4*>(words)[idx] = make_uint4(pat, pat, pat, pat);
+    else if (e == 2) words[idx] = pat;
+    else reinterpret_cast<uint8_t*>(words)[idx] = (uint8_t)pat;  // e == 1: four micro-triangles, one byte
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(128) HierTestInitial(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
+                                                        const unsigned long long* __restrict__ regionStart, const unsigned long long* __restrict__ wordStart,
+                                                        uint32_t itemBegin, uint32_t itemEnd, unsigned long long regionBegin, unsigned long long regionEnd,
+                                                        HierLists lists, uint32_t* __restrict__ stateWords) {
+    __shared__ uint32_t sFirstItem;
+    const unsigned long long blockRegion = regionBegin + (unsigned long long)blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(regionStart + itemBegin, itemEnd - itemBegin, blockRegion);
+    __syncthreads();
+    const unsigned long long region = blockRegion + threadIdx.x;
+    const bool valid = region < regionEnd;
+    uint32_t w = sFirstItem;
+    int s = 0;
+    uint32_t e = 3, idx = 0, L = 0;
+    bool slow = false;
+    if (valid) {
+        while (w + 1 < itemEnd && __ldg(&regionStart[w + 1]) <= region) ++w;
+        idx = (uint32_t)(region - __ldg(&regionStart[w]));
+        const HierItem hi = LoadHierItem(hierItems + w);
+        L = hi.level;
+        e = L < 3 ? L : 3;
+        slow = !hi.ok;
+        if (!slow && e > 0) {
+            s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, L - e);
+            if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+        }
+    }
+    const bool fail = valid && s == 0;
+    // e == 3 -> list 0, e == 2 -> list 1, e <= 1 -> list 2 (a level-0 item is one leaf: it is listed as the 4-region 0 of its item).
+    // Items the shortcuts do not cover list all their 4-regions (16, 4 or 1 per initial region).
+    HierAppend(lists.q[0], lists.count + 0, fail && !slow && e == 3, w, idx);
+    HierAppend(lists.q[1], lists.count + 1, fail && !slow && e == 2, w, idx);
+    HierAppend(lists.q[2], lists.count + 2, fail && !slow && e <= 1, w, idx);
+    const uint32_t nSlow = (valid && slow) ? (e >= 2 ? 1u << (2 * (e - 1)) : 1u) : 0u;
+    for (uint32_t k = 0; k < 16; ++k) {
+        if (__ballot_sync(0xFFFFFFFFu, k < nSlow) == 0) break;
+        HierAppend(lists.q[2], lists.count + 2, k < nSlow, w, idx * nSlow + k);
     }
 }
 
-// Items the shortcuts do not cover (zero-area UV triangles, non-finite or huge coordinates): the generic reference walk.
-// Reads the bake parameters from their copy in global memory (a reference to the kernel parameter would force a 1 KB
-// per-thread stack copy of it).
+// children of the regions in lists.q[src] (size exponent 3 - src); the children have size exponent 2 - src
 template <class Cfg>
-__device__ __noinline__ uint32_t HierSlowPath(const BakeParams* __restrict__ Pg, float2 p0, float2 p1, float2 p2, bool degenerate, uint32_t index, uint32_t level) {
-    return (uint32_t)ClassifyMicroTriangle<Cfg>(*Pg, p0, p1, p2, degenerate, index, level);
-}
-
-// Persistent warps: every warp draws nodes from a global counter until none are left (work per node varies by two orders
-// of magnitude between uniform and level-line-crossed triangles).
-template <class Cfg>
-__global__ void __launch_bounds__(kHierWarps * 32) HierClassifyKernel(const BakeParams P, const ItemRec* __restrict__ items,
-                                                                     const unsigned long long* __restrict__ nodeStart,
-                                                                     const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
-                                                                     unsigned long long nodeBegin, unsigned long long nodeEnd,
-                                                                     unsigned long long* __restrict__ nodeCounter, const BakeParams* __restrict__ Pglobal,
-                                                                     uint32_t* __restrict__ stateWords) {
-    __shared__ __align__(16) HierWarpShared sWarp[kHierWarps];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    HierWarpShared& sh = sWarp[warp];
-    const DevMip& m = P.tex.mips[0];
-    const uint32_t sGT = (uint32_t)P.stateGT, sLE = (uint32_t)P.stateLE;
-    const unsigned long long firstNodeOfShard = __ldg(&nodeStart[itemBegin]);
-
-    while (true) {
-        unsigned long long node = 0;
-        if (lane == 0) node = atomicAdd(nodeCounter, 1ull);
-        node = __shfl_sync(0xFFFFFFFFu, node, 0) + nodeBegin;
-        if (node >= nodeEnd) break;
-        // item of the node: every item has at least one node, so the item index is at most itemBegin + (node - first node)
-        uint32_t w;
-        {
-            const unsigned long long guess = (unsigned long long)itemBegin + (node - firstNodeOfShard);
-            w = guess < (unsigned long long)(itemEnd - 1) ? (uint32_t)guess : itemEnd - 1;
-            if (__ldg(&nodeStart[w]) > node) w = itemBegin + FindItem(nodeStart + itemBegin, w - itemBegin, node);
+__global__ void __launch_bounds__(128) HierTestList(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+                                                     const unsigned long long* __restrict__ inList, const unsigned long long* __restrict__ inCount,
+                                                     unsigned long long* __restrict__ outList, unsigned long long* __restrict__ outCount, int src,
+                                                     uint32_t* __restrict__ stateWords) {
+    const unsigned long long total = *inCount * 4ull;
+    const unsigned long long rounded = (total + 31ull) & ~31ull;
+    const uint32_t e = 2u - (uint32_t)src;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const bool valid = t < total;
+        uint32_t w = 0, idx = 0;
+        int s = 0;
+        if (valid) {
+            const unsigned long long entry = inList[t >> 2];
+            w = (uint32_t)(entry >> 32);
+            idx = (uint32_t)entry * 4u + (uint32_t)(t & 3ull);
+            const HierItem hi = LoadHierItem(hierItems + w);
+            s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, hi.level - e);
+            if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
         }
-        const ItemRec item = items[w];
-        const uint32_t L = item.level;
-        const uint32_t nl = L < (uint32_t)kNodeLevels ? L : (uint32_t)kNodeLevels;  // levels below the node
-        const uint32_t nodeInItem = (uint32_t)(node - __ldg(&nodeStart[w]));          // bird index of the node at level L - nl
-        const uint32_t nMicro = 1u << (2 * nl);
-        const uint32_t nWords = nMicro >= 16 ? nMicro >> 4 : 1;
-        for (uint32_t i = lane; i < nWords; i += 32) sh.states[i] = 0;
-        __syncwarp();
-
-        const HierItem hi = MakeHierItem(m, item.p0, item.p1, item.p2, L, item.degenerate != 0);
-        uint32_t cnt = 0;  // three warp-uniform list sizes, 8 bits each
-#define HCNT(i) ((cnt >> (8u * (i))) & 0xFFu)
-        // initial regions: size exponent e0 = min(nl, 3), 4^(nl - e0) of them; a level-0 item is a single leaf
-        const uint32_t e0 = nl < 3 ? nl : 3;
-        uint32_t nInit = nl == 0 ? 0u : 1u << (2 * (nl - e0));
-        uint32_t initDone = 0;
-        if (nl == 0 || !hi.ok) {
-            // no region tests: seed the leaf list with every 4-region (items the shortcuts do not cover are rare and small)
-            nInit = 0;
-            if (nl <= 1) {
-                if (lane == 0) sh.list[2][0] = 0;
-                cnt = 1u << 16;
-            }
-        }
-        const bool seedLeaves = !hi.ok && nl >= 2;
-        uint32_t seedNext = 0;  // next 4-region to seed when the whole node takes the slow path
-        const uint32_t seedCount = nMicro >> 2;
-
-        // Serve the deepest list that can fill a round, else the shallowest source.  A list grows by at most 32 per round and is
-        // served as soon as it holds 8 entries, so it never exceeds 40.
-        while (true) {
-            const uint32_t c0 = HCNT(0), c1 = HCNT(1), c2 = HCNT(2);
-            const bool moreInit = initDone < nInit;
-            if (seedLeaves && c2 == 0 && seedNext < seedCount) {
-                if (lane < 8 && seedNext + lane < seedCount) sh.list[2][lane] = (uint16_t)(seedNext + lane);
-                const uint32_t k = seedCount - seedNext < 8 ? seedCount - seedNext : 8;
-                seedNext += k;
-                cnt += k << 16;
-                __syncwarp();
-                continue;
-            }
-            if (c2 >= 8 || (c2 > 0 && c1 == 0 && c0 == 0 && !moreInit)) {
-                // leaf round: 8 failing 4-regions = 32 micro-triangles
-                const uint32_t k = c2 < 8 ? c2 : 8;
-                cnt -= k << 16;
-                const uint32_t idx = ((lane >> 2) < k ? (uint32_t)sh.list[2][c2 - k + (lane >> 2)] : 0u) * 4u + (lane & 3u);
-                if ((lane >> 2) < k && idx < nMicro) {
-                    const uint32_t index = (nodeInItem << (2 * nl)) + idx;
-                    const uint32_t st = hi.ok ? (uint32_t)LeafClassify<Cfg>(P, m, hi, index) : HierSlowPath<Cfg>(Pglobal, item.p0, item.p1, item.p2, item.degenerate != 0, index, L);
-                    HierFill(sh.states, 0, idx, st);
-                }
-                __syncwarp();
-                continue;
-            }
-            uint32_t e, idx;
-            bool active;
-            if (c1 >= 8 || (c1 > 0 && c0 == 0 && !moreInit)) {
-                const uint32_t k = c1 < 8 ? c1 : 8;
-                cnt -= k << 8;
-                active = (lane >> 2) < k;
-                idx = (active ? (uint32_t)sh.list[1][c1 - k + (lane >> 2)] : 0u) * 4u + (lane & 3u);
-                e = 1;
-            } else if (c0 >= 8 || (c0 > 0 && !moreInit)) {
-                const uint32_t k = c0 < 8 ? c0 : 8;
-                cnt -= k;
-                active = (lane >> 2) < k;
-                idx = (active ? (uint32_t)sh.list[0][c0 - k + (lane >> 2)] : 0u) * 4u + (lane & 3u);
-                e = 2;
-            } else if (moreInit) {
-                e = e0;
-                idx = initDone + lane;
-                active = idx < nInit;
-                initDone += 32;
-            } else
-                break;
-            __syncwarp();
-            int s = 0;
-            if (active) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
-            if (active && s != 0) HierFill(sh.states, e, idx, s > 0 ? sGT : sLE);
-            const bool fail = active && s == 0;
-            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, fail);
-            const uint32_t li = 3 - e;  // e = 3, 2, 1 -> list 0, 1, 2
-            if (fail) sh.list[li][HCNT(li) + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)idx;
-            cnt += (uint32_t)__popc(mask) << (8u * li);
-            __syncwarp();
-        }
-#undef HCNT
-        __syncwarp();
-        // write the node's state words (item blocks are padded to four words, see BuildItems)
-        uint32_t* dst = stateWords + __ldg(&wordStart[w]) + (unsigned long long)nodeInItem * 256ull;
-        if (nWords >= 4) {
-            for (uint32_t i = lane; i < (nWords >> 2); i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(sh.states)[i];
-        } else if (lane < nWords) {
-            dst[lane] = sh.states[lane];
-        }
-        __syncwarp();
+        HierAppend(outList, outCount, valid && s == 0, w, idx);
     }
 }
 
-typedef void (*HierFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
-                       unsigned long long, unsigned long long*, const BakeParams*, uint32_t*);
+template <class Cfg>
+__global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
+                                                   const unsigned long long* __restrict__ wordStart, HierLists lists, uint32_t* __restrict__ stateWords) {
+    const unsigned long long total = lists.count[2] * 4ull;
+    const unsigned long long rounded = (total + 31ull) & ~31ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t bits = 0, w = 0, region = 0;
+        if (t < total) {
+            const unsigned long long entry = lists.q[2][t >> 2];
+            w = (uint32_t)(entry >> 32);
+            region = (uint32_t)entry;
+            const uint32_t k = (uint32_t)(t & 3ull), index = region * 4u + k;
+            const HierItem hi = LoadHierItem(hierItems + w);
+            uint32_t st = 0;
+            if (index < (1u << (2 * hi.level))) {  // a level-0 item has one micro-triangle in its only "4-region"
+                if (hi.ok) st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
+                else st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, hi.p0, hi.p1, hi.p2, items[w].degenerate != 0, index, hi.level);
+            }
+            bits = st << (2 * k);
+        }
+        bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
+        bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 2);
+        if (t < total && (t & 3ull) == 0) reinterpret_cast<uint8_t*>(stateWords + __ldg(&wordStart[w]))[region] = (uint8_t)bits;
+    }
+}
+
+struct HierKernels {
+    void (*initial)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
+                    unsigned long long, HierLists, uint32_t*);
+    void (*list)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, const unsigned long long*, unsigned long long*,
+                 unsigned long long*, int, uint32_t*);
+    void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
+};
+template <class Cfg>
+static HierKernels MakeHierKernels() {
+    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>};
+}
+
 // OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
 static int ClassifierOverride() {
     static const int v = [] {
@@ -715,17 +703,19 @@ static int ClassifierOverride() {
     }();
     return v;
 }
-static HierFn SelectHierKernel(const BakeParams& P) {
-    if (ClassifierOverride() != 0) return nullptr;
-    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine && !P.useCoarse && P.tex.mipCount == 1)) return nullptr;
+static bool SelectHierKernels(const BakeParams& P, HierKernels* out) {
+    if (ClassifierOverride() != 0) return false;
+    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine && !P.useCoarse && P.tex.mipCount == 1)) return false;
     const bool pow2 = P.tex.mips[0].isPow2 != 0;
     if (P.tex.isFp32) {
-        if (P.addrMode == ommTextureAddressMode_Wrap && pow2) return HierClassifyKernel<KernelCfg<kAddrWrapPow2, true>>;
-        if (P.addrMode == ommTextureAddressMode_Clamp) return HierClassifyKernel<KernelCfg<kAddrClamp, true>>;
-        return HierClassifyKernel<KernelCfg<kAddrGeneric, true>>;
+        if (P.addrMode == ommTextureAddressMode_Wrap && pow2) *out = MakeHierKernels<KernelCfg<kAddrWrapPow2, true>>();
+        else if (P.addrMode == ommTextureAddressMode_Clamp) *out = MakeHierKernels<KernelCfg<kAddrClamp, true>>();
+        else *out = MakeHierKernels<KernelCfg<kAddrGeneric, true>>();
+    } else {
+        if (P.addrMode == ommTextureAddressMode_Wrap && pow2) *out = MakeHierKernels<KernelCfg<kAddrWrapPow2, false>>();
+        else *out = MakeHierKernels<KernelCfg<kAddrGeneric, false>>();
     }
-    if (P.addrMode == ommTextureAddressMode_Wrap && pow2) return HierClassifyKernel<KernelCfg<kAddrWrapPow2, false>>;
-    return HierClassifyKernel<KernelCfg<kAddrGeneric, false>>;
+    return true;
 }
 typedef void (*ClassifyFn)(const BakeParams, const ItemRec*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
                            unsigned long long, uint32_t*);
@@ -1625,22 +1615,32 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         const uint32_t itemBegin = bounds[rank].item, itemEnd = bounds[rank + 1].item;
         const unsigned long long unitBegin = bounds[rank].unit, unitEnd = bounds[rank + 1].unit;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
-        const HierFn hier = SelectHierKernel(P);
-        if (itemEnd > itemBegin && hier) {
-            const unsigned long long nodeBegin = bounds[rank].node, nodeEnd = bounds[rank + 1].node;
-            // persistent grid: as many blocks as fit on the device at once
-            int perSm = 0, sms = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, hier, kHierWarps * 32, 0));
+        HierKernels hier{};
+        const bool useHier = SelectHierKernels(P, &hier);
+        if (itemEnd > itemBegin && useHier) {
+            const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
+            const unsigned long long chunkRegions = std::min<unsigned long long>(kHierChunkRegions, regionEnd - regionBegin);
+            HierItem* hierItems = nullptr;
+            HierLists lists{};
+            CUDA_TRY(scratch.alloc(&hierItems, W));
+            CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)chunkRegions));
+            CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)chunkRegions * 4));
+            CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)chunkRegions * 16));
+            CUDA_TRY(scratch.alloc(&lists.count, 4));
+            int sms = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
-            const unsigned long long want = (nodeEnd - nodeBegin + kHierWarps - 1) / kHierWarps;
-            const unsigned long long grid = std::min<unsigned long long>(want, (unsigned long long)std::max(perSm, 1) * (unsigned long long)std::max(sms, 1));
-            BakeParams* paramsDev = nullptr;
-            CUDA_TRY(scratch.alloc(&paramsDev, 1));
-            CUDA_TRY(cudaMemcpyAsync(paramsDev, &P, sizeof(BakeParams), cudaMemcpyHostToDevice, stream));  // pageable source: staged before the call returns
-            CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
-            hier<<<(uint32_t)grid, kHierWarps * 32, 0, stream>>>(P, items, nodeStart, wordStart, itemBegin, itemEnd, nodeBegin, nodeEnd, workloadDev, paramsDev,
-                                                                 stateWords);
+            const uint32_t listGrid = (uint32_t)std::max(sms, 1) * 16u;
+            HierPrepare<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, itemBegin, itemEnd, hierItems);
             launches++;
+            for (unsigned long long r0 = regionBegin; r0 < regionEnd; r0 += chunkRegions) {
+                const unsigned long long r1 = std::min(regionEnd, r0 + chunkRegions);
+                CUDA_TRY(cudaMemsetAsync(lists.count, 0, 4 * sizeof(unsigned long long), stream));
+                hier.initial<<<(uint32_t)((r1 - r0 + 127) / 128), 128, 0, stream>>>(P, items, hierItems, nodeStart, wordStart, itemBegin, itemEnd, r0, r1, lists, stateWords);
+                hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
+                hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
+                hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
+                launches += 4;
+            }
         } else if (itemEnd > itemBegin) {
             const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
             const unsigned long long blocks = (unitEnd - unitBegin + unitsPerBlock - 1) / unitsPerBlock;

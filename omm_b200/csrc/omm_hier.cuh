@@ -55,7 +55,7 @@ namespace ommb200 {
 constexpr float kUnitRoundoff = 5.9604645e-8f;  // 2^-24
 constexpr int kHierMaxCells = 16;               // a region whose footprint is larger is split instead
 
-struct HierItem {
+struct alignas(16) HierItem {
     float2 p0, p1, p2;
     uint32_t level;
     float epsRegion, epsSingle;  // r-space enclosure slack (A)
@@ -63,7 +63,9 @@ struct HierItem {
     float kmin[3], kmax[3];      // slope range of the three edge direction classes (B)
     float pitX, pitY;            // r-space separation that makes PointInTriangle provably false (C); +inf = unavailable
     int ok;                      // shortcuts applicable to this work item at all
+    int pad;
 };
+static_assert(sizeof(HierItem) == 80, "HierItem is loaded with five 16-byte reads");
 
 OMM_HD float UlpOf(float x) {  // x >= 2^-100
     return UintAsFloat((FloatAsUint(x) & 0x7F800000u) - (23u << 23));
@@ -73,6 +75,7 @@ OMM_HD HierItem MakeHierItem(const DevMip& m, float2 p0, float2 p1, float2 p2, u
     const float u = kUnitRoundoff;
     const float inf = UintAsFloat(0x7f800000u);
     HierItem it;
+    it.pad = 0;
     it.p0 = p0; it.p1 = p1; it.p2 = p2;
     it.level = level;
     const float W = (float)m.w, H = (float)m.h;
