@@ -40,9 +40,12 @@
 // (C) Texel centres.  A cell corner whose texel is on side s can only vote s.  A corner on the other side must be provably
 //     outside every micro-triangle of the region as PointInTriangle evaluates it: each of its three edge functions is
 //     computed with relative error <= 4.1 u of |e||P - A|, the three real values sum to twice the area, and for a point at
-//     distance rho from the triangle the most negative one is >= kappa^2 emax rho / 2 (kappa = 2 Area / emax^2); so
-//     rho >= 5 * 4.1 u / kappa^2 * diam makes two of them reliably opposite in sign, which makes the function return false
-//     whatever the third one does.  In r-space: the corner is separated from [lo, hi] by pit = rho W + eps in x or y.
+//     distance rho from the triangle the most negative one is >= kappa^2 emax rho / 2 (kappa = 2 Area / emax^2: the shortest edge
+//     is >= kappa emax and every half-angle has sine >= kappa / 2), while a positive one is at least half as large; so
+//     kappa^2 rho / 2 > 2 * 4.1 u (rho + diam), guaranteed by rho >= 5 * 4.1 u / kappa^2 * diam when kappa >= 0.01, makes two of
+//     them reliably opposite in sign, and then the function returns false whatever the third one does (first test of
+//     geometry.h:107 if they are s and t, the final comparison otherwise).  In r-space: the corner is separated from [lo, hi]
+//     by pit = rho W + eps in x or in y.
 //
 // Everything here compiles for host and device (see omm_device_math.cuh); tests/hier_host_check.cpp fuzzes TestRegion
 // against the reference walk on the CPU, the GPU parity suite does the same through the library.
@@ -53,6 +56,12 @@
 namespace ommb200 {
 
 constexpr float kUnitRoundoff = 5.9604645e-8f;  // 2^-24
+#if defined(OMM_HIER_STATS)
+static unsigned long long g_hierStats[16];  // host-only instrumentation of the fuzz harness
+#define OMM_STAT(i) (g_hierStats[i]++)
+#else
+#define OMM_STAT(i) ((void)0)
+#endif
 constexpr int kHierMaxCells = 16;               // a region whose footprint is larger is split instead
 
 struct alignas(16) HierItem {
@@ -114,15 +123,17 @@ OMM_HD HierItem MakeHierItem(const DevMip& m, float2 p0, float2 p1, float2 p2, u
         if (ax[j] > 2.f * eta) it.kmax[j] = (ay[j] + eta) / (ax[j] - eta) * (1.f + 8.f * u);
         else it.kmax[j] = (ay[j] + eta) / fmaxf(9.9e-7f, tau) * (1.f + 8.f * u);
     }
-    // (C): shape factor of the base triangle; micro-triangles are similar to it up to the vertex rounding `pr`
+    // (C): shape factor kappa = 2 Area / emax^2 of the micro-triangles.  They are the base triangle scaled by 2^-level with every
+    // vertex moved by at most ev = 3.01 u Pmax (A): the area changes by <= 2 ev emax + 2 ev^2, the longest edge by <= 2 ev, so with
+    // rr = ev / emax:  kappa_t >= (kappa - 4 rr - 4 rr^2) / (1 + 2 rr)^2.
     it.pitX = it.pitY = inf;
     const float area2 = fabsf(e[0].x * e[1].y - e[0].y * e[1].x);
     const float kappa = area2 / emax2;
-    const float eminT = sqrtf(emin2) * scale;
-    const float pr = (6.02f * u * Pmax) / eminT;
-    if (kappa >= 0.01f && pr <= kappa * 0.0625f) {
-        const float kEff = 0.7f * kappa;
-        const float rho0 = (5.f * 4.1f * u / (kEff * kEff)) * sqrtf(emax2) * scale * (1.f + pr) * 1.01f;
+    const float emaxT = sqrtf(emax2) * scale;
+    const float rr = (3.02f * u * Pmax) / emaxT;
+    const float kEff = (kappa * (1.f - 8.f * u) - 4.f * rr - 4.f * rr * rr) / ((1.f + 2.f * rr) * (1.f + 2.f * rr)) * (1.f - 8.f * u);
+    if (kEff >= 0.01f) {
+        const float rho0 = (5.f * 4.1f * u / (kEff * kEff)) * emaxT * (1.f + 2.f * rr) * 1.01f;
         it.pitX = rho0 * W + it.epsRegion;
         it.pitY = rho0 * H + it.epsRegion;
     }
@@ -201,8 +212,8 @@ OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, 
             float margin;
             if (mn > 0.f) { s = 1; margin = mn; }
             else if (mx < 0.f) { s = -1; margin = -mx; }
-            else return 0;
-            if (sAll != 0 && sAll != s) return 0;
+            else { OMM_STAT(4); return 0; }
+            if (sAll != 0 && sAll != s) { OMM_STAT(5); return 0; }
             sAll = s;
             // (C) texel centres on the other side must be out of reach of PointInTriangle
             const bool want = s > 0;
@@ -214,13 +225,13 @@ OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, 
                 const bool farT = (fy + 1.f) - hiy >= it.pitY;
                 // corner 0 = (0,0), 1 = (0,1), 2 = (1,1), 3 = (1,0); a corner at local x = 1 is also "left of the region" when the
                 // region starts beyond it, i.e. lox - (fx + 1) >= pit, which implies farL; the four flags below are the cheap subset.
-                if (o0 != want && !(farL || farB)) return 0;
-                if (o1 != want && !(farL || farT)) return 0;
-                if (o2 != want && !(farR || farT)) return 0;
-                if (o3 != want && !(farR || farB)) return 0;
+                if (o0 != want && !(farL || farB)) { OMM_STAT(6); return 0; }
+                if (o1 != want && !(farL || farT)) { OMM_STAT(6); return 0; }
+                if (o2 != want && !(farR || farT)) { OMM_STAT(6); return 0; }
+                if (o3 != want && !(farR || farB)) { OMM_STAT(6); return 0; }
             }
             const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
-            if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, cutoffAbs, qx, qy)) return 0;
+            if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, cutoffAbs, qx, qy)) { OMM_STAT(7); return 0; }
         }
     }
     return sAll;
@@ -279,10 +290,20 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
             edgesCannotHit = MarginBeatsEdgeBound(it, margin, al, be, ga, de, gmaxAbs, fabsf(P.cutoff), qx, qy);
         }
     }
+#if defined(OMM_HIER_STATS)
+    g_hierStats[0]++;
+    if (s != 0) g_hierStats[1]++;
+    if (edgesCannotHit) g_hierStats[2]++;
+#endif
     // (E)
     if (edgesCannotHit && !countsMatter) {
         const bool want = s > 0;
-        if (o0 == want && o1 == want && o2 == want && o3 == want && (want ? cov.above : cov.below) != 0) return;
+        if (o0 == want && o1 == want && o2 == want && o3 == want && (want ? cov.above : cov.below) != 0) {
+#if defined(OMM_HIER_STATS)
+            g_hierStats[3]++;
+#endif
+            return;
+        }
     }
     {
         const float ipx = pfx * m.rcpw, ipy = pfy * m.rcph;

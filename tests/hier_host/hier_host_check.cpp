@@ -104,3 +104,9 @@ extern "C" __attribute__((visibility("default"))) int hier_host_check(const void
     else CheckItems<KernelCfg<kAddrGeneric, false>>(P, uvs, levels, numItems, st);
     return st->mismatches == 0 ? 0 : 1;
 }
+
+#if defined(OMM_HIER_STATS)
+extern "C" __attribute__((visibility("default"))) void hier_host_stats(unsigned long long* out) {
+    for (int i = 0; i < 16; ++i) { out[i] = g_hierStats[i]; g_hierStats[i] = 0; }
+}
+#endif
