@@ -593,7 +593,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(128) HierTestInitial(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
                                                         const unsigned long long* __restrict__ regionStart, const unsigned long long* __restrict__ wordStart,
                                                         uint32_t itemBegin, uint32_t itemEnd, unsigned long long regionBegin, unsigned long long regionEnd,
-                                                        HierLists lists, uint32_t* __restrict__ stateWords) {
+                                                        HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
     __shared__ uint32_t sFirstItem;
     const unsigned long long blockRegion = regionBegin + (unsigned long long)blockIdx.x * blockDim.x;
     if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(regionStart + itemBegin, itemEnd - itemBegin, blockRegion);
@@ -614,6 +614,15 @@ __global__ void __launch_bounds__(128) HierTestInitial(const BakeParams P, const
         if (!slow && e > 0) {
             s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, L - e);
             if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+        }
+    }
+    // per item: how many initial regions were proved to lie above / below the cutoff (ItemPostKernel's fast path)
+    {
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? w : 0xFFFFFFFFu);
+        const uint32_t up = __ballot_sync(0xFFFFFFFFu, s > 0) & peers, down = __ballot_sync(0xFFFFFFFFu, s < 0) & peers;
+        if (valid && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) {
+            if (up) atomicAdd(&uniformVotes[2 * (size_t)w], (uint32_t)__popc(up));
+            if (down) atomicAdd(&uniformVotes[2 * (size_t)w + 1], (uint32_t)__popc(down));
         }
     }
     const bool fail = valid && s == 0;
@@ -682,7 +691,7 @@ __global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const Item
 
 struct HierKernels {
     void (*initial)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
-                    unsigned long long, HierLists, uint32_t*);
+                    unsigned long long, HierLists, uint32_t*, uint32_t*);
     void (*list)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, const unsigned long long*, unsigned long long*,
                  unsigned long long*, int, uint32_t*);
     void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
@@ -770,13 +779,68 @@ __device__ __forceinline__ uint64_t Expand3State(uint32_t bits16) {
     return v | ((v >> 1) & 0x0101010101010101ull);
 }
 
+// XXH64(seed 42) of 4^level bytes that all hold the 3-state value v (0, 1 or 3): the digest of every work item whose
+// micro-triangles share one state.  Constants of the algorithm, computed once per process on the host.
+struct UniformDigests {
+    uint64_t h[3][13];  // [0] Transparent, [1] Opaque, [2] either Unknown state (both hash as 3, ref: bake_cpu_impl.cpp:374-377)
+};
+static uint64_t HostRotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+static uint64_t HostXxhRound(uint64_t acc, uint64_t in) { return HostRotl64(acc + in * XP2, 31) * XP1; }
+static uint64_t HostXxhMerge(uint64_t acc, uint64_t v) { return (acc ^ HostXxhRound(0, v)) * XP1 + XP4; }
+static uint64_t HostXxh64Constant(uint8_t value, uint64_t n) {
+    const uint64_t c8 = 0x0101010101010101ull * value;
+    uint64_t h;
+    uint64_t left = n;
+    if (n >= 32) {
+        uint64_t v1 = 42ull + XP1 + XP2, v2 = 42ull + XP2, v3 = 42ull, v4 = 42ull - XP1;
+        for (uint64_t i = 0; i < n / 32; ++i) {
+            v1 = HostXxhRound(v1, c8); v2 = HostXxhRound(v2, c8); v3 = HostXxhRound(v3, c8); v4 = HostXxhRound(v4, c8);
+        }
+        h = HostRotl64(v1, 1) + HostRotl64(v2, 7) + HostRotl64(v3, 12) + HostRotl64(v4, 18);
+        h = HostXxhMerge(h, v1); h = HostXxhMerge(h, v2); h = HostXxhMerge(h, v3); h = HostXxhMerge(h, v4);
+        left = n % 32;
+    } else
+        h = 42ull + XP5;
+    h += n;
+    for (; left >= 8; left -= 8) { h ^= HostXxhRound(0, c8); h = HostRotl64(h, 27) * XP1 + XP4; }
+    if (left >= 4) { h ^= (c8 & 0xFFFFFFFFull) * XP1; h = HostRotl64(h, 23) * XP2 + XP3; left -= 4; }
+    for (; left > 0; --left) { h ^= (uint64_t)value * XP5; h = HostRotl64(h, 11) * XP1; }
+    h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+    return h;
+}
+static const UniformDigests& GetUniformDigests() {
+    static UniformDigests table;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const uint8_t values[3] = {0, 1, 3};
+        for (int v = 0; v < 3; ++v)
+            for (int l = 0; l <= kMaxLevel; ++l) table.h[v][l] = HostXxh64Constant(values[v], 1ull << (2 * l));
+    });
+    return table;
+}
+
 __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
                                                       const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, float rejectionThreshold,
-                                                      int disableSpecial, int keepExistingSpecial, uint64_t* __restrict__ digest, int32_t* special) {
+                                                      int disableSpecial, int keepExistingSpecial, const uint32_t* __restrict__ uniformVotes,
+                                                      const UniformDigests table, uint64_t* __restrict__ digest, int32_t* special) {
     const uint32_t w = itemBegin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= itemEnd) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t level = items[w].level;
+    if (uniformVotes) {
+        // The hierarchical classifier proved all initial regions of the item to be on one side (HierTestInitial): the block is
+        // uniform, its digest is a constant, and nothing has to be read.
+        const uint32_t nInit = level > 3 ? 1u << (2 * (level - 3)) : 1u;
+        const uint32_t above = __ldg(&uniformVotes[2 * (size_t)w]), below = __ldg(&uniformVotes[2 * (size_t)w + 1]);
+        if (above == nInit || below == nInit) {
+            if (lane == 0) {
+                const uint32_t s = (__ldg(stateWords + wordStart[w])) & 3u;
+                digest[w] = table.h[s >= 2 ? 2 : s][level];
+                special[w] = disableSpecial ? 0 : -(int32_t)s - 1;
+            }
+            return;
+        }
+    }
     const uint32_t n = 1u << (2 * level);                       // micro-triangles of the item now (uniformity / rejection test)
     const uint32_t nHash = 1u << (2 * items[w].hashLevel);      // bytes the SDK's digest covers (>= n, differs only after Compress)
     const uint32_t* words = stateWords + wordStart[w];
@@ -1416,6 +1480,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr, *itemNodes = nullptr, *nodeStart = nullptr;
     ShardBound* boundsDev = nullptr;
     uint32_t* stateWords = nullptr;
+    uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;
     int32_t* special = nullptr;
     uint32_t *mergeRoot = nullptr, *survivor2 = nullptr;
@@ -1627,6 +1692,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)chunkRegions * 4));
             CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)chunkRegions * 16));
             CUDA_TRY(scratch.alloc(&lists.count, 4));
+            CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
+            CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
             int sms = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
             const uint32_t listGrid = (uint32_t)std::max(sms, 1) * 16u;
@@ -1635,7 +1702,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             for (unsigned long long r0 = regionBegin; r0 < regionEnd; r0 += chunkRegions) {
                 const unsigned long long r1 = std::min(regionEnd, r0 + chunkRegions);
                 CUDA_TRY(cudaMemsetAsync(lists.count, 0, 4 * sizeof(unsigned long long), stream));
-                hier.initial<<<(uint32_t)((r1 - r0 + 127) / 128), 128, 0, stream>>>(P, items, hierItems, nodeStart, wordStart, itemBegin, itemEnd, r0, r1, lists, stateWords);
+                hier.initial<<<(uint32_t)((r1 - r0 + 127) / 128), 128, 0, stream>>>(P, items, hierItems, nodeStart, wordStart, itemBegin, itemEnd, r0, r1, lists, uniformVotes, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
                 hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
@@ -1660,7 +1727,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         if (itemEnd > itemBegin) {
             // special-index scan + XXH64 of this rank's items (their state words are local already)
             ItemPostKernel<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
-                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, digest, special);
+                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes, GetUniformDigests(), digest, special);
             launches++;
         }
         CUDA_TRY(cudaEventRecord(ev[5], stream));  // end of the per-item post pass
@@ -1775,7 +1842,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             // ref: bake_cpu_impl.cpp:1969-1971 -- second exact dedup over ALL items with the current states, then the last promotion
             // (computed first here; the dedup overwrites duplicates with -1 exactly as the serial order does)
             ItemPostKernel<<<(W + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
-                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, digest, special);
+                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, GetUniformDigests(), digest, special);
             launches += 2;
             if (!disableDup) {
                 FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);

@@ -54,6 +54,8 @@ def cases():
                                                            unknown_state_promotion=A.PROMOTE_NEAREST, uv_lo=0.3, uv_hi=0.7), {})
     c["reuse_uv_and_content"] = (lambda: W.random_mesh(58, 600, reuse_frac=0.5, tex_kind="blocky", tri_texels=6, max_subdivision_level=2), {})
     c["flag_disable_special"] = (lambda: W.random_mesh(61, 300, tex_kind="blocky", tri_texels=5, bake_flags=A.BAKE_DISABLE_SPECIAL_INDICES), {})
+    c["flag_disable_special_levels"] = (lambda: W.random_mesh(74, 400, tex_kind="blocky", tri_texels=4, subdivision_levels=_levels(74, 400, 0, 6),
+                                                              bake_flags=A.BAKE_DISABLE_SPECIAL_INDICES), {})
     c["flag_disable_dup"] = (lambda: W.random_mesh(62, 300, reuse_frac=0.5, tex_kind="blocky", bake_flags=A.BAKE_DISABLE_DUPLICATE_DETECTION), {})
     c["flag_force32"] = (lambda: W.random_mesh(63, 300, bake_flags=A.BAKE_FORCE_32BIT_INDICES), {})
     c["flag_allow8"] = (lambda: W.random_mesh(64, 100, bake_flags=A.BAKE_ALLOW_8BIT_INDICES), {})
