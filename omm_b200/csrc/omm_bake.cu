@@ -589,52 +589,82 @@ __device__ __forceinline__ void HierFillGlobal(uint32_t* __restrict__ words, uin
     else reinterpret_cast<uint8_t*>(words)[idx] = (uint8_t)pat;  // e == 1: four micro-triangles, one byte
 }
 
+// One warp per work item.  The warp first classifies every cell of the item's footprint as a whole (F): the resulting bitmap
+// answers most region tests without touching the texture again, and an item whose cells are all on one side is finished at
+// once (the common case: most triangles do not meet the level line at all).
+constexpr int kHierInitWarps = 4;
 template <class Cfg>
-__global__ void __launch_bounds__(128) HierTestInitial(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
-                                                        const unsigned long long* __restrict__ regionStart, const unsigned long long* __restrict__ wordStart,
-                                                        uint32_t itemBegin, uint32_t itemEnd, unsigned long long regionBegin, unsigned long long regionEnd,
-                                                        HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
-    __shared__ uint32_t sFirstItem;
-    const unsigned long long blockRegion = regionBegin + (unsigned long long)blockIdx.x * blockDim.x;
-    if (threadIdx.x == 0) sFirstItem = itemBegin + FindItem(regionStart + itemBegin, itemEnd - itemBegin, blockRegion);
-    __syncthreads();
-    const unsigned long long region = blockRegion + threadIdx.x;
-    const bool valid = region < regionEnd;
-    uint32_t w = sFirstItem;
-    int s = 0;
-    uint32_t e = 3, idx = 0, L = 0;
-    bool slow = false;
-    if (valid) {
-        while (w + 1 < itemEnd && __ldg(&regionStart[w + 1]) <= region) ++w;
-        idx = (uint32_t)(region - __ldg(&regionStart[w]));
-        const HierItem hi = LoadHierItem(hierItems + w);
-        L = hi.level;
-        e = L < 3 ? L : 3;
-        slow = !hi.ok;
-        if (!slow && e > 0) {
-            s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, L - e);
-            if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+__global__ void __launch_bounds__(kHierInitWarps * 32) HierTestInitial(const BakeParams P, const HierItem* __restrict__ hierItems,
+                                                                       const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
+                                                                       HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
+    __shared__ uint32_t sPlus[kHierInitWarps][32], sMinus[kHierInitWarps][32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t w = itemBegin + blockIdx.x * kHierInitWarps + warp;
+    if (w >= itemEnd) return;
+    const DevMip& m = P.tex.mips[0];
+    const HierItem hi = LoadHierItem(hierItems + w);
+    const uint32_t L = hi.level;
+    const uint32_t e = L < 3 ? L : 3;
+    const uint32_t nInit = L > 3 ? 1u << (2 * (L - 3)) : 1u;
+    uint32_t* words = stateWords + __ldg(&wordStart[w]);
+    if (!hi.ok || e == 0) {
+        // items the shortcuts do not cover list all their 4-regions; a level-0 item is one leaf, listed as 4-region 0
+        const uint32_t n4 = L >= 1 ? 1u << (2 * (L - 1)) : 1u;
+        for (uint32_t base = 0; base < n4; base += 32) HierAppend(lists.q[2], lists.count + 2, base + lane < n4, w, base + lane);
+        return;
+    }
+    // (F) whole-cell bitmap over the item's footprint
+    ItemCellMap map{0, 0, 0, 0, sPlus[warp], sMinus[warp]};
+    RegionBox box;
+    if (L >= 3 && MakeItemBox(m, hi, box) && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
+        const int fw = box.cx1 - box.cx0 + 1, fh = box.cy1 - box.cy0 + 1;
+        sPlus[warp][lane] = 0;
+        sMinus[warp][lane] = 0;
+        __syncwarp();
+        for (int id = (int)lane; id < fw * fh; id += 32) {
+            const int y = id / fw, x = id - y * fw;
+            const int s = WholeCellSide<Cfg>(P, m, hi, box, box.cx0 + x, box.cy0 + y);
+            if (s > 0) atomicOr(&sPlus[warp][y], 1u << x);
+            else if (s < 0) atomicOr(&sMinus[warp][y], 1u << x);
+        }
+        __syncwarp();
+        map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = fw; map.fh = fh;
+        // whole item on one side?
+        const uint32_t rowMask = fw == 32 ? 0xFFFFFFFFu : (1u << fw) - 1u;
+        const bool rowPlus = (int)lane >= fh || sPlus[warp][lane] == rowMask, rowMinus = (int)lane >= fh || sMinus[warp][lane] == rowMask;
+        const bool allPlus = __all_sync(0xFFFFFFFFu, rowPlus), allMinus = __all_sync(0xFFFFFFFFu, rowMinus);
+        if (allPlus || allMinus) {
+            const uint32_t pat = (uint32_t)(allPlus ? P.stateGT : P.stateLE) * 0x55555555u;
+            // one 16-byte group per initial region (64 micro-triangles x 2 bits); the map exists for level >= 3 only
+            for (uint32_t i = lane; i < nInit; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
+            if (lane == 0) uniformVotes[2 * (size_t)w + (allPlus ? 0 : 1)] = nInit;
+            return;
         }
     }
-    // per item: how many initial regions were proved to lie above / below the cutoff (ItemPostKernel's fast path)
-    {
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? w : 0xFFFFFFFFu);
-        const uint32_t up = __ballot_sync(0xFFFFFFFFu, s > 0) & peers, down = __ballot_sync(0xFFFFFFFFu, s < 0) & peers;
-        if (valid && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) {
-            if (up) atomicAdd(&uniformVotes[2 * (size_t)w], (uint32_t)__popc(up));
-            if (down) atomicAdd(&uniformVotes[2 * (size_t)w + 1], (uint32_t)__popc(down));
+    uint32_t votesUp = 0, votesDown = 0;
+    for (uint32_t base = 0; base < nInit; base += 32) {
+        const uint32_t idx = base + lane;
+        const bool valid = idx < nInit;
+        int s = 0;
+        if (valid) {
+            RegionBox rb;
+            if (MakeRegionBox(m, hi, idx, L - e, rb)) {
+                s = LookupCellMap(map, rb);
+                if (s == 0) s = TestRegionBox<Cfg>(P, m, hi, rb);
+            }
+            if (s != 0) HierFillGlobal(words, e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
         }
+        votesUp += __popc(__ballot_sync(0xFFFFFFFFu, s > 0));
+        votesDown += __popc(__ballot_sync(0xFFFFFFFFu, s < 0));
+        const bool fail = valid && s == 0;
+        // e == 3 -> list 0, e == 2 -> list 1, e == 1 -> list 2
+        if (e == 3) HierAppend(lists.q[0], lists.count + 0, fail, w, idx);
+        else if (e == 2) HierAppend(lists.q[1], lists.count + 1, fail, w, idx);
+        else HierAppend(lists.q[2], lists.count + 2, fail, w, idx);
     }
-    const bool fail = valid && s == 0;
-    // e == 3 -> list 0, e == 2 -> list 1, e <= 1 -> list 2 (a level-0 item is one leaf: it is listed as the 4-region 0 of its item).
-    // Items the shortcuts do not cover list all their 4-regions (16, 4 or 1 per initial region).
-    HierAppend(lists.q[0], lists.count + 0, fail && !slow && e == 3, w, idx);
-    HierAppend(lists.q[1], lists.count + 1, fail && !slow && e == 2, w, idx);
-    HierAppend(lists.q[2], lists.count + 2, fail && !slow && e <= 1, w, idx);
-    const uint32_t nSlow = (valid && slow) ? (e >= 2 ? 1u << (2 * (e - 1)) : 1u) : 0u;
-    for (uint32_t k = 0; k < 16; ++k) {
-        if (__ballot_sync(0xFFFFFFFFu, k < nSlow) == 0) break;
-        HierAppend(lists.q[2], lists.count + 2, k < nSlow, w, idx * nSlow + k);
+    if (lane == 0) {
+        uniformVotes[2 * (size_t)w] = votesUp;
+        uniformVotes[2 * (size_t)w + 1] = votesDown;
     }
 }
 
@@ -690,8 +720,7 @@ __global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const Item
 }
 
 struct HierKernels {
-    void (*initial)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, unsigned long long,
-                    unsigned long long, HierLists, uint32_t*, uint32_t*);
+    void (*initial)(const BakeParams, const HierItem*, const unsigned long long*, uint32_t, uint32_t, HierLists, uint32_t*, uint32_t*);
     void (*list)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, const unsigned long long*, unsigned long long*,
                  unsigned long long*, int, uint32_t*);
     void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
@@ -1365,8 +1394,15 @@ struct ShardBound {
     unsigned long long unit, word, node;
     uint32_t item, pad;
 };
+// chunk size actually used: the nominal one, or larger when the rank's regions would need more than kHierMaxChunks chunks
+__host__ __device__ inline unsigned long long HierChunkRegions(unsigned long long totalRegions, unsigned long long nominal);
+constexpr int kHierMaxChunks = 96;  // 96 x 8M initial regions of 64 micro-triangles > the 2^35 micro-triangles a 4 GiB 1-bit array can hold
 // First work item of rank r (r = 0..world): items are split where the running unit count crosses r*U/world, so every
 // rank owns a contiguous run of whole work items and the state words of a rank are contiguous too.
+__host__ __device__ inline unsigned long long HierChunkRegions(unsigned long long totalRegions, unsigned long long nominal) {
+    const unsigned long long need = (totalRegions + kHierMaxChunks - 1) / kHierMaxChunks;
+    return need > nominal ? need : nominal;
+}
 __host__ __device__ inline uint32_t ShardFirstItem(const unsigned long long* unitStart, uint32_t entries, int world, int r) {
     const unsigned long long total = unitStart[entries - 1];
     const unsigned long long target = r >= world ? total : (total / (unsigned long long)world) * (unsigned long long)r;
@@ -1379,8 +1415,24 @@ __host__ __device__ inline uint32_t ShardFirstItem(const unsigned long long* uni
     return lo;
 }
 __global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart,
-                            const unsigned long long* __restrict__ nodeStart, uint32_t entries, int world, ShardBound* __restrict__ bounds) {
+                            const unsigned long long* __restrict__ nodeStart, uint32_t entries, int world, int rank, unsigned long long chunkRegions,
+                            ShardBound* __restrict__ bounds, uint32_t* __restrict__ chunkFirstItem) {
     const int r = threadIdx.x;
+    {
+        // chunks of the hierarchical classifier: runs of whole work items of this rank holding about `chunkRegions` initial regions each
+        const uint32_t ib = ShardFirstItem(unitStart, entries, world, rank), ie = ShardFirstItem(unitStart, entries, world, rank + 1);
+        if (r <= kHierMaxChunks) {
+            chunkRegions = HierChunkRegions(nodeStart[ie] - nodeStart[ib], chunkRegions);
+            const unsigned long long target = nodeStart[ib] + (unsigned long long)r * chunkRegions;
+            uint32_t lo = ib, hi = ie;  // smallest item in [ib, ie] whose first region is >= target
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (nodeStart[mid] >= target) hi = mid;
+                else lo = mid + 1;
+            }
+            chunkFirstItem[r] = lo;
+        }
+    }
     if (r > world) return;
     const uint32_t lo = ShardFirstItem(unitStart, entries, world, r);
     bounds[r].item = lo;
@@ -1479,6 +1531,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     ItemRec* items = nullptr;
     unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr, *itemNodes = nullptr, *nodeStart = nullptr;
     ShardBound* boundsDev = nullptr;
+    uint32_t* chunkFirstDev = nullptr;
+    uint32_t chunkFirst[kHierMaxChunks + 1];
     uint32_t* stateWords = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;
@@ -1563,6 +1617,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&triItem, T));
         CUDA_TRY(scratch.alloc(&triFinal, T));
         CUDA_TRY(scratch.alloc(&boundsDev, 65));
+        CUDA_TRY(scratch.alloc(&chunkFirstDev, kHierMaxChunks + 1));
         CUDA_TRY(cudaMemsetAsync(counters, 0, 32 * sizeof(uint32_t), stream));
         CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
         SetupTriangles<<<gridT, TPB, 0, stream>>>(sa, triUV, triLevel, triFormat, triDegenerate, fixList, counters);
@@ -1640,10 +1695,11 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemNodes, nodeStart, (int)T + 1, stream));
             launches += 6;
         }
-        ShardBounds<<<1, 96, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, world, boundsDev);
+        ShardBounds<<<1, 128, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, world, rank, (unsigned long long)kHierChunkRegions, boundsDev, chunkFirstDev);
         launches++;
         CUDA_TRY(cudaMemcpyAsync(countersHost, counters, sizeof(countersHost), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (world + 1), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(chunkFirst, chunkFirstDev, sizeof(chunkFirst), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(&totalUnits, unitStart + T, 8, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(&totalWords, wordStart + T, 8, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
@@ -1683,14 +1739,15 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
         if (itemEnd > itemBegin && useHier) {
+            // worst case of a chunk: kHierChunkRegions initial regions plus the rest of its last item (at most 4^9 regions at level 12)
             const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
-            const unsigned long long chunkRegions = std::min<unsigned long long>(kHierChunkRegions, regionEnd - regionBegin);
+            const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, kHierChunkRegions) + (1ull << 18), regionEnd - regionBegin);
             HierItem* hierItems = nullptr;
             HierLists lists{};
             CUDA_TRY(scratch.alloc(&hierItems, W));
-            CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)chunkRegions));
-            CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)chunkRegions * 4));
-            CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)chunkRegions * 16));
+            CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
+            CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
+            CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
             CUDA_TRY(scratch.alloc(&lists.count, 4));
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
@@ -1699,10 +1756,12 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             const uint32_t listGrid = (uint32_t)std::max(sms, 1) * 16u;
             HierPrepare<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, itemBegin, itemEnd, hierItems);
             launches++;
-            for (unsigned long long r0 = regionBegin; r0 < regionEnd; r0 += chunkRegions) {
-                const unsigned long long r1 = std::min(regionEnd, r0 + chunkRegions);
+            for (int c = 0; c < kHierMaxChunks; ++c) {
+                const uint32_t i0 = chunkFirst[c], i1 = chunkFirst[c + 1];
+                if (i0 >= itemEnd) break;
+                if (i1 <= i0) continue;
                 CUDA_TRY(cudaMemsetAsync(lists.count, 0, 4 * sizeof(unsigned long long), stream));
-                hier.initial<<<(uint32_t)((r1 - r0 + 127) / 128), 128, 0, stream>>>(P, items, hierItems, nodeStart, wordStart, itemBegin, itemEnd, r0, r1, lists, uniformVotes, stateWords);
+                hier.initial<<<(i1 - i0 + kHierInitWarps - 1) / kHierInitWarps, kHierInitWarps * 32, 0, stream>>>(P, hierItems, wordStart, i0, i1, lists, uniformVotes, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
                 hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);

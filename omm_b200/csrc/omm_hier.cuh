@@ -166,20 +166,99 @@ OMM_HD bool MarginBeatsEdgeBound(const HierItem& it, float margin, float al, flo
     return ok;
 }
 
-// Returns +1 / -1 when every micro-triangle of the region (bird index `index` at subdivision level `regionLevel` of the
-// work item; regionLevel == it.level means a single micro-triangle) is provably on that side of the cutoff, 0 otherwise.
-template <class Cfg>
-OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, uint32_t regionLevel) {
+// r-space enclosure [lo, hi] of a region (A).  Returns false when the coordinates are not moderate finite numbers.
+struct RegionBox {
+    float lox, loy, hix, hiy;
+    int cx0, cy0, cx1, cy1;  // footprint cells
+};
+OMM_HD bool MakeRegionBox(const DevMip& m, const HierItem& it, uint32_t index, uint32_t regionLevel, RegionBox& rb) {
     const Tri rt = MicroTri(it.p0, it.p1, it.p2, index, regionLevel);
     const float W = (float)m.w, H = (float)m.h;
     const float eps = regionLevel == it.level ? it.epsSingle : it.epsRegion;
     const float r0x = rt.p0.x * W + -0.5f, r0y = rt.p0.y * H + -0.5f;
     const float r1x = rt.p1.x * W + -0.5f, r1y = rt.p1.y * H + -0.5f;
     const float r2x = rt.p2.x * W + -0.5f, r2y = rt.p2.y * H + -0.5f;
-    const float lox = fminf(fminf(r0x, r1x), r2x) - eps, loy = fminf(fminf(r0y, r1y), r2y) - eps;
-    const float hix = fmaxf(fmaxf(r0x, r1x), r2x) + eps, hiy = fmaxf(fmaxf(r0y, r1y), r2y) + eps;
-    if (!(lox > -2097152.f && loy > -2097152.f && hix < 2097152.f && hiy < 2097152.f)) return 0;
-    const int cx0 = (int)floorf(lox), cy0 = (int)floorf(loy), cx1 = (int)floorf(hix), cy1 = (int)floorf(hiy);
+    rb.lox = fminf(fminf(r0x, r1x), r2x) - eps; rb.loy = fminf(fminf(r0y, r1y), r2y) - eps;
+    rb.hix = fmaxf(fmaxf(r0x, r1x), r2x) + eps; rb.hiy = fmaxf(fmaxf(r0y, r1y), r2y) + eps;
+    if (!(rb.lox > -2097152.f && rb.loy > -2097152.f && rb.hix < 2097152.f && rb.hiy < 2097152.f)) return false;
+    rb.cx0 = (int)floorf(rb.lox); rb.cy0 = (int)floorf(rb.loy); rb.cx1 = (int)floorf(rb.hix); rb.cy1 = (int)floorf(rb.hiy);
+    return true;
+}
+
+// (F) Whole-cell test for a work item: +1 / -1 when the cell passes (B) and (C) with B = the whole cell [0,1]^2, all four
+//     texels on side s, and Q = the largest cell-local coordinate any vertex of the ITEM can have (`box` is the item's
+//     region box widened by one more eps, so it contains the region box of every sub-region).  Every sub-region's B is a
+//     subset of the cell and its Q is smaller, and R grows with Q, so such a cell passes the test of EVERY region of the item
+//     with the same s: TestRegion may take the answer from a per-item bitmap of these cells (HierTestInitial) instead of
+//     evaluating it.
+template <class Cfg>
+OMM_HD int WholeCellSide(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& box, int cx, int cy) {
+    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx, m.w, m.log2w), x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx + 1, m.w, m.log2w);
+    const int y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy, m.h, m.log2h), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy + 1, m.h, m.log2h);
+    const float gx = TexFetch<Cfg>(P, m, x0, y0);
+    const float gy = TexFetch<Cfg>(P, m, x0, y1);
+    const float gz = TexFetch<Cfg>(P, m, x1, y1);
+    const float gw = TexFetch<Cfg>(P, m, x1, y0);
+    const bool o0 = P.cutoff < gx, o1 = P.cutoff < gy, o2 = P.cutoff < gz, o3 = P.cutoff < gw;
+    if (o0 != o1 || o0 != o2 || o0 != o3) return 0;
+    const float a = gx - P.cutoff;
+    const float b = gw - gx;
+    const float c = gy - gx;
+    const float d = gx + gz - gy - gw;
+    // h at the four cell corners, evaluated like TestRegion does for B = [0,1]^2
+    const float h00 = a, h10 = a + b, h01 = a + c, h11 = (a + b) + (c + d);
+    const float mn = fminf(fminf(h00, h01), fminf(h10, h11)), mx = fmaxf(fmaxf(h00, h01), fmaxf(h10, h11));
+    int s;
+    float margin;
+    if (mn > 0.f) { s = 1; margin = mn; }
+    else if (mx < 0.f) { s = -1; margin = -mx; }
+    else return 0;
+    if ((s > 0) != o0) return 0;
+    const float fx = (float)cx, fy = (float)cy;
+    const float qx = fmaxf(fabsf(box.lox - fx), fabsf(box.hix - fx)) + it.deltaEdge;
+    const float qy = fmaxf(fabsf(box.loy - fy), fabsf(box.hiy - fy)) + it.deltaEdge;
+    const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
+    if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, fabsf(P.cutoff), qx, qy)) return 0;
+    return s;
+}
+
+// Bitmap of whole-cell sides over the footprint of an item (at most 32 x 32 cells): bit x of plus[y] / minus[y].
+struct ItemCellMap {
+    int cx0, cy0, fw, fh;  // fw == 0: no map
+    const uint32_t* plus;
+    const uint32_t* minus;
+};
+// Item box: region box of the whole item (bird index 0 at level 0) widened by one more eps.
+OMM_HD bool MakeItemBox(const DevMip& m, const HierItem& it, RegionBox& box) {
+    HierItem whole = it;
+    whole.level = 0xFFFFFFFFu;  // forces epsRegion in MakeRegionBox
+    if (!MakeRegionBox(m, whole, 0, 0, box)) return false;
+    box.lox -= it.epsRegion; box.loy -= it.epsRegion; box.hix += it.epsRegion; box.hiy += it.epsRegion;
+    box.cx0 = (int)floorf(box.lox); box.cy0 = (int)floorf(box.loy); box.cx1 = (int)floorf(box.hix); box.cy1 = (int)floorf(box.hiy);
+    return true;
+}
+// +1 / -1 when every footprint cell of the region box is a whole-cell pass of that side, else 0
+OMM_HD int LookupCellMap(const ItemCellMap& map, const RegionBox& rb) {
+    if (map.fw == 0) return 0;
+    const int x0 = rb.cx0 - map.cx0, x1 = rb.cx1 - map.cx0, y0 = rb.cy0 - map.cy0, y1 = rb.cy1 - map.cy0;
+    if (x0 < 0 || y0 < 0 || x1 >= map.fw || y1 >= map.fh) return 0;
+    const uint32_t cols = (x1 - x0 == 31 ? 0xFFFFFFFFu : ((1u << (x1 - x0 + 1)) - 1u)) << x0;
+    uint32_t allPlus = cols, allMinus = cols;
+    for (int y = y0; y <= y1; ++y) {
+        allPlus &= map.plus[y];
+        allMinus &= map.minus[y];
+    }
+    if (allPlus == cols) return 1;
+    if (allMinus == cols) return -1;
+    return 0;
+}
+
+// Returns +1 / -1 when every micro-triangle of the region (bird index `index` at subdivision level `regionLevel` of the
+// work item; regionLevel == it.level means a single micro-triangle) is provably on that side of the cutoff, 0 otherwise.
+template <class Cfg>
+OMM_HD int TestRegionBox(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& rb) {
+    const float lox = rb.lox, loy = rb.loy, hix = rb.hix, hiy = rb.hiy;
+    const int cx0 = rb.cx0, cy0 = rb.cy0, cx1 = rb.cx1, cy1 = rb.cy1;
     if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kHierMaxCells) return 0;
     const float delta = it.deltaEdge;
     const float cutoffAbs = fabsf(P.cutoff);
@@ -235,6 +314,12 @@ OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, 
         }
     }
     return sAll;
+}
+template <class Cfg>
+OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, uint32_t regionLevel) {
+    RegionBox rb;
+    if (!MakeRegionBox(m, it, index, regionLevel, rb)) return 0;
+    return TestRegionBox<Cfg>(P, m, it, rb);
 }
 
 

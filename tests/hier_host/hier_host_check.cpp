@@ -23,7 +23,7 @@ struct HierCheckStats {
 
 template <class Cfg>
 static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, uint32_t nodeInItem, uint32_t nl, uint32_t e, uint32_t idx, uint8_t* states,
-                    HierCheckStats* st, const float2* uv, bool degenerate) {
+                    HierCheckStats* st, const float2* uv, bool degenerate, const ItemCellMap* map = nullptr) {
     const uint32_t L = hi.level;
     if (e == 0) {  // leaves: the reference walk with the exact skips of LeafCell (slow path for items the shortcuts do not cover)
         st->fullEvals++;
@@ -33,7 +33,13 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, ui
     }
     int s = 0;
     st->tests[3 - e]++;
-    if (hi.ok) s = TestRegion<Cfg>(P, m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e);
+    if (hi.ok) {
+        RegionBox rb;
+        if (MakeRegionBox(m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e, rb)) {
+            if (map) s = LookupCellMap(*map, rb);  // initial regions only, like HierTestInitial
+            if (s == 0) s = TestRegionBox<Cfg>(P, m, hi, rb);
+        }
+    }
     if (s != 0) {
         st->passes[3 - e]++;
         const uint32_t n = 1u << (2 * e);
@@ -55,9 +61,22 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
         const uint32_t nl = L < 6 ? L : 6;
         const uint32_t nodes = L > 6 ? 1u << (2 * (L - 6)) : 1u;
         const uint32_t e0 = nl < 3 ? nl : 3;
+        // whole-cell bitmap of the item (F), as HierTestInitial builds it
+        uint32_t plus[32] = {0}, minus[32] = {0};
+        ItemCellMap map{0, 0, 0, 0, plus, minus};
+        RegionBox box;
+        if (hi.ok && L >= 3 && MakeItemBox(m, hi, box) && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
+            map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = box.cx1 - box.cx0 + 1; map.fh = box.cy1 - box.cy0 + 1;
+            for (int y = 0; y < map.fh; ++y)
+                for (int x = 0; x < map.fw; ++x) {
+                    const int s = WholeCellSide<Cfg>(P, m, hi, box, box.cx0 + x, box.cy0 + y);
+                    if (s > 0) plus[y] |= 1u << x;
+                    else if (s < 0) minus[y] |= 1u << x;
+                }
+        }
         for (uint32_t node = 0; node < nodes; ++node) {
             const uint32_t nInit = 1u << (2 * (nl - e0));
-            for (uint32_t r = 0; r < nInit; ++r) Descend<Cfg>(P, m, hi, node, nl, e0, r, states.data(), st, uv, degenerate);
+            for (uint32_t r = 0; r < nInit; ++r) Descend<Cfg>(P, m, hi, node, nl, e0, r, states.data(), st, uv, degenerate, e0 == 3 ? &map : nullptr);
             const uint32_t n = 1u << (2 * nl);
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t index = (node << (2 * nl)) + i;
