@@ -693,9 +693,17 @@ __global__ void __launch_bounds__(128) HierTestList(const BakeParams P, const Hi
     }
 }
 
+// Queue of deferred edge tests (LeafCell): (item, micro-triangle, cell).  When it is full the tests are evaluated in place.
+struct HierEdgeQueue {
+    uint4* entries;
+    unsigned long long* count;
+    unsigned long long capacity;
+};
+
 template <class Cfg>
 __global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
-                                                   const unsigned long long* __restrict__ wordStart, HierLists lists, uint32_t* __restrict__ stateWords) {
+                                                   const unsigned long long* __restrict__ wordStart, HierLists lists, HierEdgeQueue queue,
+                                                   uint32_t* __restrict__ stateWords) {
     const unsigned long long total = lists.count[2] * 4ull;
     const unsigned long long rounded = (total + 31ull) & ~31ull;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
@@ -708,8 +716,12 @@ __global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const Item
             const HierItem hi = LoadHierItem(hierItems + w);
             uint32_t st = 0;
             if (index < (1u << (2 * hi.level))) {  // a level-0 item has one micro-triangle in its only "4-region"
-                if (hi.ok) st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
-                else st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, hi.p0, hi.p1, hi.p2, items[w].degenerate != 0, index, hi.level);
+                if (hi.ok) {
+                    // The edge tests stay in place: queueing them for HierEdgeTests (and a single-micro-triangle TestRegion first)
+                    // was measured slower -- both re-derive the vertices and the cell, and the tests diverge just as much there.
+                    st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
+                } else
+                    st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, hi.p0, hi.p1, hi.p2, items[w].degenerate != 0, index, hi.level);
             }
             bits = st << (2 * k);
         }
@@ -719,15 +731,33 @@ __global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const Item
     }
 }
 
+// The queued edge tests, one per thread.  A hit makes the micro-triangle Unknown (see LeafEdgeTests).
+template <class Cfg>
+__global__ void __launch_bounds__(128) HierEdgeTests(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+                                                      HierEdgeQueue queue, uint32_t* __restrict__ stateWords) {
+    const unsigned long long n = *queue.count < queue.capacity ? *queue.count : queue.capacity;
+    const uint32_t unknown = (uint32_t)StateFromCoverage(P, 1, 1);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 e = queue.entries[t];
+        const HierItem hi = LoadHierItem(hierItems + e.x);
+        if (!LeafEdgeTests<Cfg>(P, P.tex.mips[0], hi, e.y, (int)e.z, (int)e.w)) continue;
+        uint32_t* word = stateWords + __ldg(&wordStart[e.x]) + (e.y >> 4);
+        const uint32_t shift = 2u * (e.y & 15u);
+        if (unknown != 3u) atomicAnd(word, ~(3u << shift));
+        if (unknown != 0u) atomicOr(word, unknown << shift);
+    }
+}
+
 struct HierKernels {
     void (*initial)(const BakeParams, const HierItem*, const unsigned long long*, uint32_t, uint32_t, HierLists, uint32_t*, uint32_t*);
     void (*list)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, const unsigned long long*, unsigned long long*,
                  unsigned long long*, int, uint32_t*);
-    void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
+    void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, HierEdgeQueue, uint32_t*);
+    void (*edgeTests)(const BakeParams, const HierItem*, const unsigned long long*, HierEdgeQueue, uint32_t*);
 };
 template <class Cfg>
 static HierKernels MakeHierKernels() {
-    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>};
+    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierEdgeTests<Cfg>};
 }
 
 // OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
@@ -1748,7 +1778,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
             CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
             CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
-            CUDA_TRY(scratch.alloc(&lists.count, 4));
+            CUDA_TRY(scratch.alloc(&lists.count, 4));  // [3] counts the queued edge tests
+            HierEdgeQueue queue{};  // unused: see HierLeaves
+            queue.capacity = 0;
+            queue.count = lists.count + 3;
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
             int sms = 0;
@@ -1764,7 +1797,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 hier.initial<<<(i1 - i0 + kHierInitWarps - 1) / kHierInitWarps, kHierInitWarps * 32, 0, stream>>>(P, hierItems, wordStart, i0, i1, lists, uniformVotes, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
-                hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
+                hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
                 launches += 4;
             }
         } else if (itemEnd > itemBegin) {

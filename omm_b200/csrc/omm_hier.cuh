@@ -168,6 +168,8 @@ OMM_HD bool MarginBeatsEdgeBound(const HierItem& it, float margin, float al, flo
 
 // r-space enclosure [lo, hi] of a region (A).  Returns false when the coordinates are not moderate finite numbers.
 struct RegionBox {
+    float r0x, r0y, r1x, r1y, r2x, r2y;  // r-space corners of the region triangle
+    float eps;                           // the enclosure slack that was applied
     float lox, loy, hix, hiy;
     int cx0, cy0, cx1, cy1;  // footprint cells
 };
@@ -178,6 +180,8 @@ OMM_HD bool MakeRegionBox(const DevMip& m, const HierItem& it, uint32_t index, u
     const float r0x = rt.p0.x * W + -0.5f, r0y = rt.p0.y * H + -0.5f;
     const float r1x = rt.p1.x * W + -0.5f, r1y = rt.p1.y * H + -0.5f;
     const float r2x = rt.p2.x * W + -0.5f, r2y = rt.p2.y * H + -0.5f;
+    rb.r0x = r0x; rb.r0y = r0y; rb.r1x = r1x; rb.r1y = r1y; rb.r2x = r2x; rb.r2y = r2y;
+    rb.eps = eps;
     rb.lox = fminf(fminf(r0x, r1x), r2x) - eps; rb.loy = fminf(fminf(r0y, r1y), r2y) - eps;
     rb.hix = fmaxf(fmaxf(r0x, r1x), r2x) + eps; rb.hiy = fmaxf(fmaxf(r0y, r1y), r2y) + eps;
     if (!(rb.lox > -2097152.f && rb.loy > -2097152.f && rb.hix < 2097152.f && rb.hiy < 2097152.f)) return false;
@@ -291,7 +295,27 @@ OMM_HD int TestRegionBox(const BakeParams& P, const DevMip& m, const HierItem& i
             float margin;
             if (mn > 0.f) { s = 1; margin = mn; }
             else if (mx < 0.f) { s = -1; margin = -mx; }
-            else { OMM_STAT(4); return 0; }
+            else if (cx0 == cx1 && cy0 == cy1) {
+                // (G) The whole region lies in this one cell: bound h over the region TRIANGLE instead of its bounding box.  Every
+                // vertex of the region is within eps of the triangle T spanned by the three corner positions q_i (A), and a
+                // reported intersection within delta of such an edge (B).  Along a segment h deviates from the chord by at most
+                // |d| |dx dy| / 4; a point of T lies on a segment from q_0 to a point of the opposite edge, so over T
+                //     s h >= min_i s h(q_i) - |d| wx wy / 2,
+                // and moving eps + delta away costs at most (eps + delta)(|b| + |c| + |d|(Qx + Qy)).  The float evaluation of
+                // h(q_i) is off by <= 8 u (|a'| + |b| Qx + |c| Qy + |d| Qx Qy).
+                const float q0x = rb.r0x - fx, q0y = rb.r0y - fy, q1x = rb.r1x - fx, q1y = rb.r1y - fy, q2x = rb.r2x - fx, q2y = rb.r2y - fy;
+                const float v0 = (a + b * q0x) + (c + d * q0x) * q0y;
+                const float v1 = (a + b * q1x) + (c + d * q1x) * q1y;
+                const float v2 = (a + b * q2x) + (c + d * q2x) * q2y;
+                if (v0 > 0.f && v1 > 0.f && v2 > 0.f) s = 1;
+                else if (v0 < 0.f && v1 < 0.f && v2 < 0.f) s = -1;
+                else { OMM_STAT(4); return 0; }
+                const float al = fabsf(a), be = fabsf(b), ga = fabsf(c), de = fabsf(d);
+                const float wx = hix - lox, wy = hiy - loy;
+                const float pad = 0.505f * de * wx * wy + 2.f * (rb.eps + delta) * (be + ga + de * (qx + qy)) +
+                                  8.f * kUnitRoundoff * (al + be * qx + ga * qy + de * qx * qy);
+                margin = fminf(fminf(fabsf(v0), fabsf(v1)), fabsf(v2)) - pad;
+            } else { OMM_STAT(4); return 0; }
             if (sAll != 0 && sAll != s) { OMM_STAT(5); return 0; }
             sAll = s;
             // (C) texel centres on the other side must be out of reach of PointInTriangle
@@ -334,8 +358,10 @@ OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, 
 // (E) Votes that cannot matter.  Unless the promotion is Nearest the state depends only on which counters are non-zero
 //     (bake_kernels_cpu.h:27-50).  In a cell whose four texels are on side s, where side s has been voted already and the
 //     edge filter holds, the corner and flat-patch branches can only vote s again: the whole cell is skipped.
-template <class Cfg>
-OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, const Tri& tri, int px, int py, Coverage& cov, bool countsMatter) {
+// `defer(px, py)` may take over the three edge tests of this cell (HierLeaves queues them for HierEdgeTests so that the
+// expensive divisions and square roots run densely packed); it returns false to have them evaluated here.
+template <class Cfg, class Defer>
+OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, const Tri& tri, int px, int py, Coverage& cov, bool countsMatter, Defer&& defer) {
     const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
     const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
     const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
@@ -408,16 +434,41 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
         return;
     }
     if (edgesCannotHit) return;
+    if (!countsMatter && defer(px, py)) return;
     if (EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d)) {
         cov.above += 1;
         cov.below += 1;
     }
 }
 
+// The deferred part of LeafCell: the three edge tests of micro-triangle `index` in cell (px, py), same operands as above.
+// A hit votes for both sides; unless the promotion is Nearest (never deferred) the state then is StateFromCoverage(1, 1)
+// whatever else was voted, so the caller simply overwrites the state LeafClassify stored.
+template <class Cfg>
+OMM_HD bool LeafEdgeTests(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, int px, int py) {
+    const Tri tri = MicroTri(it.p0, it.p1, it.p2, index, it.level);
+    const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
+    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
+    const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
+    const float gx = TexFetch<Cfg>(P, m, x0, y0);
+    const float gy = TexFetch<Cfg>(P, m, x0, y1);
+    const float gz = TexFetch<Cfg>(P, m, x1, y1);
+    const float gw = TexFetch<Cfg>(P, m, x1, y0);
+    const float b = gw - gx;
+    const float c = gy - gx;
+    const float d = gx + gz - gy - gw;
+    const float sx = (float)m.w, sy = (float)m.h;
+    const float h0 = gx - P.cutoff;
+    const float2 q0 = make_float2(sx * tri.p0.x - pfx, sy * tri.p0.y - pfy);
+    const float2 q1 = make_float2(sx * tri.p1.x - pfx, sy * tri.p1.y - pfy);
+    const float2 q2 = make_float2(sx * tri.p2.x - pfx, sy * tri.p2.y - pfy);
+    return EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d);
+}
+
 // One micro-triangle of a non-degenerate work item, Linear filter, level-line test, single mip, no SAT pass
 // (ref: bake_cpu_impl.cpp:861-908 with ResampleFine's Normal path).
-template <class Cfg>
-OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index) {
+template <class Cfg, class Defer>
+OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, Defer&& defer) {
     const Tri st = MicroTri(it.p0, it.p1, it.p2, index, it.level);
     Coverage cov{0u, 0u};
     const bool countsMatter = P.promotion == ommUnknownStatePromotion_Nearest;
@@ -427,10 +478,17 @@ OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it
     RasterCursor cur = RasterBegin(rs);
     int x, y;
     while (RasterNext(rs, cur, x, y)) {
-        LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter);
+        LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter, defer);
         if (!countsMatter && cov.above != 0 && cov.below != 0) break;  // exact early-out, see ClassifyMicroTriangle
     }
     return StateFromCoverage(P, cov.above, cov.below);
+}
+struct NeverDefer {
+    OMM_HD bool operator()(int, int) const { return false; }
+};
+template <class Cfg>
+OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index) {
+    return LeafClassify<Cfg>(P, m, it, index, NeverDefer());
 }
 
 }  // namespace ommb200

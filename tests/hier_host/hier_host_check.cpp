@@ -5,6 +5,7 @@
 // the exact shortcuts (TestRegion) without a GPU.  Never linked into libomm-b200.so.
 #include <cstdint>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../../omm_b200/csrc/omm_hier.cuh"
@@ -28,7 +29,29 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, ui
     if (e == 0) {  // leaves: the reference walk with the exact skips of LeafCell (slow path for items the shortcuts do not cover)
         st->fullEvals++;
         const uint32_t index = (nodeInItem << (2 * nl)) + idx;
-        states[idx] = (uint8_t)(hi.ok ? LeafClassify<Cfg>(P, m, hi, index) : ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L));
+        if (hi.ok) {
+            st->tests[3]++;
+            const int s = TestRegion<Cfg>(P, m, hi, index, L);  // quick single-micro-triangle proof, as HierLeaves tries it first
+            if (s != 0) {
+                st->passes[3]++;
+                states[idx] = (uint8_t)(s > 0 ? P.stateGT : P.stateLE);
+                return;
+            }
+        }
+        if (hi.ok) {
+            // as HierLeaves + HierEdgeTests: the edge tests are queued and evaluated afterwards; any hit overwrites the state
+            std::vector<std::pair<int, int>> queued;
+            auto defer = [&](int px, int py) {
+                if ((index + (uint32_t)px) % 5u == 0) return false;  // exercise the "queue full -> evaluate in place" path too
+                queued.push_back({px, py});
+                return true;
+            };
+            int state = LeafClassify<Cfg>(P, m, hi, index, defer);
+            for (auto& q : queued)
+                if (LeafEdgeTests<Cfg>(P, m, hi, index, q.first, q.second)) state = StateFromCoverage(P, 1, 1);
+            states[idx] = (uint8_t)state;
+        } else
+            states[idx] = (uint8_t)ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L);
         return;
     }
     int s = 0;
