@@ -1,7 +1,9 @@
 #!/bin/bash
-# Evidence pass: launch list of the default bench command + full ncu capture of the dominant kernel.
+# Evidence pass: launch list (time + DRAM bytes) of the default bench command, full ncu capture of the dominant kernel.
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ClassifyKernel -s 1 -c 1 -o gpurun_out/prof_classify -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out | tail -5
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+tail -2 gpurun_out/ncu_launches.log
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:HierLeaves -s 2 -c 1 -o gpurun_out/prof_HierLeaves -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+tail -2 gpurun_out/ncu_full.log
+ls -la gpurun_out | tail -6

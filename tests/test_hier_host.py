@@ -1,0 +1,124 @@
+"""Host-side fuzz of the exact shortcuts of the hierarchical classifier (omm_b200/csrc/omm_hier.cuh).
+
+tests/hier_host/hier_host_check.cpp compiles the very header the CUDA kernels use for the HOST (g++, -ffp-contract=off),
+runs the descent of HierTestInitial / HierTestList / HierLeaves serially -- whole-cell bitmap (F), region tests (A)-(C),(G),
+leaf walk with the edge filter (D),(E) and the queued edge tests -- and compares every micro-triangle with the plain
+reference walk (ClassifyMicroTriangle), which the GPU parity suite pins to the SDK build byte for byte.  No GPU needed; this
+is test infrastructure, the product has no CPU path.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from omm_b200 import capi
+from omm_b200 import workloads as W
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "hier_host", "libhier_host_check.so")
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("microTriangles", ctypes.c_uint64), ("mismatches", ctypes.c_uint64), ("tests", ctypes.c_uint64 * 4), ("passes", ctypes.c_uint64 * 4),
+                ("fullEvals", ctypes.c_uint64), ("firstBadItem", ctypes.c_uint64), ("firstBadIndex", ctypes.c_uint64), ("firstBadGot", ctypes.c_int32),
+                ("firstBadWant", ctypes.c_int32)]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "hier_host")])
+    return ctypes.CDLL(LIB)
+
+
+def check(lib, tex, uvs, levels, addr=capi.ADDR_WRAP, cutoff=0.5, promotion=capi.PROMOTE_FORCE_OPAQUE, fmt=capi.FORMAT_4_STATE, gt=capi.STATE_O,
+          le=capi.STATE_T, border=0.0):
+    tex = np.ascontiguousarray(tex)
+    uvs = np.ascontiguousarray(uvs, dtype=np.float32)
+    levels = np.ascontiguousarray(levels, dtype=np.uint8)
+    st = Stats()
+    h, w = tex.shape
+    lib.hier_host_check(tex.ctypes.data_as(ctypes.c_void_p), int(tex.dtype == np.float32), w, h, addr, ctypes.c_float(border), ctypes.c_float(cutoff), gt, le,
+                        fmt, promotion, uvs.ctypes.data_as(ctypes.c_void_p), levels.ctypes.data_as(ctypes.c_void_p), len(levels), ctypes.byref(st))
+    assert st.mismatches == 0, (f"{st.mismatches} of {st.microTriangles} micro-triangles differ from the reference walk; first: item {st.firstBadItem} "
+                                f"index {st.firstBadIndex} got {st.firstBadGot} want {st.firstBadWant}")
+    return st
+
+
+def tris(rng, n, size_texels, texsize, lo=0.0, hi=1.0, axis_aligned=False, skinny=False):
+    c = lo + (hi - lo) * rng.random((n, 1, 2))
+    r = size_texels / texsize
+    if axis_aligned:  # two edges parallel to the texel grid: the vertical-edge and steep-slope branches of the edge test
+        base = np.array([[0, 0], [1, 0], [0, 1]], dtype=np.float64)[None] * r * (0.3 + 0.7 * rng.random((n, 1, 1)))
+        flip = rng.integers(0, 4, (n, 1, 1))
+        base = np.where(flip == 1, base * [-1, 1], base)
+        base = np.where(flip == 2, base * [1, -1], base)
+        base = np.where(flip == 3, base[:, :, ::-1], base)
+        uv = c + base
+    else:
+        ang = 2 * np.pi * (rng.random((n, 3)) / 3 + np.arange(3)[None] / 3)
+        rad = r * (0.3 + 0.7 * rng.random((n, 3)))
+        if skinny:
+            rad[:, 2] *= 0.02
+        uv = c + np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=2)
+    return uv.astype(np.float32).reshape(n, 6)
+
+
+def textures(rng):
+    yy, xx = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    return {
+        "noise": W.noise_texture(1024),
+        "noise8": W.noise_texture(512, as_unorm8=True),
+        "smooth": (0.5 + 0.4 * np.sin(xx * 0.11) * np.cos(yy * 0.07) + 0.05 * np.sin(xx * 0.9 + yy * 0.7)).astype(np.float32),
+        "ramp": ((xx + yy) / 510.0).astype(np.float32),
+        "checker": (((xx >> 3) + (yy >> 3)) & 1).astype(np.float32),
+        "nearcut": (0.5 + 1e-6 * rng.standard_normal((128, 128))).astype(np.float32),
+        "npot": W.noise_texture(256)[:200, :173].copy(),
+    }
+
+
+def test_c3_slice_level6(lib):
+    wl = W.config3(num_tris=400, tex_size=4096, level=6)
+    st = check(lib, wl.mips[0], wl.texcoords.reshape(-1, 6), np.full(400, 6))
+    # the point of the hierarchy: almost everything is decided by region tests, only a few per cent reach the leaf walk
+    assert st.fullEvals < 0.08 * st.microTriangles
+    assert st.passes[0] > 0.8 * st.tests[0]
+
+
+@pytest.mark.parametrize("addr", [capi.ADDR_WRAP, capi.ADDR_MIRROR, capi.ADDR_CLAMP, capi.ADDR_BORDER, capi.ADDR_MIRROR_ONCE])
+def test_address_modes(lib, addr):
+    rng = np.random.default_rng(100 + addr)
+    t = textures(rng)
+    check(lib, t["noise"], tris(rng, 120, 6, 1024, -0.5, 1.5), np.full(120, 6), addr=addr, border=0.4)
+    check(lib, t["npot"], tris(rng, 120, 8, 200, -1.0, 2.0), np.full(120, 5), addr=addr, border=0.6)
+
+
+def test_shapes_and_slopes(lib):
+    rng = np.random.default_rng(7)
+    t = textures(rng)
+    check(lib, t["noise"], tris(rng, 150, 6, 1024, axis_aligned=True), np.full(150, 6))
+    check(lib, t["ramp"], tris(rng, 150, 10, 256, axis_aligned=True), np.full(150, 6))
+    check(lib, t["checker"], tris(rng, 150, 9, 256, axis_aligned=True), np.full(150, 5))
+    check(lib, t["noise"], tris(rng, 150, 12, 1024, skinny=True), np.full(150, 6))
+    check(lib, t["smooth"], tris(rng, 150, 6, 256, -0.02, 0.02, axis_aligned=True), np.full(150, 6))   # around the UV origin: tiny ulps
+    check(lib, t["noise"], tris(rng, 150, 6, 1024, 100, 101), np.full(150, 6))                            # far from it: coarse ulps
+    check(lib, t["noise"], tris(rng, 150, 0.7, 1024), np.full(150, 6))                                    # micro-triangles << rounding slack
+
+
+def test_margins_and_formats(lib):
+    rng = np.random.default_rng(8)
+    t = textures(rng)
+    check(lib, t["nearcut"], tris(rng, 100, 5, 128), np.full(100, 5))                # every texel within 1e-6 of the cutoff: nothing may be skipped
+    check(lib, t["smooth"], tris(rng, 150, 10, 256, -0.2, 1.2), np.full(150, 6))
+    check(lib, t["noise8"], tris(rng, 150, 8, 512), np.full(150, 5), promotion=capi.PROMOTE_NEAREST)
+    check(lib, t["noise8"], tris(rng, 150, 8, 512), np.full(150, 5), promotion=capi.PROMOTE_FORCE_TRANSPARENT, fmt=capi.FORMAT_2_STATE)
+    check(lib, t["noise"], tris(rng, 150, 8, 1024), np.full(150, 5), gt=capi.STATE_T, le=capi.STATE_UO, cutoff=0.3)
+
+
+def test_levels(lib):
+    rng = np.random.default_rng(9)
+    t = textures(rng)
+    check(lib, t["noise"], tris(rng, 400, 10, 1024), rng.integers(0, 7, 400))       # levels 0..6: items smaller than one initial region
+    check(lib, t["noise"], tris(rng, 6, 40, 1024), np.full(6, 9))                   # more than 64 initial regions per item
+    check(lib, t["smooth"], tris(rng, 100, 60, 256), np.full(100, 3))               # micro-triangles of many texels: footprints too large to shortcut
