@@ -599,9 +599,10 @@ __global__ void __launch_bounds__(kHierInitWarps * 32) HierTestInitial(const Bak
                                                                        HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
     __shared__ uint32_t sPlus[kHierInitWarps][32], sMinus[kHierInitWarps][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t w = itemBegin + blockIdx.x * kHierInitWarps + warp;
-    if (w >= itemEnd) return;
     const DevMip& m = P.tex.mips[0];
+    // warps stride over the items (a grid of resident blocks): no launch / drain cost per item, no idle warps behind a slow one
+    for (uint32_t w = itemBegin + blockIdx.x * kHierInitWarps + warp; w < itemEnd; w += gridDim.x * kHierInitWarps) {
+    __syncwarp();
     const HierItem hi = LoadHierItem(hierItems + w);
     const uint32_t L = hi.level;
     const uint32_t e = L < 3 ? L : 3;
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(kHierInitWarps * 32) HierTestInitial(const Bak
         // items the shortcuts do not cover list all their 4-regions; a level-0 item is one leaf, listed as 4-region 0
         const uint32_t n4 = L >= 1 ? 1u << (2 * (L - 1)) : 1u;
         for (uint32_t base = 0; base < n4; base += 32) HierAppend(lists.q[2], lists.count + 2, base + lane < n4, w, base + lane);
-        return;
+        continue;
     }
     // (F) whole-cell bitmap over the item's footprint
     ItemCellMap map{0, 0, 0, 0, sPlus[warp], sMinus[warp]};
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kHierInitWarps * 32) HierTestInitial(const Bak
             // one 16-byte group per initial region (64 micro-triangles x 2 bits); the map exists for level >= 3 only
             for (uint32_t i = lane; i < nInit; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
             if (lane == 0) uniformVotes[2 * (size_t)w + (allPlus ? 0 : 1)] = nInit;
-            return;
+            continue;
         }
     }
     uint32_t votesUp = 0, votesDown = 0;
@@ -665,6 +666,7 @@ __global__ void __launch_bounds__(kHierInitWarps * 32) HierTestInitial(const Bak
     if (lane == 0) {
         uniformVotes[2 * (size_t)w] = votesUp;
         uniformVotes[2 * (size_t)w + 1] = votesDown;
+    }
     }
 }
 
@@ -878,28 +880,43 @@ static const UniformDigests& GetUniformDigests() {
     return table;
 }
 
-__global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
+// Four lanes per work item: lane j carries XXH64 accumulator j and consumes bytes [8j, 8j+8) of every 32-byte stripe (= 8 two-bit
+// states = half a state word), so the four accumulators of an item advance in parallel and a warp hashes eight items at once.
+constexpr int kItemPostItemsPerBlock = 64;
+__global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
                                                       const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, float rejectionThreshold,
                                                       int disableSpecial, int keepExistingSpecial, const uint32_t* __restrict__ uniformVotes,
                                                       const UniformDigests table, uint64_t* __restrict__ digest, int32_t* special) {
-    const uint32_t w = itemBegin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= itemEnd) return;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t level = items[w].level;
-    if (uniformVotes) {
-        // The hierarchical classifier proved all initial regions of the item to be on one side (HierTestInitial): the block is
-        // uniform, its digest is a constant, and nothing has to be read.
-        const uint32_t nInit = level > 3 ? 1u << (2 * (level - 3)) : 1u;
-        const uint32_t above = __ldg(&uniformVotes[2 * (size_t)w]), below = __ldg(&uniformVotes[2 * (size_t)w + 1]);
-        if (above == nInit || below == nInit) {
-            if (lane == 0) {
-                const uint32_t s = (__ldg(stateWords + wordStart[w])) & 3u;
-                digest[w] = table.h[s >= 2 ? 2 : s][level];
-                special[w] = disableSpecial ? 0 : -(int32_t)s - 1;
+    // Phase 1, one thread per item of the block's range: items the hierarchical classifier proved uniform (all initial regions on
+    // one side, HierTestInitial) get their constant digest without reading anything; the others are compacted into a list.
+    __shared__ uint32_t sList[kItemPostItemsPerBlock * 4];
+    __shared__ uint32_t sCount;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+    {
+        const uint32_t wi = itemBegin + blockIdx.x * (kItemPostItemsPerBlock * 4) + threadIdx.x;
+        if (wi < itemEnd) {
+            bool done = false;
+            if (uniformVotes) {
+                const uint32_t lv = items[wi].level;
+                const uint32_t nInit = lv > 3 ? 1u << (2 * (lv - 3)) : 1u;
+                const uint32_t above = __ldg(&uniformVotes[2 * (size_t)wi]), below = __ldg(&uniformVotes[2 * (size_t)wi + 1]);
+                if (above == nInit || below == nInit) {
+                    const uint32_t s = (__ldg(stateWords + wordStart[wi])) & 3u;
+                    digest[wi] = table.h[s >= 2 ? 2 : s][lv];
+                    special[wi] = disableSpecial ? 0 : -(int32_t)s - 1;
+                    done = true;
+                }
             }
-            return;
+            if (!done) sList[atomicAdd(&sCount, 1u)] = wi;
         }
     }
+    __syncthreads();
+    // Phase 2, four lanes per listed item
+    const uint32_t lane = threadIdx.x & 31, j = lane & 3u, quadBase = lane & ~3u, quadMask = 0xFu << quadBase;
+    for (uint32_t slot = threadIdx.x >> 2; slot < sCount; slot += kItemPostItemsPerBlock) {
+    const uint32_t w = sList[slot];
+    const uint32_t level = items[w].level;
     const uint32_t n = 1u << (2 * level);                       // micro-triangles of the item now (uniformity / rejection test)
     const uint32_t nHash = 1u << (2 * items[w].hashLevel);      // bytes the SDK's digest covers (>= n, differs only after Compress)
     const uint32_t* words = stateWords + wordStart[w];
@@ -927,36 +944,37 @@ __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict_
         }
         h = XxhAvalanche(h);
     } else {
-        const uint32_t numWords = nHash >> 4;
+        const uint32_t numWords = nHash >> 4;  // a multiple of 4: the block is read 16 bytes (two stripes) at a time
         const uint32_t pattern = s0 * 0x55555555u;
         uint32_t diff = 0;
         known = 0;
-        // accumulator lane j (= threadIdx lane & 3) consumes bytes [8j, 8j+8) of every 32-byte stripe
-        const uint32_t j = lane & 3;
         uint64_t acc = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
-        for (uint32_t base = 0; base < numWords; base += 32) {
-            const uint32_t wi = base + lane;
-            const uint32_t mine = (wi < numWords) ? __ldg(words + wi) : pattern;
-            const uint32_t valid = wi < fullWords ? 0xFFFFFFFFu : ((wi == 0 && n < 16) ? headMask : 0u);
-            diff |= (mine ^ pattern) & valid;
-            known += __popc(~(mine >> 1) & 0x55555555u & valid);
-            const uint32_t stripes = min(16u, (numWords - base) >> 1);
-            for (uint32_t s = 0; s < stripes; ++s) {
-                const uint32_t wsrc = __shfl_sync(0xFFFFFFFFu, mine, 2 * s + (j >> 1));
-                const uint32_t bits16 = (j & 1) ? (wsrc >> 16) : (wsrc & 0xFFFFu);
-                acc = XxhRound(acc, Expand3State(bits16));
+        const uint4* words4 = reinterpret_cast<const uint4*>(words);
+        const uint32_t half = j & 1u, pair = j >> 1;
+        for (uint32_t g = 0; g < (numWords >> 2); ++g) {
+            const uint4 v = __ldg(words4 + g);
+            if (j == 0) {
+                // uniformity / known-state statistics over the first n micro-triangles, once per word
+                const uint32_t wi = 4 * g;
+                const uint32_t m0 = wi < fullWords ? 0xFFFFFFFFu : ((wi == 0 && n < 16) ? headMask : 0u);
+                const uint32_t m1 = wi + 1 < fullWords ? 0xFFFFFFFFu : 0u, m2 = wi + 2 < fullWords ? 0xFFFFFFFFu : 0u, m3 = wi + 3 < fullWords ? 0xFFFFFFFFu : 0u;
+                diff |= ((v.x ^ pattern) & m0) | ((v.y ^ pattern) & m1) | ((v.z ^ pattern) & m2) | ((v.w ^ pattern) & m3);
+                known += __popc(~(v.x >> 1) & 0x55555555u & m0) + __popc(~(v.y >> 1) & 0x55555555u & m1) + __popc(~(v.z >> 1) & 0x55555555u & m2) +
+                         __popc(~(v.w >> 1) & 0x55555555u & m3);
             }
+            const uint32_t a0 = pair ? v.y : v.x, a1 = pair ? v.w : v.z;  // the word of this lane in stripe 2g and in stripe 2g + 1
+            acc = XxhRound(acc, Expand3State(half ? (a0 >> 16) : (a0 & 0xFFFFu)));
+            acc = XxhRound(acc, Expand3State(half ? (a1 >> 16) : (a1 & 0xFFFFu)));
         }
-        allEqual = __reduce_or_sync(0xFFFFFFFFu, diff) == 0;
-        known = __reduce_add_sync(0xFFFFFFFFu, known);
-        const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2),
-                       v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+        allEqual = diff == 0;  // meaningful on lane j == 0 only, which is the lane that writes
+        const uint64_t v1 = __shfl_sync(quadMask, acc, quadBase), v2 = __shfl_sync(quadMask, acc, quadBase + 1), v3 = __shfl_sync(quadMask, acc, quadBase + 2),
+                       v4 = __shfl_sync(quadMask, acc, quadBase + 3);
         h = Rotl64(v1, 1) + Rotl64(v2, 7) + Rotl64(v3, 12) + Rotl64(v4, 18);
         h = XxhMerge(h, v1); h = XxhMerge(h, v2); h = XxhMerge(h, v3); h = XxhMerge(h, v4);
         h += (uint64_t)nHash;
         h = XxhAvalanche(h);
     }
-    if (lane == 0) {
+    if (j == 0) {
         int common = (int)s0;
         if (!allEqual && rejectionThreshold > 0.f) {
             const float frac = (float)known / (float)n;
@@ -969,14 +987,22 @@ __global__ void __launch_bounds__(256) ItemPostKernel(const ItemRec* __restrict_
         // second promotion pass (ref: bake_cpu_impl.cpp:1439-1440): items that already carry a special index are left alone
         if (!(keepExistingSpecial && special[w] != 0)) special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
     }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K6: exact dedup on digests: the lowest item index with a digest survives (ref: bake_cpu_impl.cpp:1043-1063).
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void DigestInsert(const uint64_t* __restrict__ digest, uint32_t numItems, uint64_t* keys, uint32_t* vals, uint64_t mask) {
+    // Most items of a typical bake are uniform and share a handful of digests: lanes with equal digests elect the lowest
+    // item index among themselves first, so the table sees one atomic per distinct digest per warp.
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < numItems) TableInsertMin(keys, vals, mask, digest[w], w);
+    const bool valid = w < numItems;
+    const uint64_t d = valid ? digest[w] : 0ull;
+    const uint32_t active = __ballot_sync(0xFFFFFFFFu, valid);
+    if (!valid) return;
+    const uint32_t peers = __match_any_sync(active, d);
+    if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) TableInsertMin(keys, vals, mask, d, w);  // lowest lane = lowest item index
 }
 __global__ void DigestResolve(const uint64_t* __restrict__ digest, uint32_t numItems, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                               uint64_t mask, int disableDup, uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
@@ -1794,7 +1820,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 if (i0 >= itemEnd) break;
                 if (i1 <= i0) continue;
                 CUDA_TRY(cudaMemsetAsync(lists.count, 0, 4 * sizeof(unsigned long long), stream));
-                hier.initial<<<(i1 - i0 + kHierInitWarps - 1) / kHierInitWarps, kHierInitWarps * 32, 0, stream>>>(P, hierItems, wordStart, i0, i1, lists, uniformVotes, stateWords);
+                hier.initial<<<std::min<uint32_t>((i1 - i0 + kHierInitWarps - 1) / kHierInitWarps, listGrid), kHierInitWarps * 32, 0, stream>>>(P, hierItems, wordStart, i0, i1, lists, uniformVotes, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
                 hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
@@ -1818,7 +1844,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&special, W));
         if (itemEnd > itemBegin) {
             // special-index scan + XXH64 of this rank's items (their state words are local already)
-            ItemPostKernel<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
+            ItemPostKernel<<<(itemEnd - itemBegin + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
                                                                               (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes, GetUniformDigests(), digest, special);
             launches++;
         }
@@ -1933,7 +1959,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             UpdateItemLevels<<<gridW, TPB, 0, stream>>>(items, levelsDev, W);
             // ref: bake_cpu_impl.cpp:1969-1971 -- second exact dedup over ALL items with the current states, then the last promotion
             // (computed first here; the dedup overwrites duplicates with -1 exactly as the serial order does)
-            ItemPostKernel<<<(W + 7) / 8, 256, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
+            ItemPostKernel<<<(W + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
                                                             (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, GetUniformDigests(), digest, special);
             launches += 2;
             if (!disableDup) {
