@@ -589,84 +589,119 @@ __device__ __forceinline__ void HierFillGlobal(uint32_t* __restrict__ words, uin
     else reinterpret_cast<uint8_t*>(words)[idx] = (uint8_t)pat;  // e == 1: four micro-triangles, one byte
 }
 
-// One warp per work item.  The warp first classifies every cell of the item's footprint as a whole (F): the resulting bitmap
-// answers most region tests without touching the texture again, and an item whose cells are all on one side is finished at
-// once (the common case: most triangles do not meet the level line at all).
+// One warp per TASK = 64 consecutive initial regions of the chunk (for items of level 6 that is exactly one work item; a level-12
+// item is 4096 tasks, sixty-four level-3 items share one).  For every item piece in its task the warp first classifies the cells
+// of the piece's footprint as a whole (F): the bitmap answers most region tests without touching the texture again, and a piece
+// whose cells are all on one side is finished at once (the common case: most triangles do not meet the level line at all).
 constexpr int kHierInitWarps = 4;
+constexpr uint32_t kHierTaskRegions = 64;
 template <class Cfg>
-__global__ void __launch_bounds__(kHierInitWarps * 32) HierTestInitial(const BakeParams P, const HierItem* __restrict__ hierItems,
+__global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const BakeParams P, const HierItem* __restrict__ hierItems,
+                                                                       const unsigned long long* __restrict__ regionStart,
                                                                        const unsigned long long* __restrict__ wordStart, uint32_t itemBegin, uint32_t itemEnd,
                                                                        HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
     __shared__ uint32_t sPlus[kHierInitWarps][32], sMinus[kHierInitWarps][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const DevMip& m = P.tex.mips[0];
-    // warps stride over the items (a grid of resident blocks): no launch / drain cost per item, no idle warps behind a slow one
-    for (uint32_t w = itemBegin + blockIdx.x * kHierInitWarps + warp; w < itemEnd; w += gridDim.x * kHierInitWarps) {
-    __syncwarp();
-    const HierItem hi = LoadHierItem(hierItems + w);
-    const uint32_t L = hi.level;
-    const uint32_t e = L < 3 ? L : 3;
-    const uint32_t nInit = L > 3 ? 1u << (2 * (L - 3)) : 1u;
-    uint32_t* words = stateWords + __ldg(&wordStart[w]);
-    if (!hi.ok || e == 0) {
-        // items the shortcuts do not cover list all their 4-regions; a level-0 item is one leaf, listed as 4-region 0
-        const uint32_t n4 = L >= 1 ? 1u << (2 * (L - 1)) : 1u;
-        for (uint32_t base = 0; base < n4; base += 32) HierAppend(lists.q[2], lists.count + 2, base + lane < n4, w, base + lane);
-        continue;
-    }
-    // (F) whole-cell bitmap over the item's footprint
-    ItemCellMap map{0, 0, 0, 0, sPlus[warp], sMinus[warp]};
-    RegionBox box;
-    if (L >= 3 && MakeItemBox(m, hi, box) && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
-        const int fw = box.cx1 - box.cx0 + 1, fh = box.cy1 - box.cy0 + 1;
-        sPlus[warp][lane] = 0;
-        sMinus[warp][lane] = 0;
-        __syncwarp();
-        for (int id = (int)lane; id < fw * fh; id += 32) {
-            const int y = id / fw, x = id - y * fw;
-            const int s = WholeCellSide<Cfg>(P, m, hi, box, box.cx0 + x, box.cy0 + y);
-            if (s > 0) atomicOr(&sPlus[warp][y], 1u << x);
-            else if (s < 0) atomicOr(&sMinus[warp][y], 1u << x);
+    const unsigned long long R0 = __ldg(&regionStart[itemBegin]), R1 = __ldg(&regionStart[itemEnd]);
+    const unsigned long long numTasks = (R1 - R0 + kHierTaskRegions - 1) / kHierTaskRegions;
+    const float itemsPerRegion = (float)(itemEnd - itemBegin) / (float)(R1 - R0);
+    // warps stride over the tasks (a grid of resident blocks)
+    for (unsigned long long task = (unsigned long long)blockIdx.x * kHierInitWarps + warp; task < numTasks; task += (unsigned long long)gridDim.x * kHierInitWarps) {
+        const unsigned long long g0 = R0 + task * kHierTaskRegions, g1 = g0 + kHierTaskRegions < R1 ? g0 + kHierTaskRegions : R1;
+        // item of region g0: exact guess when all items of the chunk have the same level, binary search otherwise
+        uint32_t w;
+        {
+            const uint32_t guess = itemBegin + (uint32_t)((float)(g0 - R0) * itemsPerRegion);
+            w = guess < itemEnd - 1 ? guess : itemEnd - 1;
+            if (!(__ldg(&regionStart[w]) <= g0 && g0 < __ldg(&regionStart[w + 1]))) w = itemBegin + FindItem(regionStart + itemBegin, itemEnd - itemBegin, g0);
         }
-        __syncwarp();
-        map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = fw; map.fh = fh;
-        // whole item on one side?
-        const uint32_t rowMask = fw == 32 ? 0xFFFFFFFFu : (1u << fw) - 1u;
-        const bool rowPlus = (int)lane >= fh || sPlus[warp][lane] == rowMask, rowMinus = (int)lane >= fh || sMinus[warp][lane] == rowMask;
-        const bool allPlus = __all_sync(0xFFFFFFFFu, rowPlus), allMinus = __all_sync(0xFFFFFFFFu, rowMinus);
-        if (allPlus || allMinus) {
-            const uint32_t pat = (uint32_t)(allPlus ? P.stateGT : P.stateLE) * 0x55555555u;
-            // one 16-byte group per initial region (64 micro-triangles x 2 bits); the map exists for level >= 3 only
-            for (uint32_t i = lane; i < nInit; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
-            if (lane == 0) uniformVotes[2 * (size_t)w + (allPlus ? 0 : 1)] = nInit;
-            continue;
-        }
-    }
-    uint32_t votesUp = 0, votesDown = 0;
-    for (uint32_t base = 0; base < nInit; base += 32) {
-        const uint32_t idx = base + lane;
-        const bool valid = idx < nInit;
-        int s = 0;
-        if (valid) {
-            RegionBox rb;
-            if (MakeRegionBox(m, hi, idx, L - e, rb)) {
-                s = LookupCellMap(map, rb);
-                if (s == 0) s = TestRegionBox<Cfg>(P, m, hi, rb);
+        for (; w < itemEnd; ++w) {
+            const unsigned long long ws = __ldg(&regionStart[w]);
+            if (ws >= g1) break;
+            const unsigned long long we = __ldg(&regionStart[w + 1]);
+            // piece = regions [a, b) of item w
+            const uint32_t a = (uint32_t)((g0 > ws ? g0 : ws) - ws), b = (uint32_t)((g1 < we ? g1 : we) - ws);
+            __syncwarp();
+            const HierItem hi = LoadHierItem(hierItems + w);
+            const uint32_t L = hi.level;
+            const uint32_t e = L < 3 ? L : 3;
+            uint32_t* words = stateWords + __ldg(&wordStart[w]);
+            if (!hi.ok || e == 0) {
+                // items the shortcuts do not cover list all their 4-regions (16 per initial region from level 3 on); a level-0 item
+                // is one leaf, listed as 4-region 0
+                const uint32_t per = L >= 3 ? 16u : (L == 2 ? 4u : 1u);
+                const uint32_t n4 = (b - a) * per;
+                for (uint32_t base = 0; base < n4; base += 32) HierAppend(lists.q[2], lists.count + 2, base + lane < n4, w, a * per + base + lane);
+                continue;
             }
-            if (s != 0) HierFillGlobal(words, e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+            // (F) whole-cell bitmap over the footprint of the piece: the whole item, or the aligned node of 64 regions of a bigger item
+            ItemCellMap map{0, 0, 0, 0, sPlus[warp], sMinus[warp]};
+            RegionBox box;
+            bool haveBox = false;
+            if (L >= 3 && a == 0 && b == (uint32_t)(we - ws)) haveBox = MakeItemBox(m, hi, box);
+            else if (L > 6 && (a & 63u) == 0 && b - a == 64) haveBox = MakeNodeBox(m, hi, a >> 6, L - 6, box);
+            if (haveBox) {
+                // (H) the whole piece over a constant area: one table query, whatever its size
+                const int sFlat = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
+                if (sFlat != 0) {
+                    const uint32_t pat = (uint32_t)(sFlat > 0 ? P.stateGT : P.stateLE) * 0x55555555u;
+                    for (uint32_t i = a + lane; i < b; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
+                    if (lane == 0) atomicAdd(&uniformVotes[2 * (size_t)w + (sFlat > 0 ? 0 : 1)], b - a);
+                    continue;
+                }
+            }
+            if (haveBox && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
+                const int fw = box.cx1 - box.cx0 + 1, fh = box.cy1 - box.cy0 + 1;
+                sPlus[warp][lane] = 0;
+                sMinus[warp][lane] = 0;
+                __syncwarp();
+                for (int id = (int)lane; id < fw * fh; id += 32) {
+                    const int y = id / fw, x = id - y * fw;
+                    const int s = WholeCellSide<Cfg>(P, m, hi, box, box.cx0 + x, box.cy0 + y);
+                    if (s > 0) atomicOr(&sPlus[warp][y], 1u << x);
+                    else if (s < 0) atomicOr(&sMinus[warp][y], 1u << x);
+                }
+                __syncwarp();
+                map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = fw; map.fh = fh;
+                // whole piece on one side?
+                const uint32_t rowMask = fw == 32 ? 0xFFFFFFFFu : (1u << fw) - 1u;
+                const bool rowPlus = (int)lane >= fh || sPlus[warp][lane] == rowMask, rowMinus = (int)lane >= fh || sMinus[warp][lane] == rowMask;
+                const bool allPlus = __all_sync(0xFFFFFFFFu, rowPlus), allMinus = __all_sync(0xFFFFFFFFu, rowMinus);
+                if (allPlus || allMinus) {
+                    // one 16-byte group per initial region (64 micro-triangles x 2 bits); boxes exist for level >= 3 only
+                    const uint32_t pat = (uint32_t)(allPlus ? P.stateGT : P.stateLE) * 0x55555555u;
+                    for (uint32_t i = a + lane; i < b; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
+                    if (lane == 0) atomicAdd(&uniformVotes[2 * (size_t)w + (allPlus ? 0 : 1)], b - a);
+                    continue;
+                }
+            }
+            uint32_t votesUp = 0, votesDown = 0;
+            for (uint32_t base = a; base < b; base += 32) {
+                const uint32_t idx = base + lane;
+                const bool valid = idx < b;
+                int s = 0;
+                if (valid) {
+                    RegionBox rb;
+                    if (MakeRegionBox(m, hi, idx, L - e, rb)) {
+                        s = LookupCellMap(map, rb);
+                        if (s == 0) s = TestRegionBox<Cfg>(P, m, hi, rb);
+                    }
+                    if (s != 0) HierFillGlobal(words, e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+                }
+                votesUp += __popc(__ballot_sync(0xFFFFFFFFu, s > 0));
+                votesDown += __popc(__ballot_sync(0xFFFFFFFFu, s < 0));
+                const bool fail = valid && s == 0;
+                // e == 3 -> list 0, e == 2 -> list 1, e == 1 -> list 2
+                if (e == 3) HierAppend(lists.q[0], lists.count + 0, fail, w, idx);
+                else if (e == 2) HierAppend(lists.q[1], lists.count + 1, fail, w, idx);
+                else HierAppend(lists.q[2], lists.count + 2, fail, w, idx);
+            }
+            if (lane == 0) {
+                if (votesUp) atomicAdd(&uniformVotes[2 * (size_t)w], votesUp);
+                if (votesDown) atomicAdd(&uniformVotes[2 * (size_t)w + 1], votesDown);
+            }
         }
-        votesUp += __popc(__ballot_sync(0xFFFFFFFFu, s > 0));
-        votesDown += __popc(__ballot_sync(0xFFFFFFFFu, s < 0));
-        const bool fail = valid && s == 0;
-        // e == 3 -> list 0, e == 2 -> list 1, e == 1 -> list 2
-        if (e == 3) HierAppend(lists.q[0], lists.count + 0, fail, w, idx);
-        else if (e == 2) HierAppend(lists.q[1], lists.count + 1, fail, w, idx);
-        else HierAppend(lists.q[2], lists.count + 2, fail, w, idx);
-    }
-    if (lane == 0) {
-        uniformVotes[2 * (size_t)w] = votesUp;
-        uniformVotes[2 * (size_t)w + 1] = votesDown;
-    }
     }
 }
 
@@ -703,7 +738,7 @@ struct HierEdgeQueue {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(128) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
+__global__ void __launch_bounds__(128, 8) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
                                                    const unsigned long long* __restrict__ wordStart, HierLists lists, HierEdgeQueue queue,
                                                    uint32_t* __restrict__ stateWords) {
     const unsigned long long total = lists.count[2] * 4ull;
@@ -751,7 +786,7 @@ __global__ void __launch_bounds__(128) HierEdgeTests(const BakeParams P, const H
 }
 
 struct HierKernels {
-    void (*initial)(const BakeParams, const HierItem*, const unsigned long long*, uint32_t, uint32_t, HierLists, uint32_t*, uint32_t*);
+    void (*initial)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, HierLists, uint32_t*, uint32_t*);
     void (*list)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, const unsigned long long*, unsigned long long*,
                  unsigned long long*, int, uint32_t*);
     void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, HierEdgeQueue, uint32_t*);
@@ -951,6 +986,7 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
         uint64_t acc = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
         const uint4* words4 = reinterpret_cast<const uint4*>(words);
         const uint32_t half = j & 1u, pair = j >> 1;
+#pragma unroll 4
         for (uint32_t g = 0; g < (numWords >> 2); ++g) {
             const uint4 v = __ldg(words4 + g);
             if (j == 0) {
@@ -1173,6 +1209,80 @@ __global__ void SatRows(const void* __restrict__ texels, int isFp32, unsigned lo
         carry = __shfl_sync(0xFFFFFFFFu, v, 31);
     }
 }
+// (H) row pass of the constant-cell table: inclusive prefix sums of "cell (x, y) is not flat-good" over the (w-1) x (h-1) interior cells
+__global__ void FlatSatRows(const void* __restrict__ texels, int isFp32, int w, int h, float cutoff, uint32_t* __restrict__ sat) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= h - 1) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t carry = 0;
+    for (int base = 0; base < w - 1; base += 32) {
+        const int x = base + lane;
+        uint32_t v = 0;
+        if (x < w - 1) {
+            const size_t i00 = (size_t)row * w + x;
+            float g00, g10, g01, g11;
+            if (isFp32) {
+                const float* t = (const float*)texels;
+                g00 = t[i00]; g10 = t[i00 + 1]; g01 = t[i00 + w]; g11 = t[i00 + w + 1];
+            } else {
+                const uint8_t* t = (const uint8_t*)texels;
+                g00 = (float)t[i00] * (1.f / 255.f); g10 = (float)t[i00 + 1] * (1.f / 255.f); g01 = (float)t[i00 + w] * (1.f / 255.f);
+                g11 = (float)t[i00 + w + 1] * (1.f / 255.f);
+            }
+            v = CellIsFlatGood(g00, g10, g01, g11, cutoff) ? 0u : 1u;
+        }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= d) v += o;
+        }
+        v += carry;
+        if (x < w - 1) sat[(size_t)row * (w - 1) + x] = v;
+        carry = __shfl_sync(0xFFFFFFFFu, v, 31);
+    }
+}
+// Column pass of a summed-area table in three parallel steps over segments of kSatSegRows rows: per-segment column totals, their
+// running sums, then the in-segment scan with the segment's offset (the single-thread-per-column loop below needs ~1 ms per 1024 rows).
+constexpr int kSatSegRows = 64;
+__global__ void SatColSegTotals(int w, int h, const uint32_t* __restrict__ sat, uint32_t* __restrict__ segTotals) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
+    if (x >= w) return;
+    const int y0 = seg * kSatSegRows, y1 = min(h, y0 + kSatSegRows);
+    uint32_t acc = 0;
+    for (int y = y0; y < y1; ++y) acc += sat[(size_t)y * w + x];
+    segTotals[(size_t)seg * w + x] = acc;
+}
+__global__ void SatColSegScan(int w, int numSegs, uint32_t* __restrict__ segTotals) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    uint32_t acc = 0;
+    for (int sgm = 0; sgm < numSegs; ++sgm) {
+        const uint32_t v = segTotals[(size_t)sgm * w + x];
+        segTotals[(size_t)sgm * w + x] = acc;  // exclusive
+        acc += v;
+    }
+}
+__global__ void SatColSegApply(int w, int h, const uint32_t* __restrict__ segTotals, uint32_t* __restrict__ sat) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, seg = blockIdx.y;
+    if (x >= w) return;
+    const int y0 = seg * kSatSegRows, y1 = min(h, y0 + kSatSegRows);
+    uint32_t acc = segTotals[(size_t)seg * w + x];
+    for (int y = y0; y < y1; ++y) {
+        acc += sat[(size_t)y * w + x];
+        sat[(size_t)y * w + x] = acc;
+    }
+}
+static cudaError_t SatColumnPass(int w, int h, uint32_t* sat, cudaStream_t stream) {
+    const int numSegs = (h + kSatSegRows - 1) / kSatSegRows;
+    uint32_t* segTotals = nullptr;
+    cudaError_t e = cudaMallocAsync(&segTotals, sizeof(uint32_t) * (size_t)numSegs * w, stream);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((w + 127) / 128, numSegs);
+    SatColSegTotals<<<grid, 128, 0, stream>>>(w, h, sat, segTotals);
+    SatColSegScan<<<(w + 127) / 128, 128, 0, stream>>>(w, numSegs, segTotals);
+    SatColSegApply<<<grid, 128, 0, stream>>>(w, h, segTotals, sat);
+    cudaFreeAsync(segTotals, stream);
+    return cudaGetLastError();
+}
 __global__ void SatCols(int w, int h, uint32_t* __restrict__ sat) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
@@ -1282,6 +1392,7 @@ ommResult UploadTexture(TextureObject* tex, const Logger& log) {
     tex->dev.texels = tex->devTexels;
     tex->dev.isFp32 = tex->format == ommCpuTextureFormat_FP32;
     tex->dev.sat = nullptr;
+    tex->dev.flatSat = nullptr;
     if (tex->HasAlphaCutoff()) {  // ref: texture_impl.cpp:91 -- SAT <=> alphaCutoff >= 0
         CUDA_TRY(cudaMalloc(&tex->devSat, totalTexels * sizeof(uint32_t)));
         for (uint32_t i = 0; i < tex->mipCount; ++i) {
@@ -1299,11 +1410,46 @@ cleanup:
     return rc;
 }
 void DestroyTextureDevice(TextureObject* tex) {
-    if (tex->devTexels || tex->devSat) cudaSetDevice(tex->device);
+    if (tex->devTexels || tex->devSat || tex->devFlatSat) cudaSetDevice(tex->device);
     if (tex->devTexels) cudaFree(tex->devTexels);
     if (tex->devSat) cudaFree(tex->devSat);
+    if (tex->devFlatSat) cudaFree(tex->devFlatSat);
     tex->devTexels = nullptr;
     tex->devSat = nullptr;
+    tex->devFlatSat = nullptr;
+    tex->flatValid = false;
+}
+
+// (H) The constant-cell table of mip 0 for `cutoff`: built on the first bake that needs it and kept with the texture (a texture is
+// normally baked with one cutoff; another cutoff rebuilds it).  Returns nullptr when the texture is too small or memory is short --
+// the classifier then simply has no O(1) answer for large footprints.  The build is ordered before the caller's later work on
+// `stream` by running on that stream; concurrent bakes serialise on the texture's mutex.
+static const uint32_t* GetFlatSat(TextureObject* tex, float cutoff, cudaStream_t stream, uint32_t* launches) {
+    const DevMip& m = tex->dev.mips[0];
+    if (m.w < 2 || m.h < 2) return nullptr;
+    std::lock_guard<std::mutex> g(tex->flatMu);
+    if (tex->flatValid && tex->flatCutoff == cutoff) return tex->devFlatSat;
+    if (tex->flatValid) {
+        // another bake may still be reading the table of the previous cutoff
+        cudaDeviceSynchronize();
+        tex->flatValid = false;
+    }
+    if (!tex->devFlatSat && cudaMalloc(&tex->devFlatSat, sizeof(uint32_t) * (size_t)(m.w - 1) * (size_t)(m.h - 1)) != cudaSuccess) {
+        cudaGetLastError();
+        tex->devFlatSat = nullptr;
+        return nullptr;
+    }
+    FlatSatRows<<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(tex->devTexels, tex->dev.isFp32, m.w, m.h, cutoff, tex->devFlatSat);
+    if (SatColumnPass(m.w - 1, m.h - 1, tex->devFlatSat, stream) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    *launches += 4;
+    // later bakes may run on other streams: make the table visible to them before it is published
+    cudaStreamSynchronize(stream);
+    tex->flatCutoff = cutoff;
+    tex->flatValid = true;
+    return tex->devFlatSat;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1795,6 +1941,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
         if (itemEnd > itemBegin && useHier) {
+            P.tex.flatSat = GetFlatSat(const_cast<TextureObject*>(tex), P.cutoff, stream, &launches);
             // worst case of a chunk: kHierChunkRegions initial regions plus the rest of its last item (at most 4^9 regions at level 12)
             const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
             const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, kHierChunkRegions) + (1ull << 18), regionEnd - regionBegin);
@@ -1820,7 +1967,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 if (i0 >= itemEnd) break;
                 if (i1 <= i0) continue;
                 CUDA_TRY(cudaMemsetAsync(lists.count, 0, 4 * sizeof(unsigned long long), stream));
-                hier.initial<<<std::min<uint32_t>((i1 - i0 + kHierInitWarps - 1) / kHierInitWarps, listGrid), kHierInitWarps * 32, 0, stream>>>(P, hierItems, wordStart, i0, i1, lists, uniformVotes, stateWords);
+                hier.initial<<<listGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
                 hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);

@@ -241,6 +241,15 @@ OMM_HD bool MakeItemBox(const DevMip& m, const HierItem& it, RegionBox& box) {
     box.cx0 = (int)floorf(box.lox); box.cy0 = (int)floorf(box.loy); box.cx1 = (int)floorf(box.hix); box.cy1 = (int)floorf(box.hiy);
     return true;
 }
+// Node box: the same for the sub-triangle `index` at `nodeLevel` of the item (an aligned group of initial regions of a large item).
+OMM_HD bool MakeNodeBox(const DevMip& m, const HierItem& it, uint32_t index, uint32_t nodeLevel, RegionBox& box) {
+    HierItem whole = it;
+    whole.level = 0xFFFFFFFFu;  // forces epsRegion in MakeRegionBox
+    if (!MakeRegionBox(m, whole, index, nodeLevel, box)) return false;
+    box.lox -= it.epsRegion; box.loy -= it.epsRegion; box.hix += it.epsRegion; box.hiy += it.epsRegion;
+    box.cx0 = (int)floorf(box.lox); box.cy0 = (int)floorf(box.loy); box.cx1 = (int)floorf(box.hix); box.cy1 = (int)floorf(box.hiy);
+    return true;
+}
 // +1 / -1 when every footprint cell of the region box is a whole-cell pass of that side, else 0
 OMM_HD int LookupCellMap(const ItemCellMap& map, const RegionBox& rb) {
     if (map.fw == 0) return 0;
@@ -257,13 +266,38 @@ OMM_HD int LookupCellMap(const ItemCellMap& map, const RegionBox& rb) {
     return 0;
 }
 
+// (H) Constant areas.  A cell is FLAT-GOOD for a cutoff when its four texels are the same float g and |g - cutoff| exceeds
+//     1e-5 (1 + |g| + |cutoff|).  There b = c = d = 0 exactly, so the kernel takes its "all points on the same level" branch
+//     (bake_kernels_cpu.h:343-354) and never tests an edge; texel centres vote the side of g; the bilinear sample is a lerp of four
+//     equal values, off by <= 7 u |g| from g.  A rectangle of cells inside the texture (texel columns cx0 .. cx1 + 1 < w, no
+//     addressing involved) that contains only flat-good cells holds a single value, because neighbouring cells share texels: every
+//     region whose footprint lies in it is on the side of that value, whatever its size.  flatSat is the inclusive summed-area
+//     table of the NOT-flat-good flags of mip 0, built per texture and cutoff (BuildFlatSat); this makes large triangles in fully
+//     opaque / fully transparent parts of a texture O(1) instead of O(cells).
+OMM_HD bool CellIsFlatGood(float g00, float g10, float g01, float g11, float cutoff) {
+    if (!(g00 == g10 && g00 == g01 && g00 == g11)) return false;
+    return fabsf(g00 - cutoff) > 1e-5f * (1.f + fabsf(g00) + fabsf(cutoff));
+}
+template <class Cfg>
+OMM_HD int FlatRectSide(const BakeParams& P, const DevMip& m, int cx0, int cy0, int cx1, int cy1) {
+    const uint32_t* sat = P.tex.flatSat;
+    if (!sat || cx0 < 0 || cy0 < 0 || cx1 > m.w - 2 || cy1 > m.h - 2 || cx1 < cx0 || cy1 < cy0) return 0;
+    const size_t sw = (size_t)(m.w - 1);
+    const uint32_t A = (cx0 > 0 && cy0 > 0) ? LoadRO(sat + (size_t)(cy0 - 1) * sw + (cx0 - 1)) : 0u;
+    const uint32_t B = cy0 > 0 ? LoadRO(sat + (size_t)(cy0 - 1) * sw + cx1) : 0u;
+    const uint32_t C = cx0 > 0 ? LoadRO(sat + (size_t)cy1 * sw + (cx0 - 1)) : 0u;
+    const uint32_t D = LoadRO(sat + (size_t)cy1 * sw + cx1);
+    if (D + A - B - C != 0u) return 0;
+    return P.cutoff < TexLoad<Cfg>(P.tex, m, cx0, cy0) ? 1 : -1;
+}
+
 // Returns +1 / -1 when every micro-triangle of the region (bird index `index` at subdivision level `regionLevel` of the
 // work item; regionLevel == it.level means a single micro-triangle) is provably on that side of the cutoff, 0 otherwise.
 template <class Cfg>
 OMM_HD int TestRegionBox(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& rb) {
     const float lox = rb.lox, loy = rb.loy, hix = rb.hix, hiy = rb.hiy;
     const int cx0 = rb.cx0, cy0 = rb.cy0, cx1 = rb.cx1, cy1 = rb.cy1;
-    if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kHierMaxCells) return 0;
+    if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kHierMaxCells) return FlatRectSide<Cfg>(P, m, cx0, cy0, cx1, cy1);  // (H) or split
     const float delta = it.deltaEdge;
     const float cutoffAbs = fabsf(P.cutoff);
     int sAll = 0;
@@ -470,6 +504,18 @@ OMM_HD bool LeafEdgeTests(const BakeParams& P, const DevMip& m, const HierItem& 
 template <class Cfg, class Defer>
 OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, Defer&& defer) {
     const Tri st = MicroTri(it.p0, it.p1, it.p2, index, it.level);
+    if (P.tex.flatSat) {
+        // (H) a micro-triangle of many texels over a constant area: its footprint (A) instead of a walk over every cell
+        const float W = (float)m.w, H = (float)m.h, eps = it.epsSingle;
+        const float r0x = st.p0.x * W + -0.5f, r0y = st.p0.y * H + -0.5f, r1x = st.p1.x * W + -0.5f, r1y = st.p1.y * H + -0.5f;
+        const float r2x = st.p2.x * W + -0.5f, r2y = st.p2.y * H + -0.5f;
+        const float lox = fminf(fminf(r0x, r1x), r2x) - eps, loy = fminf(fminf(r0y, r1y), r2y) - eps;
+        const float hix = fmaxf(fmaxf(r0x, r1x), r2x) + eps, hiy = fmaxf(fmaxf(r0y, r1y), r2y) + eps;
+        if (lox > -2097152.f && loy > -2097152.f && hix < 2097152.f && hiy < 2097152.f && (hix - lox) * (hiy - loy) > 16.f) {
+            const int s = FlatRectSide<Cfg>(P, m, (int)floorf(lox), (int)floorf(loy), (int)floorf(hix), (int)floorf(hiy));
+            if (s != 0) return s > 0 ? P.stateGT : P.stateLE;
+        }
+    }
     Coverage cov{0u, 0u};
     const bool countsMatter = P.promotion == ommUnknownStatePromotion_Nearest;
     if (P.cutoff < TexBilinear<Cfg>(P, m, st.p0)) cov.above++;

@@ -83,6 +83,8 @@ struct DevMip {
 struct DevTexture {
     const void* texels;       // row-major, float or uint8_t
     const uint32_t* sat;      // inclusive summed-area table of (alpha > cutoff), or nullptr
+    const uint32_t* flatSat;  // mip 0: inclusive summed-area table over the (w-1) x (h-1) interior cells of "not a constant, clearly one-sided
+                              // cell" for the bake's alpha cutoff (omm_hier.cuh (H)), or nullptr
     int isFp32;
     int mipCount;
     DevMip mips[kMaxMips];
@@ -99,6 +101,11 @@ struct TextureObject {
     size_t hostBytes = 0;
     void* devTexels = nullptr;
     uint32_t* devSat = nullptr;
+    // constant-cell table of the hierarchical classifier, built on first use for a given alpha cutoff and kept with the texture
+    std::mutex flatMu;
+    uint32_t* devFlatSat = nullptr;
+    float flatCutoff = 0.f;
+    bool flatValid = false;
     DevTexture dev{};
     bool HasAlphaCutoff() const { return alphaCutoff >= 0.f; }
 };

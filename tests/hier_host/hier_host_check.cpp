@@ -84,20 +84,21 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
         const uint32_t nl = L < 6 ? L : 6;
         const uint32_t nodes = L > 6 ? 1u << (2 * (L - 6)) : 1u;
         const uint32_t e0 = nl < 3 ? nl : 3;
-        // whole-cell bitmap of the item (F), as HierTestInitial builds it
-        uint32_t plus[32] = {0}, minus[32] = {0};
-        ItemCellMap map{0, 0, 0, 0, plus, minus};
-        RegionBox box;
-        if (hi.ok && L >= 3 && MakeItemBox(m, hi, box) && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
-            map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = box.cx1 - box.cx0 + 1; map.fh = box.cy1 - box.cy0 + 1;
-            for (int y = 0; y < map.fh; ++y)
-                for (int x = 0; x < map.fw; ++x) {
-                    const int s = WholeCellSide<Cfg>(P, m, hi, box, box.cx0 + x, box.cy0 + y);
-                    if (s > 0) plus[y] |= 1u << x;
-                    else if (s < 0) minus[y] |= 1u << x;
-                }
-        }
         for (uint32_t node = 0; node < nodes; ++node) {
+            // whole-cell bitmap (F) of the item, or of the aligned node of 64 initial regions of a bigger item, as HierTestInitial builds it
+            uint32_t plus[32] = {0}, minus[32] = {0};
+            ItemCellMap map{0, 0, 0, 0, plus, minus};
+            RegionBox box;
+            const bool haveBox = hi.ok && L >= 3 && (L > 6 ? MakeNodeBox(m, hi, node, L - 6, box) : MakeItemBox(m, hi, box));
+            if (haveBox && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
+                map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = box.cx1 - box.cx0 + 1; map.fh = box.cy1 - box.cy0 + 1;
+                for (int y = 0; y < map.fh; ++y)
+                    for (int x = 0; x < map.fw; ++x) {
+                        const int s = WholeCellSide<Cfg>(P, m, hi, box, box.cx0 + x, box.cy0 + y);
+                        if (s > 0) plus[y] |= 1u << x;
+                        else if (s < 0) minus[y] |= 1u << x;
+                    }
+            }
             const uint32_t nInit = 1u << (2 * (nl - e0));
             for (uint32_t r = 0; r < nInit; ++r) Descend<Cfg>(P, m, hi, node, nl, e0, r, states.data(), st, uv, degenerate, e0 == 3 ? &map : nullptr);
             const uint32_t n = 1u << (2 * nl);
@@ -142,6 +143,22 @@ extern "C" __attribute__((visibility("default"))) int hier_host_check(const void
     P.globalFormat = format;
     P.promotion = promotion;
     P.pow2Mip0 = m.isPow2;
+    // (H) constant-cell table of mip 0, as BuildFlatSat / FlatSatRows + SatCols compute it on the device
+    std::vector<uint32_t> flat;
+    if (w >= 2 && h >= 2) {
+        flat.resize((size_t)(w - 1) * (h - 1));
+        for (int y = 0; y < h - 1; ++y)
+            for (int x = 0; x < w - 1; ++x) {
+                auto tx = [&](int xx, int yy) {
+                    const size_t i = (size_t)yy * w + xx;
+                    return isFp32 ? ((const float*)texels)[i] : (float)((const uint8_t*)texels)[i] * (1.f / 255.f);
+                };
+                const uint32_t bad = CellIsFlatGood(tx(x, y), tx(x + 1, y), tx(x, y + 1), tx(x + 1, y + 1), cutoff) ? 0u : 1u;
+                const size_t i = (size_t)y * (w - 1) + x;
+                flat[i] = bad + (x ? flat[i - 1] : 0u) + (y ? flat[i - (w - 1)] : 0u) - ((x && y) ? flat[i - (w - 1) - 1] : 0u);
+            }
+        P.tex.flatSat = flat.data();
+    }
     if (isFp32) CheckItems<KernelCfg<kAddrGeneric, true>>(P, uvs, levels, numItems, st);
     else CheckItems<KernelCfg<kAddrGeneric, false>>(P, uvs, levels, numItems, st);
     return st->mismatches == 0 ? 0 : 1;

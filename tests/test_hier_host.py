@@ -122,3 +122,16 @@ def test_levels(lib):
     check(lib, t["noise"], tris(rng, 400, 10, 1024), rng.integers(0, 7, 400))       # levels 0..6: items smaller than one initial region
     check(lib, t["noise"], tris(rng, 6, 40, 1024), np.full(6, 9))                   # more than 64 initial regions per item
     check(lib, t["smooth"], tris(rng, 100, 60, 256), np.full(100, 3))               # micro-triangles of many texels: footprints too large to shortcut
+
+
+def test_constant_areas_and_large_micro_triangles(lib):
+    """(H): triangles of hundreds of texels at low levels over fully opaque / transparent areas with islands of detail."""
+    rng = np.random.default_rng(10)
+    tex = np.zeros((512, 512), dtype=np.float32)
+    tex[:, 256:] = 1.0
+    tex[100:140, 60:120] = W.noise_texture(64)[:40, :60]          # detail inside the transparent half
+    tex[300:330, 300:360] = 0.5 + 1e-6                              # constant, but too close to the cutoff to be trusted
+    st = check(lib, tex, tris(rng, 200, 120, 512, 0.1, 0.9), rng.integers(0, 5, 200))
+    assert st.passes[0] + st.passes[1] + st.passes[2] > 0
+    check(lib, tex, tris(rng, 100, 150, 512, -0.3, 1.3), rng.integers(0, 4, 100), addr=capi.ADDR_CLAMP)
+    check(lib, (tex * 255).astype(np.uint8), tris(rng, 100, 100, 512, 0.1, 0.9), rng.integers(1, 5, 100))
