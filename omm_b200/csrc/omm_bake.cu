@@ -548,7 +548,19 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS)
 // Every kernel is small and homogeneous (no divergence between phases, full occupancy); a list entry is (item, region index).
 // The lists are sized for the worst case (every test fails) of one CHUNK of initial regions; a bake is a sequence of chunks.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kHierChunkRegions = 8u << 20;  // initial regions per chunk: lists of 8M + 32M + 128M entries (1.3 GiB) at most
+// Initial regions per chunk.  The lists are sized for the worst case (every test fails): 21 entries of 8 bytes per initial region.
+// The nominal chunk is 64 M regions = 4.3e9 micro-triangles (10.7 GiB of lists, a sixteenth of a B200's HBM), so that a bake of
+// config-3 size is ONE chunk and pays the kernel-boundary drains once; it shrinks to an eighth of the free memory on smaller devices.
+constexpr unsigned long long kHierChunkRegionsMax = 64ull << 20, kHierChunkRegionsMin = 1ull << 20;
+static unsigned long long HierNominalChunkRegions() {
+    size_t freeB = 0, totalB = 0;
+    if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) {
+        cudaGetLastError();
+        return kHierChunkRegionsMin;
+    }
+    const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (21ull * 8ull);
+    return std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));
+}
 struct HierLists {
     unsigned long long* q[3];   // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
     unsigned long long* count;  // [3]
@@ -1735,6 +1747,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     ShardBound* boundsDev = nullptr;
     uint32_t* chunkFirstDev = nullptr;
     uint32_t chunkFirst[kHierMaxChunks + 1];
+    const unsigned long long hierChunkRegions = HierNominalChunkRegions();
     uint32_t* stateWords = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;
@@ -1897,7 +1910,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemNodes, nodeStart, (int)T + 1, stream));
             launches += 6;
         }
-        ShardBounds<<<1, 128, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, world, rank, (unsigned long long)kHierChunkRegions, boundsDev, chunkFirstDev);
+        ShardBounds<<<1, 128, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, world, rank, hierChunkRegions, boundsDev, chunkFirstDev);
         launches++;
         CUDA_TRY(cudaMemcpyAsync(countersHost, counters, sizeof(countersHost), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (world + 1), cudaMemcpyDeviceToHost, stream));
@@ -1942,9 +1955,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         const bool useHier = SelectHierKernels(P, &hier);
         if (itemEnd > itemBegin && useHier) {
             P.tex.flatSat = GetFlatSat(const_cast<TextureObject*>(tex), P.cutoff, stream, &launches);
-            // worst case of a chunk: kHierChunkRegions initial regions plus the rest of its last item (at most 4^9 regions at level 12)
+            // worst case of a chunk: the nominal number of initial regions plus the rest of its last item (at most 4^9 regions at level 12)
             const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
-            const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, kHierChunkRegions) + (1ull << 18), regionEnd - regionBegin);
+            const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, hierChunkRegions) + (1ull << 18), regionEnd - regionBegin);
             HierItem* hierItems = nullptr;
             HierLists lists{};
             CUDA_TRY(scratch.alloc(&hierItems, W));
