@@ -549,9 +549,10 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS)
 // The lists are sized for the worst case (every test fails) of one CHUNK of initial regions; a bake is a sequence of chunks.
 // ---------------------------------------------------------------------------------------------------------------------
 // Initial regions per chunk.  The lists are sized for the worst case (every test fails): 21 entries of 8 bytes per initial region.
-// The nominal chunk is 64 M regions = 4.3e9 micro-triangles (10.7 GiB of lists, a sixteenth of a B200's HBM), so that a bake of
-// config-3 size is ONE chunk and pays the kernel-boundary drains once; it shrinks to an eighth of the free memory on smaller devices.
-constexpr unsigned long long kHierChunkRegionsMax = 64ull << 20, kHierChunkRegionsMin = 1ull << 20;
+// The nominal chunk is 32 M regions = 2.1e9 micro-triangles (5.6 GiB of lists, 3 % of a B200's HBM): a bake of config-3 size is two
+// chunks and pays the kernel-boundary drains twice (one chunk of 64 M is 1 % faster per bake but doubles the one-off cost of growing
+// the memory pool on the first bake); it shrinks to an eighth of the free memory on smaller devices.
+constexpr unsigned long long kHierChunkRegionsMax = 32ull << 20, kHierChunkRegionsMin = 1ull << 20;
 static unsigned long long HierNominalChunkRegions() {
     size_t freeB = 0, totalB = 0;
     if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) {
@@ -562,8 +563,9 @@ static unsigned long long HierNominalChunkRegions() {
     return std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));
 }
 struct HierLists {
-    unsigned long long* q[3];   // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
-    unsigned long long* count;  // [3]
+    unsigned long long* q[3];        // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
+    unsigned long long* unresolved;  // initial regions the whole-cell bitmap did not answer
+    unsigned long long* count;       // [4]: the three lists, then `unresolved`
 };
 
 __global__ void HierPrepare(const BakeParams P, const ItemRec* __restrict__ items, uint32_t itemBegin, uint32_t itemEnd, HierItem* __restrict__ hierItems) {
@@ -695,19 +697,13 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
                 int s = 0;
                 if (valid) {
                     RegionBox rb;
-                    if (MakeRegionBox(m, hi, idx, L - e, rb)) {
-                        s = LookupCellMap(map, rb);
-                        if (s == 0) s = TestRegionBox<Cfg>(P, m, hi, rb);
-                    }
+                    if (MakeRegionBox(m, hi, idx, L - e, rb)) s = LookupCellMap(map, rb);
                     if (s != 0) HierFillGlobal(words, e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
                 }
                 votesUp += __popc(__ballot_sync(0xFFFFFFFFu, s > 0));
                 votesDown += __popc(__ballot_sync(0xFFFFFFFFu, s < 0));
-                const bool fail = valid && s == 0;
-                // e == 3 -> list 0, e == 2 -> list 1, e == 1 -> list 2
-                if (e == 3) HierAppend(lists.q[0], lists.count + 0, fail, w, idx);
-                else if (e == 2) HierAppend(lists.q[1], lists.count + 1, fail, w, idx);
-                else HierAppend(lists.q[2], lists.count + 2, fail, w, idx);
+                // regions the bitmap does not answer get the full test in HierTestUnresolved, where every lane has one
+                HierAppend(lists.unresolved, lists.count + 3, valid && s == 0, w, idx);
             }
             if (lane == 0) {
                 if (votesUp) atomicAdd(&uniformVotes[2 * (size_t)w], votesUp);
@@ -739,6 +735,36 @@ __global__ void __launch_bounds__(128) HierTestList(const BakeParams P, const Hi
             if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
         }
         HierAppend(outList, outCount, valid && s == 0, w, idx);
+    }
+}
+
+// Initial regions the whole-cell bitmap left open: the full region test, one region per thread.
+template <class Cfg>
+__global__ void __launch_bounds__(128) HierTestUnresolved(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+                                                           HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
+    const unsigned long long total = lists.count[3];
+    const unsigned long long rounded = (total + 31ull) & ~31ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const bool valid = t < total;
+        uint32_t w = 0, idx = 0, e = 3;
+        int s = 0;
+        if (valid) {
+            const unsigned long long entry = lists.unresolved[t];
+            w = (uint32_t)(entry >> 32);
+            idx = (uint32_t)entry;
+            const HierItem hi = LoadHierItem(hierItems + w);
+            e = hi.level < 3 ? hi.level : 3;
+            s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, hi.level - e);
+            if (s != 0) {
+                HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+                atomicAdd(&uniformVotes[2 * (size_t)w + (s > 0 ? 0 : 1)], 1u);
+            }
+        }
+        const bool fail = valid && s == 0;
+        // e == 3 -> list 0, e == 2 -> list 1, e == 1 -> list 2
+        HierAppend(lists.q[0], lists.count + 0, fail && e == 3, w, idx);
+        HierAppend(lists.q[1], lists.count + 1, fail && e == 2, w, idx);
+        HierAppend(lists.q[2], lists.count + 2, fail && e == 1, w, idx);
     }
 }
 
@@ -803,10 +829,11 @@ struct HierKernels {
                  unsigned long long*, int, uint32_t*);
     void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, HierEdgeQueue, uint32_t*);
     void (*edgeTests)(const BakeParams, const HierItem*, const unsigned long long*, HierEdgeQueue, uint32_t*);
+    void (*unresolved)(const BakeParams, const HierItem*, const unsigned long long*, HierLists, uint32_t*, uint32_t*);
 };
 template <class Cfg>
 static HierKernels MakeHierKernels() {
-    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierEdgeTests<Cfg>};
+    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierEdgeTests<Cfg>, HierTestUnresolved<Cfg>};
 }
 
 // OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
@@ -1964,10 +1991,11 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
             CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
             CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
-            CUDA_TRY(scratch.alloc(&lists.count, 4));  // [3] counts the queued edge tests
+            CUDA_TRY(scratch.alloc(&lists.unresolved, (size_t)cap));
+            CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [4] queued edge tests (unused)
             HierEdgeQueue queue{};  // unused: see HierLeaves
             queue.capacity = 0;
-            queue.count = lists.count + 3;
+            queue.count = lists.count + 4;
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
             int sms = 0;
@@ -1979,12 +2007,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 const uint32_t i0 = chunkFirst[c], i1 = chunkFirst[c + 1];
                 if (i0 >= itemEnd) break;
                 if (i1 <= i0) continue;
-                CUDA_TRY(cudaMemsetAsync(lists.count, 0, 4 * sizeof(unsigned long long), stream));
+                CUDA_TRY(cudaMemsetAsync(lists.count, 0, 8 * sizeof(unsigned long long), stream));
                 hier.initial<<<listGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
+                hier.unresolved<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
                 hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
-                launches += 4;
+                launches += 5;
             }
         } else if (itemEnd > itemBegin) {
             const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);

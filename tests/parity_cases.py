@@ -56,6 +56,10 @@ def cases():
     c["flag_disable_special"] = (lambda: W.random_mesh(61, 300, tex_kind="blocky", tri_texels=5, bake_flags=A.BAKE_DISABLE_SPECIAL_INDICES), {})
     c["flag_disable_special_levels"] = (lambda: W.random_mesh(74, 400, tex_kind="blocky", tri_texels=4, subdivision_levels=_levels(74, 400, 0, 6),
                                                               bake_flags=A.BAKE_DISABLE_SPECIAL_INDICES), {})
+    # large triangles at low levels over a texture with big constant areas (constant-cell table (H) of the hierarchical classifier)
+    c["flat_areas_big_triangles"] = (lambda: W.config5(num_tris=1500, tex_size=256, distinct=128, flat_tris=700, max_level=6), {})
+    c["flat_areas_clamp_outside"] = (lambda: W.random_mesh(75, 200, tex_kind="blocky", tri_texels=90, uv_lo=-0.4, uv_hi=1.4, addressing_mode=A.ADDR_CLAMP,
+                                                           subdivision_levels=_levels(75, 200, 0, 4)), {})
     c["flag_disable_dup"] = (lambda: W.random_mesh(62, 300, reuse_frac=0.5, tex_kind="blocky", bake_flags=A.BAKE_DISABLE_DUPLICATE_DETECTION), {})
     c["flag_force32"] = (lambda: W.random_mesh(63, 300, bake_flags=A.BAKE_FORCE_32BIT_INDICES), {})
     c["flag_allow8"] = (lambda: W.random_mesh(64, 100, bake_flags=A.BAKE_ALLOW_8BIT_INDICES), {})
