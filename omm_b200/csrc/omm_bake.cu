@@ -553,14 +553,21 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS)
 // chunks and pays the kernel-boundary drains twice (one chunk of 64 M is 1 % faster per bake but doubles the one-off cost of growing
 // the memory pool on the first bake); it shrinks to an eighth of the free memory on smaller devices.
 constexpr unsigned long long kHierChunkRegionsMax = 32ull << 20, kHierChunkRegionsMin = 1ull << 20;
-static unsigned long long HierNominalChunkRegions() {
+static unsigned long long HierNominalChunkRegions(int device) {
+    // cudaMemGetInfo is a slow driver query (milliseconds with a large memory pool): ask once per device
+    static std::mutex mu;
+    static unsigned long long cached[64] = {};
+    std::lock_guard<std::mutex> g(mu);
+    if (device >= 0 && device < 64 && cached[device]) return cached[device];
     size_t freeB = 0, totalB = 0;
-    if (cudaMemGetInfo(&freeB, &totalB) != cudaSuccess) {
+    unsigned long long regions = kHierChunkRegionsMin;
+    if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
+        const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (21ull * 8ull);
+        regions = std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));
+    } else
         cudaGetLastError();
-        return kHierChunkRegionsMin;
-    }
-    const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (21ull * 8ull);
-    return std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));
+    if (device >= 0 && device < 64) cached[device] = regions;
+    return regions;
 }
 struct HierLists {
     unsigned long long* q[3];        // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
@@ -601,6 +608,74 @@ __device__ __forceinline__ void HierFillGlobal(uint32_t* __restrict__ words, uin
     if (e == 3) reinterpret_cast<uint4*>(words)[idx] = make_uint4(pat, pat, pat, pat);
     else if (e == 2) words[idx] = pat;
     else reinterpret_cast<uint8_t*>(words)[idx] = (uint8_t)pat;  // e == 1: four micro-triangles, one byte
+}
+
+// Region tests of a whole warp, one region per lane, with the CELLS of all thirty-two footprints spread evenly over the lanes: a
+// region has 1 to 16 footprint cells and fails at its first bad one, so evaluating them lane by lane leaves two thirds of the warp
+// idle.  Returns this lane's verdict: +1 / -1 = every micro-triangle of the region is on that side, 0 = split it.
+template <class Cfg>
+__device__ __forceinline__ int WarpTestRegions(const BakeParams& P, const DevMip& m, const HierItem* __restrict__ hierItems, bool valid, uint32_t w,
+                                               const RegionBox& rb) {
+    const uint32_t lane = threadIdx.x & 31;
+    const int fw = rb.cx1 - rb.cx0 + 1, fh = rb.cy1 - rb.cy0 + 1;
+    int n = valid ? fw * fh : 0;
+    int verdict = 0;
+    bool decided = !valid;
+    if (valid && n > kHierMaxCells) {
+        verdict = FlatRectSide<Cfg>(P, m, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (H) or split
+        decided = true;
+        n = 0;
+    }
+    // inclusive prefix sums of the cell counts
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((int)lane >= d) incl += o;
+    }
+    const int excl = incl - n, total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t anyPlus = 0, anyMinus = 0, anyFail = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int task = base + (int)lane;
+        const bool active = task < total;
+        // owner = the lane whose cell range holds `task`: the number of lanes with incl <= task
+        int owner = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(0xFFFFFFFFu, incl, owner + step - 1);
+            if (v <= task) owner += step;
+        }
+        owner = owner > 31 ? 31 : owner;
+        RegionBox ob;
+        ob.lox = __shfl_sync(0xFFFFFFFFu, rb.lox, owner); ob.loy = __shfl_sync(0xFFFFFFFFu, rb.loy, owner);
+        ob.hix = __shfl_sync(0xFFFFFFFFu, rb.hix, owner); ob.hiy = __shfl_sync(0xFFFFFFFFu, rb.hiy, owner);
+        ob.r0x = __shfl_sync(0xFFFFFFFFu, rb.r0x, owner); ob.r0y = __shfl_sync(0xFFFFFFFFu, rb.r0y, owner);
+        ob.r1x = __shfl_sync(0xFFFFFFFFu, rb.r1x, owner); ob.r1y = __shfl_sync(0xFFFFFFFFu, rb.r1y, owner);
+        ob.r2x = __shfl_sync(0xFFFFFFFFu, rb.r2x, owner); ob.r2y = __shfl_sync(0xFFFFFFFFu, rb.r2y, owner);
+        ob.eps = __shfl_sync(0xFFFFFFFFu, rb.eps, owner);
+        const int ocx0 = __shfl_sync(0xFFFFFFFFu, rb.cx0, owner), ocy0 = __shfl_sync(0xFFFFFFFFu, rb.cy0, owner);
+        const int ofw = __shfl_sync(0xFFFFFFFFu, fw, owner), on = __shfl_sync(0xFFFFFFFFu, n, owner), oexcl = __shfl_sync(0xFFFFFFFFu, excl, owner);
+        const uint32_t ow = __shfl_sync(0xFFFFFFFFu, w, owner);
+        int s = 0;
+        if (active) {
+            const int local = task - oexcl, ly = local / ofw, lx = local - ly * ofw;
+            const HierItem hi = LoadHierItem(hierItems + ow);
+            s = TestRegionCell<Cfg>(P, m, hi, ob, ocx0 + lx, ocy0 + ly, on == 1);
+        }
+        const uint32_t bp = __ballot_sync(0xFFFFFFFFu, active && s > 0), bm = __ballot_sync(0xFFFFFFFFu, active && s < 0),
+                       bf = __ballot_sync(0xFFFFFFFFu, active && s == 0);
+        // the tasks of this round that belong to this lane's region
+        const int lo = (excl > base ? excl : base) - base, hiE = (incl < base + 32 ? incl : base + 32) - base;
+        if (hiE > lo) {
+            const uint32_t mine = (hiE - lo == 32 ? 0xFFFFFFFFu : ((1u << (hiE - lo)) - 1u)) << lo;
+            anyPlus |= bp & mine;
+            anyMinus |= bm & mine;
+            anyFail |= bf & mine;
+        }
+    }
+    if (decided) return verdict;
+    if (n == 0 || anyFail != 0 || (anyPlus != 0 && anyMinus != 0)) return 0;
+    return anyPlus != 0 ? 1 : -1;
 }
 
 // One warp per TASK = 64 consecutive initial regions of the chunk (for items of level 6 that is exactly one work item; a level-12
@@ -715,7 +790,7 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
 
 // children of the regions in lists.q[src] (size exponent 3 - src); the children have size exponent 2 - src
 template <class Cfg>
-__global__ void __launch_bounds__(128) HierTestList(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+__global__ void __launch_bounds__(128, 8) HierTestList(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
                                                      const unsigned long long* __restrict__ inList, const unsigned long long* __restrict__ inCount,
                                                      unsigned long long* __restrict__ outList, unsigned long long* __restrict__ outCount, int src,
                                                      uint32_t* __restrict__ stateWords) {
@@ -723,44 +798,46 @@ __global__ void __launch_bounds__(128) HierTestList(const BakeParams P, const Hi
     const unsigned long long rounded = (total + 31ull) & ~31ull;
     const uint32_t e = 2u - (uint32_t)src;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
-        const bool valid = t < total;
+        bool valid = t < total;
         uint32_t w = 0, idx = 0;
-        int s = 0;
+        RegionBox rb{};
         if (valid) {
             const unsigned long long entry = inList[t >> 2];
             w = (uint32_t)(entry >> 32);
             idx = (uint32_t)entry * 4u + (uint32_t)(t & 3ull);
             const HierItem hi = LoadHierItem(hierItems + w);
-            s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, hi.level - e);
-            if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+            valid = MakeRegionBox(P.tex.mips[0], hi, idx, hi.level - e, rb);  // false: coordinates out of range, the region is split
         }
-        HierAppend(outList, outCount, valid && s == 0, w, idx);
+        const int s = WarpTestRegions<Cfg>(P, P.tex.mips[0], hierItems, valid, w, rb);
+        if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+        HierAppend(outList, outCount, t < total && s == 0, w, idx);
     }
 }
 
 // Initial regions the whole-cell bitmap left open: the full region test, one region per thread.
 template <class Cfg>
-__global__ void __launch_bounds__(128) HierTestUnresolved(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+__global__ void __launch_bounds__(128, 8) HierTestUnresolved(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
                                                            HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
     const unsigned long long total = lists.count[3];
     const unsigned long long rounded = (total + 31ull) & ~31ull;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
-        const bool valid = t < total;
+        bool valid = t < total;
         uint32_t w = 0, idx = 0, e = 3;
-        int s = 0;
+        RegionBox rb{};
         if (valid) {
             const unsigned long long entry = lists.unresolved[t];
             w = (uint32_t)(entry >> 32);
             idx = (uint32_t)entry;
             const HierItem hi = LoadHierItem(hierItems + w);
             e = hi.level < 3 ? hi.level : 3;
-            s = TestRegion<Cfg>(P, P.tex.mips[0], hi, idx, hi.level - e);
-            if (s != 0) {
-                HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
-                atomicAdd(&uniformVotes[2 * (size_t)w + (s > 0 ? 0 : 1)], 1u);
-            }
+            valid = MakeRegionBox(P.tex.mips[0], hi, idx, hi.level - e, rb);
         }
-        const bool fail = valid && s == 0;
+        const int s = WarpTestRegions<Cfg>(P, P.tex.mips[0], hierItems, valid, w, rb);
+        if (s != 0) {
+            HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
+            atomicAdd(&uniformVotes[2 * (size_t)w + (s > 0 ? 0 : 1)], 1u);
+        }
+        const bool fail = t < total && s == 0;
         // e == 3 -> list 0, e == 2 -> list 1, e == 1 -> list 2
         HierAppend(lists.q[0], lists.count + 0, fail && e == 3, w, idx);
         HierAppend(lists.q[1], lists.count + 1, fail && e == 2, w, idx);
@@ -1452,7 +1529,7 @@ void DestroyTextureDevice(TextureObject* tex) {
     if (tex->devTexels || tex->devSat || tex->devFlatSat) cudaSetDevice(tex->device);
     if (tex->devTexels) cudaFree(tex->devTexels);
     if (tex->devSat) cudaFree(tex->devSat);
-    if (tex->devFlatSat) cudaFree(tex->devFlatSat);
+    if (tex->devFlatSat) cudaFreeAsync(tex->devFlatSat, 0);
     tex->devTexels = nullptr;
     tex->devSat = nullptr;
     tex->devFlatSat = nullptr;
@@ -1473,7 +1550,7 @@ static const uint32_t* GetFlatSat(TextureObject* tex, float cutoff, cudaStream_t
         cudaDeviceSynchronize();
         tex->flatValid = false;
     }
-    if (!tex->devFlatSat && cudaMalloc(&tex->devFlatSat, sizeof(uint32_t) * (size_t)(m.w - 1) * (size_t)(m.h - 1)) != cudaSuccess) {
+    if (!tex->devFlatSat && cudaMallocAsync((void**)&tex->devFlatSat, sizeof(uint32_t) * (size_t)(m.w - 1) * (size_t)(m.h - 1), stream) != cudaSuccess) {
         cudaGetLastError();
         tex->devFlatSat = nullptr;
         return nullptr;
@@ -1774,7 +1851,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     ShardBound* boundsDev = nullptr;
     uint32_t* chunkFirstDev = nullptr;
     uint32_t chunkFirst[kHierMaxChunks + 1];
-    const unsigned long long hierChunkRegions = HierNominalChunkRegions();
+    const unsigned long long hierChunkRegions = HierNominalChunkRegions(baker->device);
     uint32_t* stateWords = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;

@@ -293,84 +293,94 @@ OMM_HD int FlatRectSide(const BakeParams& P, const DevMip& m, int cx0, int cy0, 
 
 // Returns +1 / -1 when every micro-triangle of the region (bird index `index` at subdivision level `regionLevel` of the
 // work item; regionLevel == it.level means a single micro-triangle) is provably on that side of the cutoff, 0 otherwise.
+// One footprint cell of a region: +1 / -1 when the cell passes (B), (C) [and (G) when `single`: the region lies in this one cell]
+// on that side, 0 when it does not.  Only the enclosure, the corners and eps of `rb` are used, so HierTestList can evaluate the
+// cells of thirty-two regions side by side, one cell per lane.
+template <class Cfg>
+OMM_HD int TestRegionCell(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& rb, int cx, int cy, bool single) {
+    const float lox = rb.lox, loy = rb.loy, hix = rb.hix, hiy = rb.hiy;
+    const float delta = it.deltaEdge;
+    const int y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy, m.h, m.log2h), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy + 1, m.h, m.log2h);
+    const float fy = (float)cy;
+    const float by0 = fmaxf(0.f, loy - fy - delta), by1 = fminf(1.f, hiy - fy + delta);
+    const float qy = fmaxf(fabsf(loy - fy), fabsf(hiy - fy)) + delta;
+    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx, m.w, m.log2w), x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx + 1, m.w, m.log2w);
+    // (c00, c01, c11, c10) as the reference gathers them
+    const float gx = TexFetch<Cfg>(P, m, x0, y0);
+    const float gy = TexFetch<Cfg>(P, m, x0, y1);
+    const float gz = TexFetch<Cfg>(P, m, x1, y1);
+    const float gw = TexFetch<Cfg>(P, m, x1, y0);
+    const float a = gx - P.cutoff;
+    const float b = gw - gx;
+    const float c = gy - gx;
+    const float d = gx + gz - gy - gw;
+    const float fx = (float)cx;
+    const float bx0 = fmaxf(0.f, lox - fx - delta), bx1 = fminf(1.f, hix - fx + delta);
+    const float qx = fmaxf(fabsf(lox - fx), fabsf(hix - fx)) + delta;
+    // h at the four corners of B
+    const float e0 = a + b * bx0, e1 = a + b * bx1;
+    const float f0 = c + d * bx0, f1 = c + d * bx1;
+    const float h00 = e0 + f0 * by0, h01 = e0 + f0 * by1, h10 = e1 + f1 * by0, h11 = e1 + f1 * by1;
+    const float mn = fminf(fminf(h00, h01), fminf(h10, h11)), mx = fmaxf(fmaxf(h00, h01), fmaxf(h10, h11));
+    int s;
+    float margin;
+    if (mn > 0.f) { s = 1; margin = mn; }
+    else if (mx < 0.f) { s = -1; margin = -mx; }
+    else if (single) {
+        // (G) The whole region lies in this one cell: bound h over the region TRIANGLE instead of its bounding box.  Every
+        // vertex of the region is within eps of the triangle T spanned by the three corner positions q_i (A), and a
+        // reported intersection within delta of such an edge (B).  Along a segment h deviates from the chord by at most
+        // |d| |dx dy| / 4; a point of T lies on a segment from q_0 to a point of the opposite edge, so over T
+        //     s h >= min_i s h(q_i) - |d| wx wy / 2,
+        // and moving eps + delta away costs at most (eps + delta)(|b| + |c| + |d|(Qx + Qy)).  The float evaluation of
+        // h(q_i) is off by <= 8 u (|a'| + |b| Qx + |c| Qy + |d| Qx Qy).
+        const float q0x = rb.r0x - fx, q0y = rb.r0y - fy, q1x = rb.r1x - fx, q1y = rb.r1y - fy, q2x = rb.r2x - fx, q2y = rb.r2y - fy;
+        const float v0 = (a + b * q0x) + (c + d * q0x) * q0y;
+        const float v1 = (a + b * q1x) + (c + d * q1x) * q1y;
+        const float v2 = (a + b * q2x) + (c + d * q2x) * q2y;
+        if (v0 > 0.f && v1 > 0.f && v2 > 0.f) s = 1;
+        else if (v0 < 0.f && v1 < 0.f && v2 < 0.f) s = -1;
+        else { OMM_STAT(4); return 0; }
+        const float al = fabsf(a), be = fabsf(b), ga = fabsf(c), de = fabsf(d);
+        const float wx = hix - lox, wy = hiy - loy;
+        const float pad = 0.505f * de * wx * wy + 2.f * (rb.eps + delta) * (be + ga + de * (qx + qy)) +
+                          8.f * kUnitRoundoff * (al + be * qx + ga * qy + de * qx * qy);
+        margin = fminf(fminf(fabsf(v0), fabsf(v1)), fabsf(v2)) - pad;
+    } else { OMM_STAT(4); return 0; }
+    // (C) texel centres on the other side must be out of reach of PointInTriangle
+    const bool want = s > 0;
+    const bool o0 = P.cutoff < gx, o1 = P.cutoff < gy, o2 = P.cutoff < gz, o3 = P.cutoff < gw;
+    if (o0 != want || o1 != want || o2 != want || o3 != want) {
+        const bool farL = lox - fx >= it.pitX;             // corners with local x = 0 are left of the region
+        const bool farR = (fx + 1.f) - hix >= it.pitX;     // corners with local x = 1 are right of it
+        const bool farB = loy - fy >= it.pitY;
+        const bool farT = (fy + 1.f) - hiy >= it.pitY;
+        // corner 0 = (0,0), 1 = (0,1), 2 = (1,1), 3 = (1,0); a corner at local x = 1 is also "left of the region" when the
+        // region starts beyond it, i.e. lox - (fx + 1) >= pit, which implies farL; the four flags below are the cheap subset.
+        if (o0 != want && !(farL || farB)) { OMM_STAT(6); return 0; }
+        if (o1 != want && !(farL || farT)) { OMM_STAT(6); return 0; }
+        if (o2 != want && !(farR || farT)) { OMM_STAT(6); return 0; }
+        if (o3 != want && !(farR || farB)) { OMM_STAT(6); return 0; }
+    }
+    const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
+    if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, fabsf(P.cutoff), qx, qy)) { OMM_STAT(7); return 0; }
+    return s;
+}
+
+// All footprint cells must pass on the same side.
 template <class Cfg>
 OMM_HD int TestRegionBox(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& rb) {
-    const float lox = rb.lox, loy = rb.loy, hix = rb.hix, hiy = rb.hiy;
     const int cx0 = rb.cx0, cy0 = rb.cy0, cx1 = rb.cx1, cy1 = rb.cy1;
     if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kHierMaxCells) return FlatRectSide<Cfg>(P, m, cx0, cy0, cx1, cy1);  // (H) or split
-    const float delta = it.deltaEdge;
-    const float cutoffAbs = fabsf(P.cutoff);
+    const bool single = cx0 == cx1 && cy0 == cy1;
     int sAll = 0;
-    for (int cy = cy0; cy <= cy1; ++cy) {
-        const int y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy, m.h, m.log2h), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy + 1, m.h, m.log2h);
-        const float fy = (float)cy;
-        const float by0 = fmaxf(0.f, loy - fy - delta), by1 = fminf(1.f, hiy - fy + delta);
-        const float qy = fmaxf(fabsf(loy - fy), fabsf(hiy - fy)) + delta;
+    for (int cy = cy0; cy <= cy1; ++cy)
         for (int cx = cx0; cx <= cx1; ++cx) {
-            const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx, m.w, m.log2w), x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx + 1, m.w, m.log2w);
-            // (c00, c01, c11, c10) as the reference gathers them
-            const float gx = TexFetch<Cfg>(P, m, x0, y0);
-            const float gy = TexFetch<Cfg>(P, m, x0, y1);
-            const float gz = TexFetch<Cfg>(P, m, x1, y1);
-            const float gw = TexFetch<Cfg>(P, m, x1, y0);
-            const float a = gx - P.cutoff;
-            const float b = gw - gx;
-            const float c = gy - gx;
-            const float d = gx + gz - gy - gw;
-            const float fx = (float)cx;
-            const float bx0 = fmaxf(0.f, lox - fx - delta), bx1 = fminf(1.f, hix - fx + delta);
-            const float qx = fmaxf(fabsf(lox - fx), fabsf(hix - fx)) + delta;
-            // h at the four corners of B
-            const float e0 = a + b * bx0, e1 = a + b * bx1;
-            const float f0 = c + d * bx0, f1 = c + d * bx1;
-            const float h00 = e0 + f0 * by0, h01 = e0 + f0 * by1, h10 = e1 + f1 * by0, h11 = e1 + f1 * by1;
-            const float mn = fminf(fminf(h00, h01), fminf(h10, h11)), mx = fmaxf(fmaxf(h00, h01), fmaxf(h10, h11));
-            int s;
-            float margin;
-            if (mn > 0.f) { s = 1; margin = mn; }
-            else if (mx < 0.f) { s = -1; margin = -mx; }
-            else if (cx0 == cx1 && cy0 == cy1) {
-                // (G) The whole region lies in this one cell: bound h over the region TRIANGLE instead of its bounding box.  Every
-                // vertex of the region is within eps of the triangle T spanned by the three corner positions q_i (A), and a
-                // reported intersection within delta of such an edge (B).  Along a segment h deviates from the chord by at most
-                // |d| |dx dy| / 4; a point of T lies on a segment from q_0 to a point of the opposite edge, so over T
-                //     s h >= min_i s h(q_i) - |d| wx wy / 2,
-                // and moving eps + delta away costs at most (eps + delta)(|b| + |c| + |d|(Qx + Qy)).  The float evaluation of
-                // h(q_i) is off by <= 8 u (|a'| + |b| Qx + |c| Qy + |d| Qx Qy).
-                const float q0x = rb.r0x - fx, q0y = rb.r0y - fy, q1x = rb.r1x - fx, q1y = rb.r1y - fy, q2x = rb.r2x - fx, q2y = rb.r2y - fy;
-                const float v0 = (a + b * q0x) + (c + d * q0x) * q0y;
-                const float v1 = (a + b * q1x) + (c + d * q1x) * q1y;
-                const float v2 = (a + b * q2x) + (c + d * q2x) * q2y;
-                if (v0 > 0.f && v1 > 0.f && v2 > 0.f) s = 1;
-                else if (v0 < 0.f && v1 < 0.f && v2 < 0.f) s = -1;
-                else { OMM_STAT(4); return 0; }
-                const float al = fabsf(a), be = fabsf(b), ga = fabsf(c), de = fabsf(d);
-                const float wx = hix - lox, wy = hiy - loy;
-                const float pad = 0.505f * de * wx * wy + 2.f * (rb.eps + delta) * (be + ga + de * (qx + qy)) +
-                                  8.f * kUnitRoundoff * (al + be * qx + ga * qy + de * qx * qy);
-                margin = fminf(fminf(fabsf(v0), fabsf(v1)), fabsf(v2)) - pad;
-            } else { OMM_STAT(4); return 0; }
+            const int s = TestRegionCell<Cfg>(P, m, it, rb, cx, cy, single);
+            if (s == 0) return 0;
             if (sAll != 0 && sAll != s) { OMM_STAT(5); return 0; }
             sAll = s;
-            // (C) texel centres on the other side must be out of reach of PointInTriangle
-            const bool want = s > 0;
-            const bool o0 = P.cutoff < gx, o1 = P.cutoff < gy, o2 = P.cutoff < gz, o3 = P.cutoff < gw;
-            if (o0 != want || o1 != want || o2 != want || o3 != want) {
-                const bool farL = lox - fx >= it.pitX;             // corners with local x = 0 are left of the region
-                const bool farR = (fx + 1.f) - hix >= it.pitX;     // corners with local x = 1 are right of it
-                const bool farB = loy - fy >= it.pitY;
-                const bool farT = (fy + 1.f) - hiy >= it.pitY;
-                // corner 0 = (0,0), 1 = (0,1), 2 = (1,1), 3 = (1,0); a corner at local x = 1 is also "left of the region" when the
-                // region starts beyond it, i.e. lox - (fx + 1) >= pit, which implies farL; the four flags below are the cheap subset.
-                if (o0 != want && !(farL || farB)) { OMM_STAT(6); return 0; }
-                if (o1 != want && !(farL || farT)) { OMM_STAT(6); return 0; }
-                if (o2 != want && !(farR || farT)) { OMM_STAT(6); return 0; }
-                if (o3 != want && !(farR || farB)) { OMM_STAT(6); return 0; }
-            }
-            const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
-            if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, cutoffAbs, qx, qy)) { OMM_STAT(7); return 0; }
         }
-    }
     return sAll;
 }
 template <class Cfg>
