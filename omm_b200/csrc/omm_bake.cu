@@ -572,7 +572,8 @@ static unsigned long long HierNominalChunkRegions(int device) {
 struct HierLists {
     unsigned long long* q[3];        // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
     unsigned long long* unresolved;  // initial regions the whole-cell bitmap did not answer
-    unsigned long long* count;       // [4]: the three lists, then `unresolved`
+    unsigned long long* slow;        // 4-regions of items the shortcuts do not cover (HierLeavesSlow)
+    unsigned long long* count;       // [0..2] the three lists, [3] unresolved, [5] slow
 };
 
 __global__ void HierPrepare(const BakeParams P, const ItemRec* __restrict__ items, uint32_t itemBegin, uint32_t itemEnd, HierItem* __restrict__ hierItems) {
@@ -721,7 +722,10 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
                 // is one leaf, listed as 4-region 0
                 const uint32_t per = L >= 3 ? 16u : (L == 2 ? 4u : 1u);
                 const uint32_t n4 = (b - a) * per;
-                for (uint32_t base = 0; base < n4; base += 32) HierAppend(lists.q[2], lists.count + 2, base + lane < n4, w, a * per + base + lane);
+                // level-0 items the shortcuts DO cover go to the ordinary leaf list
+                unsigned long long* list = hi.ok ? lists.q[2] : lists.slow;
+                unsigned long long* count = hi.ok ? lists.count + 2 : lists.count + 5;
+                for (uint32_t base = 0; base < n4; base += 32) HierAppend(list, count, base + lane < n4, w, a * per + base + lane);
                 continue;
             }
             // (F) whole-cell bitmap over the footprint of the piece: the whole item, or the aligned node of 64 regions of a bigger item
@@ -872,9 +876,33 @@ __global__ void __launch_bounds__(128, 8) HierLeaves(const BakeParams P, const I
                     // The edge tests stay in place: queueing them for HierEdgeTests (and a single-micro-triangle TestRegion first)
                     // was measured slower -- both re-derive the vertices and the cell, and the tests diverge just as much there.
                     st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
-                } else
-                    st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, hi.p0, hi.p1, hi.p2, items[w].degenerate != 0, index, hi.level);
+                }
             }
+            bits = st << (2 * k);
+        }
+        bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
+        bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 2);
+        if (t < total && (t & 3ull) == 0) reinterpret_cast<uint8_t*>(stateWords + __ldg(&wordStart[w]))[region] = (uint8_t)bits;
+    }
+}
+
+// Micro-triangles of the items the shortcuts do not cover (zero-area UV triangles, non-finite or huge coordinates): the generic
+// reference walk, in a kernel of its own so that HierLeaves stays small.
+template <class Cfg>
+__global__ void __launch_bounds__(128) HierLeavesSlow(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
+                                                       const unsigned long long* __restrict__ wordStart, HierLists lists, uint32_t* __restrict__ stateWords) {
+    const unsigned long long total = lists.count[5] * 4ull;
+    const unsigned long long rounded = (total + 31ull) & ~31ull;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t bits = 0, w = 0, region = 0;
+        if (t < total) {
+            const unsigned long long entry = lists.slow[t >> 2];
+            w = (uint32_t)(entry >> 32);
+            region = (uint32_t)entry;
+            const uint32_t k = (uint32_t)(t & 3ull), index = region * 4u + k;
+            const ItemRec it = items[w];
+            uint32_t st = 0;
+            if (index < (1u << (2 * it.level))) st = (uint32_t)ClassifyMicroTriangle<Cfg>(P, it.p0, it.p1, it.p2, it.degenerate != 0, index, it.level);
             bits = st << (2 * k);
         }
         bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
@@ -907,10 +935,11 @@ struct HierKernels {
     void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, HierEdgeQueue, uint32_t*);
     void (*edgeTests)(const BakeParams, const HierItem*, const unsigned long long*, HierEdgeQueue, uint32_t*);
     void (*unresolved)(const BakeParams, const HierItem*, const unsigned long long*, HierLists, uint32_t*, uint32_t*);
+    void (*leavesSlow)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
 };
 template <class Cfg>
 static HierKernels MakeHierKernels() {
-    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierEdgeTests<Cfg>, HierTestUnresolved<Cfg>};
+    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierEdgeTests<Cfg>, HierTestUnresolved<Cfg>, HierLeavesSlow<Cfg>};
 }
 
 // OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
@@ -2095,6 +2124,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
             CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
             CUDA_TRY(scratch.alloc(&lists.unresolved, (size_t)cap));
+            CUDA_TRY(scratch.alloc(&lists.slow, (size_t)cap * 16));
             CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [4] queued edge tests (unused)
             HierEdgeQueue queue{};  // unused: see HierLeaves
             queue.capacity = 0;
@@ -2116,7 +2146,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                 hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
                 hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
-                launches += 5;
+                hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
+                launches += 6;
             }
         } else if (itemEnd > itemBegin) {
             const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
@@ -2186,7 +2217,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 CompactBoundsKernel<<<1, 96, 0, stream>>>(compactStart, boundsDev, world, compactBoundsDev);
                 if (itemEnd > itemBegin)
                     CompactCopy<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(special, itemWords, wordStart, compactStart, stateWords, itemBegin, itemEnd, compactWords);
-                launches += 5;
+                launches += 6;
                 CUDA_TRY(cudaMemcpyAsync(compactBounds, compactBoundsDev, sizeof(unsigned long long) * (world + 1), cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
                 ncclOk = nccl.GroupStart() == ncclSuccess;
