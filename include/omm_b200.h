@@ -324,6 +324,24 @@ static inline ommCpuBakeInputDesc ommCpuBakeInputDescDefault(void) {
 /* ref: omm.h:576   (bake.cpp:118) */ OMM_API ommResult ommCpuDestroyBakeResult(ommCpuBakeResult bakeResult);
 /* ref: omm.h:578   (bake.cpp:129) */ OMM_API ommResult ommCpuGetBakeResultDesc(ommCpuBakeResult bakeResult, const ommCpuBakeResultDesc** desc);
 /* ref: omm.h:1201  (debug_impl.cpp:512-641): state counts of a result, as the SDK's known-answer tests read them. */
+/* ---- serialization of bake inputs / results ---------------------------------------------------------------
+ * ABI note: omm.h declares the two descs below as C++ references inside extern "C" (omm.h:583, 590); at the ABI level they are
+ * pointers, which is what this C header says. */
+typedef struct ommCpuBlobDesc { void* data; uint64_t size; } ommCpuBlobDesc;                           /* ref: omm.h:532-536 */
+typedef struct ommCpuDeserializedDesc {                                                                 /* ref: omm.h:546-555 */
+    ommCpuSerializeFlags flags;
+    int numInputDescs;
+    const ommCpuBakeInputDesc* inputDescs;
+    int numResultDescs;
+    const ommCpuBakeResultDesc* resultDescs;
+} ommCpuDeserializedDesc;
+/* ref: omm.h:583 (bake.cpp:137) */ OMM_API ommResult ommCpuSerialize(ommBaker baker, const ommCpuDeserializedDesc* desc, ommCpuSerializedResult* outResult);
+/* ref: omm.h:585 (bake.cpp:169) */ OMM_API ommResult ommCpuGetSerializedResultDesc(ommCpuSerializedResult result, const ommCpuBlobDesc** desc);
+/* ref: omm.h:587 (bake.cpp:182) */ OMM_API ommResult ommCpuDestroySerializedResult(ommCpuSerializedResult result);
+/* ref: omm.h:590 (bake.cpp:195) */ OMM_API ommResult ommCpuDeserialize(ommBaker baker, const ommCpuBlobDesc* desc, ommCpuDeserializedResult* outResult);
+/* ref: omm.h:592 (bake.cpp:224) */ OMM_API ommResult ommCpuGetDeserializedDesc(ommCpuDeserializedResult result, const ommCpuDeserializedDesc** desc);
+/* ref: omm.h:594 (bake.cpp:240) */ OMM_API ommResult ommCpuDestroyDeserializedResult(ommCpuDeserializedResult result);
+
 OMM_API ommResult ommDebugGetStats(ommBaker baker, const ommCpuBakeResultDesc* res, ommDebugStats* out);
 
 /* ======================================================================================

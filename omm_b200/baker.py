@@ -218,6 +218,52 @@ class Baker:
         rc = self.lib.dll.ommCpuBake(self.handle, C.byref(desc), C.byref(h))
         return rc, h.value
 
+    # -- serialization (ommCpuSerialize / ommCpuDeserialize) -----------------------------------------
+    def serialize(self, input_descs=(), result_descs=(), flags: int = capi.SERIALIZE_NONE) -> bytes:
+        """Blob of the given capi.CpuBakeInputDesc / capi.CpuBakeResultDesc structures."""
+        d = capi.CpuDeserializedDesc()
+        ins = (capi.CpuBakeInputDesc * max(1, len(input_descs)))(*input_descs)
+        outs = (capi.CpuBakeResultDesc * max(1, len(result_descs)))(*result_descs)
+        d.flags, d.numInputDescs, d.inputDescs = flags, len(input_descs), ins
+        d.numResultDescs, d.resultDescs = len(result_descs), outs
+        h = C.c_void_p()
+        rc = self.lib.dll.ommCpuSerialize(self.handle, C.byref(d), C.byref(h))
+        if rc != capi.SUCCESS:
+            raise OmmError("ommCpuSerialize", rc)
+        try:
+            pb = C.POINTER(capi.CpuBlobDesc)()
+            rc = self.lib.dll.ommCpuGetSerializedResultDesc(h, C.byref(pb))
+            if rc != capi.SUCCESS:
+                raise OmmError("ommCpuGetSerializedResultDesc", rc)
+            return C.string_at(pb.contents.data, pb.contents.size)
+        finally:
+            self.lib.dll.ommCpuDestroySerializedResult(h)
+
+    def deserialize_raw(self, blob: bytes):
+        """(rc, handle, POINTER(CpuDeserializedDesc)); the caller destroys the handle with ommCpuDestroyDeserializedResult."""
+        buf = C.create_string_buffer(blob, len(blob))
+        bd = capi.CpuBlobDesc(C.cast(buf, C.c_void_p).value, len(blob))
+        h = C.c_void_p()
+        rc = self.lib.dll.ommCpuDeserialize(self.handle, C.byref(bd), C.byref(h))
+        if rc != capi.SUCCESS:
+            return rc, None, None
+        pd = C.POINTER(capi.CpuDeserializedDesc)()
+        rc = self.lib.dll.ommCpuGetDeserializedDesc(h, C.byref(pd))
+        return rc, h, pd
+
+    def bake_desc(self, desc: capi.CpuBakeInputDesc) -> BakeResult:
+        rc, h = self.bake_raw(desc)
+        if rc != capi.SUCCESS:
+            raise OmmError("ommCpuBake", rc)
+        try:
+            pdesc = C.POINTER(capi.CpuBakeResultDesc)()
+            rc = self.lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc))
+            if rc != capi.SUCCESS:
+                raise OmmError("ommCpuGetBakeResultDesc", rc)
+            return _copy_result(pdesc.contents)
+        finally:
+            self.lib.dll.ommCpuDestroyBakeResult(h)
+
     def bake(self, inp: BakeInput) -> BakeResult:
         desc = inp.to_desc()
         rc, h = self.bake_raw(desc)

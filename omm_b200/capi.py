@@ -172,6 +172,18 @@ class B200DeviceResultDesc(C.Structure):
                 ("descArrayCount", C.c_uint32), ("indexCount", C.c_uint32), ("indexFormat", C.c_int)]
 
 
+class CpuBlobDesc(C.Structure):  # ref: omm.h:532-536
+    _fields_ = [("data", C.c_void_p), ("size", C.c_uint64)]
+
+
+class CpuDeserializedDesc(C.Structure):  # ref: omm.h:546-555
+    _fields_ = [("flags", C.c_int), ("numInputDescs", C.c_int), ("inputDescs", C.POINTER(CpuBakeInputDesc)), ("numResultDescs", C.c_int),
+                ("resultDescs", C.POINTER(CpuBakeResultDesc))]
+
+
+SERIALIZE_NONE, SERIALIZE_COMPRESS = 0, 1
+
+
 def bake_input_desc_default() -> CpuBakeInputDesc:
     """ref: omm.h:462-490 (ommCpuBakeInputDescDefault)."""
     d = CpuBakeInputDesc()
@@ -211,6 +223,11 @@ CORE_SYMBOLS = [
     "ommGetLibraryDesc", "ommCreateBaker", "ommDestroyBaker", "ommCpuCreateTexture", "ommCpuGetTextureDesc",
     "ommCpuDestroyTexture", "ommCpuBake", "ommCpuDestroyBakeResult", "ommCpuGetBakeResultDesc",
 ]
+# SURVEY 8f row N2 (the product and the SDK build export them; the plain-C port of the bake path does not)
+SERIALIZE_SYMBOLS = [
+    "ommCpuSerialize", "ommCpuGetSerializedResultDesc", "ommCpuDestroySerializedResult", "ommCpuDeserialize",
+    "ommCpuGetDeserializedDesc", "ommCpuDestroyDeserializedResult",
+]
 # product-only symbols (include/omm_b200.h, second half + ommDebugGetStats)
 B200_SYMBOLS = [
     "ommDebugGetStats", "ommB200SetDevice", "ommB200GetDeviceCount", "ommB200GetLastBakeTimings", "ommB200StageInputs",
@@ -246,10 +263,32 @@ class OmmLib:
         d.ommCpuDestroyBakeResult.argtypes = [C.c_void_p]
         d.ommCpuGetBakeResultDesc.restype = C.c_int
         d.ommCpuGetBakeResultDesc.argtypes = [C.c_void_p, C.POINTER(C.POINTER(CpuBakeResultDesc))]
+        # serialization: omm.h passes the two descs by C++ reference = by pointer at the ABI level
+        self.has_serialize = hasattr(d, "ommCpuSerialize")
+        if self.has_serialize:
+            self._bind_serialize(d)
         self.has_debug_stats = hasattr(d, "ommDebugGetStats")
         if self.has_debug_stats:
             d.ommDebugGetStats.restype = C.c_int
             d.ommDebugGetStats.argtypes = [C.c_void_p, C.POINTER(CpuBakeResultDesc), C.POINTER(DebugStats)]
+        self._bind_b200(d)
+
+    @staticmethod
+    def _bind_serialize(d):
+        d.ommCpuSerialize.restype = C.c_int
+        d.ommCpuSerialize.argtypes = [C.c_void_p, C.POINTER(CpuDeserializedDesc), C.POINTER(C.c_void_p)]
+        d.ommCpuGetSerializedResultDesc.restype = C.c_int
+        d.ommCpuGetSerializedResultDesc.argtypes = [C.c_void_p, C.POINTER(C.POINTER(CpuBlobDesc))]
+        d.ommCpuDestroySerializedResult.restype = C.c_int
+        d.ommCpuDestroySerializedResult.argtypes = [C.c_void_p]
+        d.ommCpuDeserialize.restype = C.c_int
+        d.ommCpuDeserialize.argtypes = [C.c_void_p, C.POINTER(CpuBlobDesc), C.POINTER(C.c_void_p)]
+        d.ommCpuGetDeserializedDesc.restype = C.c_int
+        d.ommCpuGetDeserializedDesc.argtypes = [C.c_void_p, C.POINTER(C.POINTER(CpuDeserializedDesc))]
+        d.ommCpuDestroyDeserializedResult.restype = C.c_int
+        d.ommCpuDestroyDeserializedResult.argtypes = [C.c_void_p]
+
+    def _bind_b200(self, d):
         self.is_b200 = hasattr(d, "ommB200BakeResident")
         if self.is_b200:
             d.ommB200SetDevice.restype = C.c_int

@@ -269,6 +269,48 @@ OMM_API ommResult ommCpuDestroyTexture(ommBaker baker, ommCpuTexture texture) { 
     return ommResult_SUCCESS;
 }
 
+// ---- serialization (ref: bake.cpp:137-252) ---------------------------------------------------------------------------------------
+OMM_API ommResult ommCpuSerialize(ommBaker baker, const ommCpuDeserializedDesc* desc, ommCpuSerializedResult* outResult) {
+    if (baker == 0 || outResult == nullptr) return ommResult_INVALID_ARGUMENT;
+    BakerObject* b = HandlePtr<BakerObject>(baker);
+    if (HandleTagOf(baker) != HandleTag::CpuBaker) return b->log.InvalidArg("Baker was not created as the right type");
+    if (desc == nullptr) return ommResult_INVALID_ARGUMENT;
+    SerializedResultObject* r = nullptr;
+    const ommResult rc = SerializeImpl(b, *desc, &r);
+    *outResult = rc == ommResult_SUCCESS ? MakeHandle<ommCpuSerializedResult>(r, HandleTag::SerializeResult) : (ommCpuSerializedResult) nullptr;
+    return rc;
+}
+OMM_API ommResult ommCpuGetSerializedResultDesc(ommCpuSerializedResult result, const ommCpuBlobDesc** desc) {
+    if (result == 0 || desc == nullptr) return ommResult_INVALID_ARGUMENT;
+    *desc = SerializedDesc(HandlePtr<SerializedResultObject>(result));
+    return ommResult_SUCCESS;
+}
+OMM_API ommResult ommCpuDestroySerializedResult(ommCpuSerializedResult result) {
+    if (result == 0 || HandleTagOf(result) != HandleTag::SerializeResult) return ommResult_INVALID_ARGUMENT;
+    DestroySerialized(HandlePtr<SerializedResultObject>(result));
+    return ommResult_SUCCESS;
+}
+OMM_API ommResult ommCpuDeserialize(ommBaker baker, const ommCpuBlobDesc* desc, ommCpuDeserializedResult* outResult) {
+    if (baker == 0) return ommResult_INVALID_ARGUMENT;
+    BakerObject* b = HandlePtr<BakerObject>(baker);
+    if (HandleTagOf(baker) != HandleTag::CpuBaker) return b->log.InvalidArg("Baker was not created as the right type");
+    if (desc == nullptr || outResult == nullptr) return ommResult_INVALID_ARGUMENT;
+    DeserializedResultObject* r = nullptr;
+    const ommResult rc = DeserializeImpl(b, *desc, &r);
+    *outResult = rc == ommResult_SUCCESS ? MakeHandle<ommCpuDeserializedResult>(r, HandleTag::DeserializeResult) : (ommCpuDeserializedResult) nullptr;
+    return rc;
+}
+OMM_API ommResult ommCpuGetDeserializedDesc(ommCpuDeserializedResult result, const ommCpuDeserializedDesc** desc) {
+    if (result == 0 || HandleTagOf(result) != HandleTag::DeserializeResult || desc == nullptr) return ommResult_INVALID_ARGUMENT;
+    *desc = DeserializedDesc(HandlePtr<DeserializedResultObject>(result));
+    return ommResult_SUCCESS;
+}
+OMM_API ommResult ommCpuDestroyDeserializedResult(ommCpuDeserializedResult result) {
+    if (result == 0 || HandleTagOf(result) != HandleTag::DeserializeResult) return ommResult_INVALID_ARGUMENT;
+    DestroyDeserialized(HandlePtr<DeserializedResultObject>(result));
+    return ommResult_SUCCESS;
+}
+
 static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, BakerObject** outBaker) {
     if (baker == 0) return ommResult_INVALID_ARGUMENT;
     BakerObject* b = HandlePtr<BakerObject>(baker);

@@ -378,4 +378,6 @@ ommResult RunHostPasses(const ommCpuBakeInputDesc& desc, HostPassItem* items, ui
     return ommResult_SUCCESS;
 }
 
+uint64_t HostXxh64(const void* data, size_t len, uint64_t seed) { return Xxh64(data, len, seed); }
+
 }  // namespace ommb200

@@ -62,7 +62,7 @@ struct Logger {
 };
 
 // ---- handle tags (ref: libraries/omm-lib/src/omm_handle.h:17-53): low 3 bits of the pointer ------------------
-enum class HandleTag : uintptr_t { Reserved = 0, GpuBaker = 1, Pipeline = 2, CpuBaker = 3, Texture = 4 };
+enum class HandleTag : uintptr_t { Reserved = 0, GpuBaker = 1, Pipeline = 2, CpuBaker = 3, Texture = 4, BakeResult = 5, SerializeResult = 6, DeserializeResult = 7 };
 template <class H, class T>
 H MakeHandle(T* p, HandleTag tag) { return (H)((uintptr_t)p | (uintptr_t)tag); }
 template <class T, class H>
@@ -106,6 +106,7 @@ struct TextureObject {
     uint32_t* devFlatSat = nullptr;
     float flatCutoff = 0.f;
     bool flatValid = false;
+    bool hasSerializedSat = false;  // deserialized textures: the blob carried a summed-area table (ref: texture_impl.h:105-108)
     DevTexture dev{};
     bool HasAlphaCutoff() const { return alphaCutoff >= 0.f; }
 };
@@ -178,6 +179,16 @@ struct HostPassItem {
 };
 bool HostPassesNeeded(const ommCpuBakeInputDesc& desc);
 ommResult RunHostPasses(const ommCpuBakeInputDesc& desc, HostPassItem* items, uint32_t count, uint32_t* words, const unsigned long long* wordStart);
+
+// implemented in omm_serialize.cpp
+struct SerializedResultObject;
+struct DeserializedResultObject;
+ommResult SerializeImpl(BakerObject* baker, const ommCpuDeserializedDesc& desc, SerializedResultObject** out);
+const ommCpuBlobDesc* SerializedDesc(const SerializedResultObject* r);
+void DestroySerialized(SerializedResultObject* r);
+ommResult DeserializeImpl(BakerObject* baker, const ommCpuBlobDesc& blob, DeserializedResultObject** out);
+const ommCpuDeserializedDesc* DeserializedDesc(const DeserializedResultObject* r);
+void DestroyDeserialized(DeserializedResultObject* r);
 
 // implemented in omm_bake.cu
 ommResult UploadTexture(TextureObject* tex, const Logger& log);

@@ -33,7 +33,7 @@ def declared_symbols():
 
 def test_header_declares_the_bake_path():
     syms = declared_symbols()
-    for s in capi.CORE_SYMBOLS + capi.B200_SYMBOLS:
+    for s in capi.CORE_SYMBOLS + capi.SERIALIZE_SYMBOLS + capi.B200_SYMBOLS:
         assert s in syms, s
 
 
