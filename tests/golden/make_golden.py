@@ -6,6 +6,8 @@
   std_hash_float.json   libstdc++ std::hash<float> (what glm's std::hash<vec2> -> the SDK's UV pre-dedup key is built from)
   morton.json           xy_to_morton of src/util/bit_tricks.h
   bake_digests.json     sha256 of the five result arrays of the UNMODIFIED SDK build (oracle/_ref) for a set of parity cases
+  serialized_inputs.json  the DeserializeInput_* golden blobs (SDK 1.4 - 1.7 formats, plain and LZ4-compressed) of
+                        support/tests/test_omm_bake_cpu.cpp with the state totals the SDK's tests expect after baking them
 
 Usage: python tests/golden/make_golden.py
 """
@@ -49,6 +51,21 @@ def texcoord_kats():
             ex, ey = val(toks[0]), val(toks[1])
         out.append([MODES[mode], int(x), int(y), int(w), int(h), ex, ey])
     return out
+
+
+def serialized_inputs():
+    src = open(os.path.join(REF, "support/tests/test_omm_bake_cpu.cpp")).read()
+    out = []
+    for m in re.finditer(r"TEST_P\(OMMBakeTestCPU, (DeserializeInput\w+)\)\s*\{(.*?)\n\t\}", src, re.S):
+        name, body = m.group(1), m.group(2)
+        arr = re.search(r"=\s*\{(.*?)\};", body, re.S)
+        if not arr:
+            continue
+        data = bytes(int(x, 16) for x in re.findall(r"0x([0-9A-Fa-f]{2})", arr.group(1)))
+        exp = {k: int(v) for k, v in re.findall(r"\.(\w+)\s*=\s*(\d+)", body)}
+        out.append({"name": name, "line": src[:m.start()].count("\n") + 1, "blob_hex": data.hex(), "expect": exp})
+    return {"source": "support/tests/test_omm_bake_cpu.cpp (golden serialized inputs of SDK versions 1.4 - 1.7 with the expected ommDebugGetStats totals)",
+            "cases": out}
 
 
 def run_c(code, lang, extra):
@@ -141,6 +158,7 @@ def main():
     dump("std_hash_float.json", std_hash_float_vectors())
     dump("morton.json", morton_vectors())
     dump("bake_digests.json", bake_digests())
+    dump("serialized_inputs.json", serialized_inputs())
 
 
 if __name__ == "__main__":

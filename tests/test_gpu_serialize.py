@@ -114,3 +114,21 @@ def test_corrupted_blob_is_rejected(libs):
         assert any("corrupted" in m for m in msgs)
         rc, h, _ = b.deserialize_raw(blob[:20])
         assert rc != capi.SUCCESS
+
+
+def _golden_cases():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "serialized_inputs.json")) as f:
+        return json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_golden_blobs_of_older_sdk_versions(case):
+    """The SDK's own DeserializeInput_* tests: blobs written by SDK 1.4 - 1.7 (older header / texture layouts, one LZ4-compressed)
+    must deserialize and bake to the state totals those tests expect (committed fixture, tests/golden/make_golden.py)."""
+    import kat_cases as K
+    lib = load_product_library()
+    res, _ = _bake_blob(lib, bytes.fromhex(case["blob_hex"]))
+    got = K.collect_stats(res)
+    for k, v in case["expect"].items():
+        assert got[k] == v, (case["name"], case["line"], k, got)
