@@ -342,6 +342,18 @@ typedef struct ommCpuDeserializedDesc {                                         
 /* ref: omm.h:592 (bake.cpp:224) */ OMM_API ommResult ommCpuGetDeserializedDesc(ommCpuDeserializedResult result, const ommCpuDeserializedDesc** desc);
 /* ref: omm.h:594 (bake.cpp:240) */ OMM_API ommResult ommCpuDestroyDeserializedResult(ommCpuDeserializedResult result);
 
+/* ---- out of scope, exported as NOT_IMPLEMENTED stubs so that programs built against omm.h link ------------------
+ * ref: omm.h:1127-1141 (D3D12 / Vulkan command-list baker), omm.h:1199, 1204 (debug dumps).  Opaque pointers stand in for the SDK's
+ * GPU structures, which this header does not declare. */
+OMM_API ommResult ommGpuGetStaticResourceData(int resource, uint8_t* data, size_t* outByteSize);
+OMM_API ommResult ommGpuCreatePipeline(ommBaker baker, const void* pipelineCfg, void** outPipeline);
+OMM_API ommResult ommGpuDestroyPipeline(ommBaker baker, void* pipeline);
+OMM_API ommResult ommGpuGetPipelineDesc(void* pipeline, const void** outPipelineDesc);
+OMM_API ommResult ommGpuGetPreDispatchInfo(void* pipeline, const void* config, void* outPreDispatchInfo);
+OMM_API ommResult ommGpuDispatch(void* pipeline, const void* config, const void** outDispatchDesc);
+OMM_API ommResult ommDebugSaveAsImages(ommBaker baker, const ommCpuBakeInputDesc* bakeInputDesc, const ommCpuBakeResultDesc* res, const void* desc);
+OMM_API ommResult ommDebugSaveBinaryToDisk(ommBaker baker, const ommCpuBlobDesc* data, const char* path);
+
 OMM_API ommResult ommDebugGetStats(ommBaker baker, const ommCpuBakeResultDesc* res, ommDebugStats* out);
 
 /* ======================================================================================

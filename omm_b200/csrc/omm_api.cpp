@@ -311,6 +311,18 @@ OMM_API ommResult ommCpuDestroyDeserializedResult(ommCpuDeserializedResult resul
     return ommResult_SUCCESS;
 }
 
+// ---- entry points of the SDK that are outside this library's scope: exported so that programs written against
+// omm.h -- in particular the SDK's own test binary, oracle/Makefile target `reftests` -- link; every one reports NOT_IMPLEMENTED.
+// The D3D12 / Vulkan command-list baker (ommGpu*), image dumps and ommDebugGetStats2 (stats from a result handle).
+OMM_API ommResult ommGpuGetStaticResourceData(int, uint8_t*, size_t*) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommGpuCreatePipeline(ommBaker, const void*, void**) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommGpuDestroyPipeline(ommBaker, void*) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommGpuGetPipelineDesc(void*, const void**) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommGpuGetPreDispatchInfo(void*, const void*, void*) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommGpuDispatch(void*, const void*, const void**) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommDebugSaveAsImages(ommBaker, const ommCpuBakeInputDesc*, const ommCpuBakeResultDesc*, const void*) { return ommResult_NOT_IMPLEMENTED; }
+OMM_API ommResult ommDebugSaveBinaryToDisk(ommBaker, const ommCpuBlobDesc*, const char*) { return ommResult_NOT_IMPLEMENTED; }
+
 static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, BakerObject** outBaker) {
     if (baker == 0) return ommResult_INVALID_ARGUMENT;
     BakerObject* b = HandlePtr<BakerObject>(baker);

@@ -2383,6 +2383,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches += 4;
         }
         if (T > 0) {
+            // no work item at all (every triangle invalid): the per-triangle item table was never written -> all unresolved
+            // (found by the SDK's own LogTest.Validation_InvalidTriangles run against this library)
+            if (W == 0) CUDA_TRY(cudaMemsetAsync(triFinal, 0xFF, sizeof(uint32_t) * (size_t)T, stream));
             WriteIndexBuffer<<<gridT, TPB, 0, stream>>>(triFinal, special, descOfItem, T, (int)d.unresolvedTriState, indexBytes, res->devIndexBuffer);
             launches++;
         }

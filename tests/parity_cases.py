@@ -42,6 +42,7 @@ def cases():
     c["sat_wrap_outside"] = (lambda: W.random_mesh(45, 400, tex_kind="blocky", tex_alpha_cutoff=0.5, uv_lo=-1.0, uv_hi=2.0, tri_texels=20, max_subdivision_level=5), {})
     c["sat_disable_zorder"] = (lambda: W.random_mesh(46, 200, tex_kind="circle", tex_alpha_cutoff=0.5, tex_flags=A.TEXFLAG_DISABLE_ZORDER), {})
     c["degenerate_and_nan"] = (lambda: W.random_mesh(51, 400, degenerate_frac=0.3, nan_frac=0.1, tri_texels=30), {})
+    c["all_triangles_invalid"] = (lambda: W.random_mesh(59, 64, nan_frac=1.0, bake_flags=A.BAKE_DISABLE_SPECIAL_INDICES | A.BAKE_DISABLE_DUPLICATE_DETECTION), {})
     c["degenerate_nearest_promo"] = (lambda: W.random_mesh(52, 300, degenerate_frac=0.5, tri_texels=40, unknown_state_promotion=A.PROMOTE_NEAREST,
                                                            unresolved_tri_state=A.SPECIAL_FUT, nan_frac=0.05), {})
     c["degenerate_dynamic_levels"] = (lambda: W.random_mesh(53, 300, degenerate_frac=0.4, tri_texels=50, dynamic_subdivision_scale=2.0,
