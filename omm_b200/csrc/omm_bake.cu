@@ -732,14 +732,18 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
             ItemCellMap map{0, 0, 0, 0, sPlus[warp], sMinus[warp]};
             RegionBox box;
             bool haveBox = false;
-            if (L >= 3 && a == 0 && b == (uint32_t)(we - ws)) haveBox = MakeItemBox(m, hi, box);
+            const bool wholeItem = a == 0 && b == (uint32_t)(we - ws);
+            if (L >= 3 && wholeItem) haveBox = MakeItemBox(m, hi, box);
             else if (L > 6 && (a & 63u) == 0 && b - a == 64) haveBox = MakeNodeBox(m, hi, a >> 6, L - 6, box);
             if (haveBox) {
                 // (H) the whole piece over a constant area: one table query, whatever its size
                 const int sFlat = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
                 if (sFlat != 0) {
                     const uint32_t pat = (uint32_t)(sFlat > 0 ? P.stateGT : P.stateLE) * 0x55555555u;
-                    for (uint32_t i = a + lane; i < b; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
+                    // a WHOLE item proved uniform becomes a special index and its block is never read (ItemPostKernel takes the state
+                    // from the votes): skip the write unless special indices are disabled or the host passes want every block
+                    if (!(P.skipUniformFill && wholeItem))
+                        for (uint32_t i = a + lane; i < b; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
                     if (lane == 0) atomicAdd(&uniformVotes[2 * (size_t)w + (sFlat > 0 ? 0 : 1)], b - a);
                     continue;
                 }
@@ -764,7 +768,8 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
                 if (allPlus || allMinus) {
                     // one 16-byte group per initial region (64 micro-triangles x 2 bits); boxes exist for level >= 3 only
                     const uint32_t pat = (uint32_t)(allPlus ? P.stateGT : P.stateLE) * 0x55555555u;
-                    for (uint32_t i = a + lane; i < b; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
+                    if (!(P.skipUniformFill && wholeItem))
+                        for (uint32_t i = a + lane; i < b; i += 32) reinterpret_cast<uint4*>(words)[i] = make_uint4(pat, pat, pat, pat);
                     if (lane == 0) atomicAdd(&uniformVotes[2 * (size_t)w + (allPlus ? 0 : 1)], b - a);
                     continue;
                 }
@@ -1066,7 +1071,8 @@ constexpr int kItemPostItemsPerBlock = 64;
 __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
                                                       const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, float rejectionThreshold,
                                                       int disableSpecial, int keepExistingSpecial, const uint32_t* __restrict__ uniformVotes,
-                                                      const UniformDigests table, uint64_t* __restrict__ digest, int32_t* special) {
+                                                      uint32_t stateGT, uint32_t stateLE, const UniformDigests table, uint64_t* __restrict__ digest,
+                                                      int32_t* special) {
     // Phase 1, one thread per item of the block's range: items the hierarchical classifier proved uniform (all initial regions on
     // one side, HierTestInitial) get their constant digest without reading anything; the others are compacted into a list.
     __shared__ uint32_t sList[kItemPostItemsPerBlock * 4];
@@ -1082,7 +1088,7 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
                 const uint32_t nInit = lv > 3 ? 1u << (2 * (lv - 3)) : 1u;
                 const uint32_t above = __ldg(&uniformVotes[2 * (size_t)wi]), below = __ldg(&uniformVotes[2 * (size_t)wi + 1]);
                 if (above == nInit || below == nInit) {
-                    const uint32_t s = (__ldg(stateWords + wordStart[wi])) & 3u;
+                    const uint32_t s = above == nInit ? stateGT : stateLE;  // the block itself may not have been written (skipUniformFill)
                     digest[wi] = table.h[s >= 2 ? 2 : s][lv];
                     special[wi] = disableSpecial ? 0 : -(int32_t)s - 1;
                     done = true;
@@ -1958,6 +1964,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     P.disableFine = (flags & (1u << 9)) != 0;
     P.disableLevelLine = (flags & (1u << 8)) != 0;
     P.aabbTesting = (flags & (1u << 7)) != 0;
+    P.skipUniformFill = (flags & ommCpuBakeFlags_DisableSpecialIndices) == 0 && !HostPassesNeeded(d);
 
     sa.indices = in.devIndices;
     sa.texCoords = in.devTexCoords;
@@ -2168,7 +2175,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         if (itemEnd > itemBegin) {
             // special-index scan + XXH64 of this rank's items (their state words are local already)
             ItemPostKernel<<<(itemEnd - itemBegin + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
-                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes, GetUniformDigests(), digest, special);
+                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
+                                                                              GetUniformDigests(), digest, special);
             launches++;
         }
         CUDA_TRY(cudaEventRecord(ev[5], stream));  // end of the per-item post pass
@@ -2309,7 +2317,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             // ref: bake_cpu_impl.cpp:1969-1971 -- second exact dedup over ALL items with the current states, then the last promotion
             // (computed first here; the dedup overwrites duplicates with -1 exactly as the serial order does)
             ItemPostKernel<<<(W + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
-                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, GetUniformDigests(), digest, special);
+                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
+                                                            GetUniformDigests(), digest, special);
             launches += 2;
             if (!disableDup) {
                 FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);

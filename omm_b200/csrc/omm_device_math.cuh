@@ -68,6 +68,7 @@ struct BakeParams {
     int disableFine;       // internal flag bit 9
     int disableLevelLine;  // internal flag bit 8
     int aabbTesting;       // internal flag bit 7
+    int skipUniformFill;   // hierarchical classifier: items proved uniform as a whole need no state words (they become special indices)
 };
 
 struct Tri {

@@ -154,6 +154,15 @@ OMM_HD bool MarginBeatsEdgeBound(const HierItem& it, float margin, float al, flo
     if (!(rem > 0.f)) return false;
     // quadratic branch: needs |d k| >= 1e-6.  2.1 u (ga K + de M(K) + be)^2 <= rem * de * K (1 - 4u)  at both ends of the range
     const float k0 = 9.9e-7f / (de * (1.f + 4.f * u));  // +inf when d == 0: no quadratic branch
+    {
+        // first the hull of the three slope ranges: the bound is convex in K, so passing at the two ends of the hull implies passing
+        // for every class (the common case; three times cheaper than the per-class test below)
+        const float klo = fmaxf(fminf(fminf(it.kmin[0], it.kmin[1]), it.kmin[2]), k0), khi = kAll;
+        if (!(klo <= khi)) return true;  // no slope can reach the quadratic branch
+        const float c1lo = (ga * klo + de * (qy + qx * klo) + be) * (1.f + 8.f * u);
+        const float c1hi = (ga * khi + de * (qy + qx * khi) + be) * (1.f + 8.f * u);
+        if ((2.1f * u * c1lo * c1lo < rem * (de * klo * (1.f - 8.f * u))) && (2.1f * u * c1hi * c1hi < rem * (de * khi * (1.f - 8.f * u)))) return true;
+    }
     bool ok = true;
     for (int j = 0; j < 3; ++j) {
         const float klo = fmaxf(it.kmin[j], k0), khi = it.kmax[j];
