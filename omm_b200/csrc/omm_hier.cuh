@@ -436,10 +436,10 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
     // (D) edge filter
     bool edgesCannotHit = false;
     int s = 0;
+    const float v0 = (h0 + b * q0.x) + (c + d * q0.x) * q0.y;
+    const float v1 = (h0 + b * q1.x) + (c + d * q1.x) * q1.y;
+    const float v2 = (h0 + b * q2.x) + (c + d * q2.x) * q2.y;
     {
-        const float v0 = (h0 + b * q0.x) + (c + d * q0.x) * q0.y;
-        const float v1 = (h0 + b * q1.x) + (c + d * q1.x) * q1.y;
-        const float v2 = (h0 + b * q2.x) + (c + d * q2.x) * q2.y;
         if (v0 > 0.f && v1 > 0.f && v2 > 0.f) s = 1;
         else if (v0 < 0.f && v1 < 0.f && v2 < 0.f) s = -1;
         if (s != 0 && it.ok) {
@@ -488,7 +488,10 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
     }
     if (edgesCannotHit) return;
     if (!countsMatter && defer(px, py)) return;
-    if (EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d)) {
+    // (Testing the edges whose end points straddle the level line first was measured: the per-lane order makes the calls diverge
+    // and costs more than the skipped tests save.)
+    const bool hit = EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d);
+    if (hit) {
         cov.above += 1;
         cov.below += 1;
     }
