@@ -622,7 +622,17 @@ __device__ __forceinline__ int WarpTestRegions(const BakeParams& P, const DevMip
     int n = valid ? fw * fh : 0;
     int verdict = 0;
     bool decided = !valid;
-    if (valid && n > kHierMaxCells) {
+    if (valid && P.tex.strongPlus != nullptr) {
+        const HierItem hi = LoadHierItem(hierItems + w);
+        if (ItemWithinStrongCaps(hi)) {
+            verdict = StrongRectSide(P, m, hi, rb, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (I)
+            if (verdict != 0) {
+                decided = true;
+                n = 0;
+            }
+        }
+    }
+    if (valid && !decided && n > kHierMaxCells) {
         verdict = FlatRectSide<Cfg>(P, m, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (H) or split
         decided = true;
         n = 0;
@@ -737,7 +747,8 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
             else if (L > 6 && (a & 63u) == 0 && b - a == 64) haveBox = MakeNodeBox(m, hi, a >> 6, L - 6, box);
             if (haveBox) {
                 // (H) the whole piece over a constant area: one table query, whatever its size
-                const int sFlat = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
+                int sFlat = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
+                if (sFlat == 0 && ItemWithinStrongCaps(hi)) sFlat = StrongRectSide(P, m, hi, box, box.cx0, box.cy0, box.cx1, box.cy1);  // (I)
                 if (sFlat != 0) {
                     const uint32_t pat = (uint32_t)(sFlat > 0 ? P.stateGT : P.stateLE) * 0x55555555u;
                     // a WHOLE item proved uniform becomes a special index and its block is never read (ItemPostKernel takes the state
@@ -748,7 +759,11 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
                     continue;
                 }
             }
-            if (haveBox && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
+            // (I) answers region queries from the tables when the piece lies inside the texture and within the caps: no bitmap then
+            const bool strongOk = ItemWithinStrongCaps(hi) && P.tex.strongPlus != nullptr;
+            const bool strongCovers = strongOk && haveBox && box.cx0 >= 0 && box.cy0 >= 0 && box.cx1 <= m.w - 2 && box.cy1 <= m.h - 2 &&
+                                      box.hix - box.lox + 1.f + hi.deltaEdge <= kStrongMaxExtent && box.hiy - box.loy + 1.f + hi.deltaEdge <= kStrongMaxExtent;
+            if (haveBox && !strongCovers && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
                 const int fw = box.cx1 - box.cx0 + 1, fh = box.cy1 - box.cy0 + 1;
                 sPlus[warp][lane] = 0;
                 sMinus[warp][lane] = 0;
@@ -781,7 +796,10 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
                 int s = 0;
                 if (valid) {
                     RegionBox rb;
-                    if (MakeRegionBox(m, hi, idx, L - e, rb)) s = LookupCellMap(map, rb);
+                    if (MakeRegionBox(m, hi, idx, L - e, rb)) {
+                        if (strongOk) s = StrongRectSide(P, m, hi, rb, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (I)
+                        if (s == 0) s = LookupCellMap(map, rb);
+                    }
                     if (s != 0) HierFillGlobal(words, e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
                 }
                 votesUp += __popc(__ballot_sync(0xFFFFFFFFu, s > 0));
@@ -1434,6 +1452,36 @@ static cudaError_t SatColumnPass(int w, int h, uint32_t* sat, cudaStream_t strea
     cudaFreeAsync(segTotals, stream);
     return cudaGetLastError();
 }
+// (I) row pass of the two item-independent whole-cell tables (not a cap pass above / below the cutoff), interior cells of mip 0
+template <bool kFp32>
+__global__ void StrongSatRows(const BakeParams P, uint32_t* __restrict__ satPlus, uint32_t* __restrict__ satMinus) {
+    const DevMip& m = P.tex.mips[0];
+    const int w = m.w, h = m.h;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= h - 1) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t carryP = 0, carryM = 0;
+    for (int base = 0; base < w - 1; base += 32) {
+        const int x = base + lane;
+        uint32_t vp = 0, vm = 0;
+        if (x < w - 1) {
+            const int s = StrongCellSide<KernelCfg<kAddrClamp, kFp32>>(P, m, x, row);
+            vp = s > 0 ? 0u : 1u;
+            vm = s < 0 ? 0u : 1u;
+        }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t op = __shfl_up_sync(0xFFFFFFFFu, vp, d), om = __shfl_up_sync(0xFFFFFFFFu, vm, d);
+            if (lane >= d) { vp += op; vm += om; }
+        }
+        vp += carryP; vm += carryM;
+        if (x < w - 1) {
+            satPlus[(size_t)row * (w - 1) + x] = vp;
+            satMinus[(size_t)row * (w - 1) + x] = vm;
+        }
+        carryP = __shfl_sync(0xFFFFFFFFu, vp, 31);
+        carryM = __shfl_sync(0xFFFFFFFFu, vm, 31);
+    }
+}
 __global__ void SatCols(int w, int h, uint32_t* __restrict__ sat) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= w) return;
@@ -1544,6 +1592,7 @@ ommResult UploadTexture(TextureObject* tex, const Logger& log) {
     tex->dev.isFp32 = tex->format == ommCpuTextureFormat_FP32;
     tex->dev.sat = nullptr;
     tex->dev.flatSat = nullptr;
+    tex->dev.strongPlus = tex->dev.strongMinus = nullptr;
     if (tex->HasAlphaCutoff()) {  // ref: texture_impl.cpp:91 -- SAT <=> alphaCutoff >= 0
         CUDA_TRY(cudaMalloc(&tex->devSat, totalTexels * sizeof(uint32_t)));
         for (uint32_t i = 0; i < tex->mipCount; ++i) {
@@ -1565,6 +1614,9 @@ void DestroyTextureDevice(TextureObject* tex) {
     if (tex->devTexels) cudaFree(tex->devTexels);
     if (tex->devSat) cudaFree(tex->devSat);
     if (tex->devFlatSat) cudaFreeAsync(tex->devFlatSat, 0);
+    if (tex->devStrongPlus) cudaFreeAsync(tex->devStrongPlus, 0);
+    if (tex->devStrongMinus) cudaFreeAsync(tex->devStrongMinus, 0);
+    tex->devStrongPlus = tex->devStrongMinus = nullptr;
     tex->devTexels = nullptr;
     tex->devSat = nullptr;
     tex->devFlatSat = nullptr;
@@ -1575,32 +1627,54 @@ void DestroyTextureDevice(TextureObject* tex) {
 // normally baked with one cutoff; another cutoff rebuilds it).  Returns nullptr when the texture is too small or memory is short --
 // the classifier then simply has no O(1) answer for large footprints.  The build is ordered before the caller's later work on
 // `stream` by running on that stream; concurrent bakes serialise on the texture's mutex.
-static const uint32_t* GetFlatSat(TextureObject* tex, float cutoff, cudaStream_t stream, uint32_t* launches) {
+// (I) is OFF by default: measured on B200 at config 3, answering region tests from the two 64 MB tables (four to eight scattered
+// 4-byte loads each) is 7 % SLOWER than the per-item bitmap, whose texel gathers are coalesced and shared (13.0 vs 12.2 ms).  The
+// code stays for textures / workloads where it may pay; OMM_B200_STRONG_TABLES=1 enables it.
+static bool UseStrongTables() {
+    static const bool on = getenv("OMM_B200_STRONG_TABLES") != nullptr;
+    return on;
+}
+static bool GetCellTables(TextureObject* tex, BakeParams& P, cudaStream_t stream, uint32_t* launches) {
     const DevMip& m = tex->dev.mips[0];
-    if (m.w < 2 || m.h < 2) return nullptr;
+    P.tex.flatSat = P.tex.strongPlus = P.tex.strongMinus = nullptr;
+    if (m.w < 2 || m.h < 2) return false;
+    const float cutoff = P.cutoff;
     std::lock_guard<std::mutex> g(tex->flatMu);
-    if (tex->flatValid && tex->flatCutoff == cutoff) return tex->devFlatSat;
-    if (tex->flatValid) {
-        // another bake may still be reading the table of the previous cutoff
-        cudaDeviceSynchronize();
-        tex->flatValid = false;
+    if (!(tex->flatValid && tex->flatCutoff == cutoff)) {
+        if (tex->flatValid) {
+            // another bake may still be reading the tables of the previous cutoff
+            cudaDeviceSynchronize();
+            tex->flatValid = false;
+        }
+        const size_t bytes = sizeof(uint32_t) * (size_t)(m.w - 1) * (size_t)(m.h - 1);
+        uint32_t** bufs[3] = {&tex->devFlatSat, &tex->devStrongPlus, &tex->devStrongMinus};
+        const int numTables = UseStrongTables() ? 3 : 1;
+        for (int i = 0; i < numTables; ++i)
+            if (!*bufs[i] && cudaMallocAsync((void**)bufs[i], bytes, stream) != cudaSuccess) {
+                cudaGetLastError();
+                *bufs[i] = nullptr;
+                return false;
+            }
+        FlatSatRows<<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(tex->devTexels, tex->dev.isFp32, m.w, m.h, cutoff, tex->devFlatSat);
+        if (numTables == 3) {
+            if (tex->dev.isFp32) StrongSatRows<true><<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(P, tex->devStrongPlus, tex->devStrongMinus);
+            else StrongSatRows<false><<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(P, tex->devStrongPlus, tex->devStrongMinus);
+        }
+        for (int i = 0; i < numTables; ++i)
+            if (SatColumnPass(m.w - 1, m.h - 1, *bufs[i], stream) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+        *launches += numTables == 3 ? 11 : 4;
+        // later bakes may run on other streams: make the tables visible to them before they are published
+        cudaStreamSynchronize(stream);
+        tex->flatCutoff = cutoff;
+        tex->flatValid = true;
     }
-    if (!tex->devFlatSat && cudaMallocAsync((void**)&tex->devFlatSat, sizeof(uint32_t) * (size_t)(m.w - 1) * (size_t)(m.h - 1), stream) != cudaSuccess) {
-        cudaGetLastError();
-        tex->devFlatSat = nullptr;
-        return nullptr;
-    }
-    FlatSatRows<<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(tex->devTexels, tex->dev.isFp32, m.w, m.h, cutoff, tex->devFlatSat);
-    if (SatColumnPass(m.w - 1, m.h - 1, tex->devFlatSat, stream) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    *launches += 4;
-    // later bakes may run on other streams: make the table visible to them before it is published
-    cudaStreamSynchronize(stream);
-    tex->flatCutoff = cutoff;
-    tex->flatValid = true;
-    return tex->devFlatSat;
+    P.tex.flatSat = tex->devFlatSat;
+    P.tex.strongPlus = UseStrongTables() ? tex->devStrongPlus : nullptr;
+    P.tex.strongMinus = UseStrongTables() ? tex->devStrongMinus : nullptr;
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -2126,7 +2200,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
         if (itemEnd > itemBegin && useHier) {
-            P.tex.flatSat = GetFlatSat(const_cast<TextureObject*>(tex), P.cutoff, stream, &launches);
+            GetCellTables(const_cast<TextureObject*>(tex), P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
             // worst case of a chunk: the nominal number of initial regions plus the rest of its last item (at most 4^9 regions at level 12)
             const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
             const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, hierChunkRegions) + (1ull << 18), regionEnd - regionBegin);

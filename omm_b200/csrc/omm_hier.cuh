@@ -205,7 +205,7 @@ OMM_HD bool MakeRegionBox(const DevMip& m, const HierItem& it, uint32_t index, u
 //     with the same s: TestRegion may take the answer from a per-item bitmap of these cells (HierTestInitial) instead of
 //     evaluating it.
 template <class Cfg>
-OMM_HD int WholeCellSide(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& box, int cx, int cy) {
+OMM_HD int WholeCellSideQ(const BakeParams& P, const DevMip& m, const HierItem& it, float qx, float qy, int cx, int cy) {
     const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx, m.w, m.log2w), x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cx + 1, m.w, m.log2w);
     const int y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy, m.h, m.log2h), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, cy + 1, m.h, m.log2h);
     const float gx = TexFetch<Cfg>(P, m, x0, y0);
@@ -227,12 +227,63 @@ OMM_HD int WholeCellSide(const BakeParams& P, const DevMip& m, const HierItem& i
     else if (mx < 0.f) { s = -1; margin = -mx; }
     else return 0;
     if ((s > 0) != o0) return 0;
-    const float fx = (float)cx, fy = (float)cy;
-    const float qx = fmaxf(fabsf(box.lox - fx), fabsf(box.hix - fx)) + it.deltaEdge;
-    const float qy = fmaxf(fabsf(box.loy - fy), fabsf(box.hiy - fy)) + it.deltaEdge;
     const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
     if (!MarginBeatsEdgeBound(it, margin, fabsf(a), fabsf(b), fabsf(c), fabsf(d), gmaxAbs, fabsf(P.cutoff), qx, qy)) return 0;
     return s;
+}
+template <class Cfg>
+OMM_HD int WholeCellSide(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& box, int cx, int cy) {
+    const float fx = (float)cx, fy = (float)cy;
+    const float qx = fmaxf(fabsf(box.lox - fx), fabsf(box.hix - fx)) + it.deltaEdge;
+    const float qy = fmaxf(fabsf(box.loy - fy), fabsf(box.hiy - fy)) + it.deltaEdge;
+    return WholeCellSideQ<Cfg>(P, m, it, qx, qy, cx, cy);
+}
+
+// (I) Item-independent whole-cell sides.  The bound R of (B) grows with the hull of the slope ranges, with the pad delta and with
+//     the coordinate extent Q (MarginBeatsEdgeBound is monotone in all of them; the quadratic term is convex in K, so its maximum
+//     over a sub-range is at most its maximum over the hull).  A cell that passes the whole-cell test (F) for the CAP item
+//     -- every slope in [0, kStrongMaxSlope], delta = kStrongMaxDelta, Q = kStrongMaxExtent -- therefore passes it for every item
+//     within the caps.  The two summed-area tables strongPlus / strongMinus count, over the interior cells of mip 0, the cells
+//     that are NOT such a pass on the respective side (built per texture and cutoff, like (H)); a footprint inside the texture
+//     with a zero count is answered with four loads instead of one texture gather and one bound evaluation per cell.
+constexpr float kStrongMaxSlope = 64.f, kStrongMaxDelta = 0.05f, kStrongMaxExtent = 16.f;
+OMM_HD HierItem StrongCapItem() {
+    HierItem it;
+    it.p0 = it.p1 = it.p2 = make_float2(0.f, 0.f);
+    it.level = 0;
+    it.epsRegion = it.epsSingle = 0.f;
+    it.deltaEdge = kStrongMaxDelta;
+    for (int j = 0; j < 3; ++j) { it.kmin[j] = 0.f; it.kmax[j] = kStrongMaxSlope; }
+    it.pitX = it.pitY = 0.f;
+    it.ok = 1;
+    it.pad = 0;
+    return it;
+}
+OMM_HD bool ItemWithinStrongCaps(const HierItem& it) {
+    return it.ok && it.deltaEdge <= kStrongMaxDelta && it.kmax[0] <= kStrongMaxSlope && it.kmax[1] <= kStrongMaxSlope && it.kmax[2] <= kStrongMaxSlope;
+}
+// side of interior cell (cx, cy) for the cap item: +1 / -1 / 0   (0 <= cx <= w - 2, 0 <= cy <= h - 2: no addressing involved)
+template <class Cfg>
+OMM_HD int StrongCellSide(const BakeParams& P, const DevMip& m, int cx, int cy) {
+    return WholeCellSideQ<Cfg>(P, m, StrongCapItem(), kStrongMaxExtent, kStrongMaxExtent, cx, cy);
+}
+// +1 / -1 when every cell of the rectangle is a cap pass of that side; `box` gives the coordinate extent the caller needs covered
+OMM_HD int StrongRectSide(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& box, int cx0, int cy0, int cx1, int cy1) {
+    const uint32_t* sp = P.tex.strongPlus;
+    const uint32_t* sm = P.tex.strongMinus;
+    if (!sp || !sm || cx0 < 0 || cy0 < 0 || cx1 > m.w - 2 || cy1 > m.h - 2 || cx1 < cx0 || cy1 < cy0) return 0;
+    // Q of any cell of the box: at most the box size plus delta
+    // (a footprint cell is at most one cell beyond either end of the box)
+    if (!(box.hix - box.lox + 1.f + it.deltaEdge <= kStrongMaxExtent && box.hiy - box.loy + 1.f + it.deltaEdge <= kStrongMaxExtent)) return 0;
+    const size_t sw = (size_t)(m.w - 1);
+    const size_t iA = (size_t)(cy0 - 1) * sw + (size_t)(cx0 - 1), iB = (size_t)(cy0 - 1) * sw + (size_t)cx1, iC = (size_t)cy1 * sw + (size_t)(cx0 - 1),
+                 iD = (size_t)cy1 * sw + (size_t)cx1;
+    const bool hasA = cx0 > 0 && cy0 > 0, hasB = cy0 > 0, hasC = cx0 > 0;
+    const uint32_t badPlus = LoadRO(sp + iD) + (hasA ? LoadRO(sp + iA) : 0u) - (hasB ? LoadRO(sp + iB) : 0u) - (hasC ? LoadRO(sp + iC) : 0u);
+    if (badPlus == 0u) return 1;
+    const uint32_t badMinus = LoadRO(sm + iD) + (hasA ? LoadRO(sm + iA) : 0u) - (hasB ? LoadRO(sm + iB) : 0u) - (hasC ? LoadRO(sm + iC) : 0u);
+    if (badMinus == 0u) return -1;
+    return 0;
 }
 
 // Bitmap of whole-cell sides over the footprint of an item (at most 32 x 32 cells): bit x of plus[y] / minus[y].
@@ -380,6 +431,10 @@ OMM_HD int TestRegionCell(const BakeParams& P, const DevMip& m, const HierItem& 
 template <class Cfg>
 OMM_HD int TestRegionBox(const BakeParams& P, const DevMip& m, const HierItem& it, const RegionBox& rb) {
     const int cx0 = rb.cx0, cy0 = rb.cy0, cx1 = rb.cx1, cy1 = rb.cy1;
+    if (ItemWithinStrongCaps(it)) {
+        const int s = StrongRectSide(P, m, it, rb, cx0, cy0, cx1, cy1);  // (I)
+        if (s != 0) return s;
+    }
     if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kHierMaxCells) return FlatRectSide<Cfg>(P, m, cx0, cy0, cx1, cy1);  // (H) or split
     const bool single = cx0 == cx1 && cy0 == cy1;
     int sAll = 0;

@@ -85,6 +85,8 @@ struct DevTexture {
     const uint32_t* sat;      // inclusive summed-area table of (alpha > cutoff), or nullptr
     const uint32_t* flatSat;  // mip 0: inclusive summed-area table over the (w-1) x (h-1) interior cells of "not a constant, clearly one-sided
                               // cell" for the bake's alpha cutoff (omm_hier.cuh (H)), or nullptr
+    const uint32_t* strongPlus;   // mip 0: summed-area tables of "not an item-independent whole-cell pass above / below the cutoff"
+    const uint32_t* strongMinus;  // (omm_hier.cuh (I)), same layout as flatSat, or nullptr
     int isFp32;
     int mipCount;
     DevMip mips[kMaxMips];
@@ -104,6 +106,8 @@ struct TextureObject {
     // constant-cell table of the hierarchical classifier, built on first use for a given alpha cutoff and kept with the texture
     std::mutex flatMu;
     uint32_t* devFlatSat = nullptr;
+    uint32_t* devStrongPlus = nullptr;
+    uint32_t* devStrongMinus = nullptr;
     float flatCutoff = 0.f;
     bool flatValid = false;
     bool hasSerializedSat = false;  // deserialized textures: the blob carried a summed-area table (ref: texture_impl.h:105-108)

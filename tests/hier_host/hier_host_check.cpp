@@ -90,7 +90,29 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
             ItemCellMap map{0, 0, 0, 0, plus, minus};
             RegionBox box;
             const bool haveBox = hi.ok && L >= 3 && (L > 6 ? MakeNodeBox(m, hi, node, L - 6, box) : MakeItemBox(m, hi, box));
-            if (haveBox && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
+            // piece-level answers of HierTestInitial: constant area (H), then the item-independent tables (I)
+            if (haveBox) {
+                int sPiece = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
+                if (sPiece == 0 && ItemWithinStrongCaps(hi)) sPiece = StrongRectSide(P, m, hi, box, box.cx0, box.cy0, box.cx1, box.cy1);
+                if (sPiece != 0) {
+                    const uint32_t n = 1u << (2 * nl);
+                    for (uint32_t i = 0; i < n; ++i) {
+                        const int want = ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, (node << (2 * nl)) + i, L);
+                        st->microTriangles++;
+                        if (want != (sPiece > 0 ? P.stateGT : P.stateLE)) {
+                            if (st->mismatches == 0) { st->firstBadItem = it; st->firstBadIndex = (node << (2 * nl)) + i; st->firstBadGot = sPiece; st->firstBadWant = want; }
+                            st->mismatches++;
+                        }
+                    }
+                    st->passes[0] += 1u << (2 * (nl - e0));
+                    st->tests[0] += 1u << (2 * (nl - e0));
+                    continue;
+                }
+            }
+            const bool strongCovers = ItemWithinStrongCaps(hi) && P.tex.strongPlus != nullptr && haveBox && box.cx0 >= 0 && box.cy0 >= 0 &&
+                                      box.cx1 <= m.w - 2 && box.cy1 <= m.h - 2 && box.hix - box.lox + 1.f + hi.deltaEdge <= kStrongMaxExtent &&
+                                      box.hiy - box.loy + 1.f + hi.deltaEdge <= kStrongMaxExtent;
+            if (haveBox && !strongCovers && box.cx1 - box.cx0 < 32 && box.cy1 - box.cy0 < 32) {
                 map.cx0 = box.cx0; map.cy0 = box.cy0; map.fw = box.cx1 - box.cx0 + 1; map.fh = box.cy1 - box.cy0 + 1;
                 for (int y = 0; y < map.fh; ++y)
                     for (int x = 0; x < map.fw; ++x) {
@@ -158,6 +180,24 @@ extern "C" __attribute__((visibility("default"))) int hier_host_check(const void
                 flat[i] = bad + (x ? flat[i - 1] : 0u) + (y ? flat[i - (w - 1)] : 0u) - ((x && y) ? flat[i - (w - 1) - 1] : 0u);
             }
         P.tex.flatSat = flat.data();
+    }
+    // (I) item-independent whole-cell tables, as StrongSatRows + the column pass compute them
+    std::vector<uint32_t> strongP, strongM;
+    if (w >= 2 && h >= 2) {
+        strongP.resize((size_t)(w - 1) * (h - 1));
+        strongM.resize((size_t)(w - 1) * (h - 1));
+        for (int y = 0; y < h - 1; ++y)
+            for (int x = 0; x < w - 1; ++x) {
+                const int s = isFp32 ? StrongCellSide<KernelCfg<kAddrClamp, true>>(P, P.tex.mips[0], x, y) : StrongCellSide<KernelCfg<kAddrClamp, false>>(P, P.tex.mips[0], x, y);
+                const size_t i = (size_t)y * (w - 1) + x;
+                auto acc = [&](std::vector<uint32_t>& v, uint32_t bad) {
+                    v[i] = bad + (x ? v[i - 1] : 0u) + (y ? v[i - (w - 1)] : 0u) - ((x && y) ? v[i - (w - 1) - 1] : 0u);
+                };
+                acc(strongP, s > 0 ? 0u : 1u);
+                acc(strongM, s < 0 ? 0u : 1u);
+            }
+        P.tex.strongPlus = strongP.data();
+        P.tex.strongMinus = strongM.data();
     }
     if (isFp32) CheckItems<KernelCfg<kAddrGeneric, true>>(P, uvs, levels, numItems, st);
     else CheckItems<KernelCfg<kAddrGeneric, false>>(P, uvs, levels, numItems, st);
