@@ -317,18 +317,18 @@ def run_b200(a):
     cls_ms = sum(classify_ms) / len(classify_ms)
     achieved = classify_bytes / (cls_ms * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1b_stage_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1c_stage_traffic.json")
     if world == 1 and a.tris == 1_000_000 and a.level == 6 and a.tex == 4096 and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_read_per_bake"] + tj["dram_bytes_written_per_bake"]  # ncu capture of this very command, see the file
-    roofline = {"bound": "hbm", "kernel": "classification stage = HierTestInitial + 2x HierTestList + HierLeaves per chunk (HierLeaves ~55 % of it)",
+    roofline = {"bound": "hbm", "kernel": "classification stage = HierTestInitial + HierTestUnresolved + 2x HierTestList + HierLeaves per chunk (HierLeaves ~55 % of it)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "kernel_ms": cls_ms, "algorithmic_bytes": classify_bytes,
                 "note": "instruction-issue bound, not HBM bound: 0.27 algorithmic bytes per micro-triangle against the bit-exact level-line arithmetic "
                         "(IEEE divisions and square roots) of every micro-triangle the level line touches; the hierarchical classifier removes the "
-                        "arithmetic of provably uniform regions (97 % of the micro-triangles), profiles/r1b_* hold issue utilisation and pipe mix"}
+                        "arithmetic of provably uniform regions (97 % of the micro-triangles), profiles/r1c_* hold issue utilisation and pipe mix"}
     # whole-path algorithmic bytes per SURVEY 8d: texture + geometry + outputs
     path_bytes = tex_bytes + wl.indices.nbytes + wl.texcoords.nbytes + array_bytes + 8 * desc_count + 4 * a.tris
 
