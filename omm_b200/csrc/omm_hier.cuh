@@ -525,11 +525,16 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
         }
     }
     {
+        // (C) at the leaf: a texel centre separated from the micro-triangle's box by pit in x or in y is provably outside for
+        // PointInTriangle (the q are the cell-local vertex coordinates, epsSingle covers their rounding against r - cell)
+        const float lox = fminf(fminf(q0.x, q1.x), q2.x) - it.epsSingle, hix = fmaxf(fmaxf(q0.x, q1.x), q2.x) + it.epsSingle;
+        const float loy = fminf(fminf(q0.y, q1.y), q2.y) - it.epsSingle, hiy = fmaxf(fmaxf(q0.y, q1.y), q2.y) + it.epsSingle;
+        const bool farL = lox >= it.pitX, farR = 1.f - hix >= it.pitX, farB = loy >= it.pitY, farT = 1.f - hiy >= it.pitY;
         const float ipx = pfx * m.rcpw, ipy = pfy * m.rcph;
-        const bool in0 = PointInTri(tri, ipx, ipy);
-        const bool in1 = PointInTri(tri, ipx + 0.0f, ipy + m.rcph);
-        const bool in2 = PointInTri(tri, ipx + m.rcpw, ipy + m.rcph);
-        const bool in3 = PointInTri(tri, ipx + m.rcpw, ipy + 0.0f);
+        const bool in0 = !(farL || farB) && PointInTri(tri, ipx, ipy);
+        const bool in1 = !(farL || farT) && PointInTri(tri, ipx + 0.0f, ipy + m.rcph);
+        const bool in2 = !(farR || farT) && PointInTri(tri, ipx + m.rcpw, ipy + m.rcph);
+        const bool in3 = !(farR || farB) && PointInTri(tri, ipx + m.rcpw, ipy + 0.0f);
         const bool isOpaque = (in0 && o0) || (in1 && o1) || (in2 && o2) || (in3 && o3);
         const bool isTransparent = (in0 && !o0) || (in1 && !o1) || (in2 && !o2) || (in3 && !o3);
         if (isOpaque) cov.above += 1;
