@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise ncu outputs into text files for profiles/:
-   tools_ncu_summary.py launches <launches.csv>          -> per-kernel device-time shares
-   tools_ncu_summary.py kernel <raw.csv>                 -> key metrics of one captured kernel (ncu -i rep --page raw --csv)
+   scripts/ncu_summary.py launches <launches.csv>          -> per-kernel device-time shares
+   scripts/ncu_summary.py kernel <raw.csv>                 -> key metrics of one captured kernel (ncu -i rep --page raw --csv)
 """
 import collections
 import csv
