@@ -345,7 +345,7 @@ def run_b200(a):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "256 MiB buffer written between steps (outside the timed events)",
                        "work_items": work_items, "array_data_bytes": array_bytes, "desc_count": desc_count,
-                       "path_algorithmic_bytes": path_bytes, "setup_ms": setup_ms, "classify_ms": cls_ms, "post_ms": post_ms, "item_post_ms": item_post_ms, "gather_ms": gather_ms,
+                       "path_algorithmic_bytes": path_bytes, "step_ms": [round(x, 3) for x in step_ms], "setup_ms": setup_ms, "classify_ms": cls_ms, "post_ms": post_ms, "item_post_ms": item_post_ms, "gather_ms": gather_ms,
                        "sharding": "none" if world == 1 else f"work items split over {world} ranks, 1 NCCL all-gather of state blocks"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -978,7 +978,8 @@ static int ClassifierOverride() {
 }
 static bool SelectHierKernels(const BakeParams& P, HierKernels* out) {
     if (ClassifierOverride() != 0) return false;
-    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine && !P.useCoarse && P.tex.mipCount == 1)) return false;
+    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine && P.tex.mipCount == 1)) return false;
+    if (P.useCoarse && !P.coarseSameCutoff) return false;  // SAT of another cutoff than the bake's: see LeafClassify
     const bool pow2 = P.tex.mips[0].isPow2 != 0;
     if (P.tex.isFp32) {
         if (P.addrMode == ommTextureAddressMode_Wrap && pow2) *out = MakeHierKernels<KernelCfg<kAddrWrapPow2, true>>();
@@ -2041,6 +2042,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     P.promotion = d.unknownStatePromotion;
     P.pow2Mip0 = tex->dev.mips[0].isPow2;
     P.useCoarse = tex->dev.sat != nullptr && tex->mipCount == 1 && P.filterLinear;
+    P.coarseSameCutoff = tex->alphaCutoff == d.alphaCutoff;
     P.disableFine = (flags & (1u << 9)) != 0;
     P.disableLevelLine = (flags & (1u << 8)) != 0;
     P.aabbTesting = (flags & (1u << 7)) != 0;

@@ -68,6 +68,7 @@ struct BakeParams {
     int disableFine;       // internal flag bit 9
     int disableLevelLine;  // internal flag bit 8
     int aabbTesting;       // internal flag bit 7
+    int coarseSameCutoff;  // the texture's SAT was built for the bake's alpha cutoff
     int skipUniformFill;   // hierarchical classifier: items proved uniform as a whole need no state words (they become special indices)
 };
 

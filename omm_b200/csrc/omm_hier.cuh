@@ -586,6 +586,14 @@ OMM_HD bool LeafEdgeTests(const BakeParams& P, const DevMip& m, const HierItem& 
 template <class Cfg, class Defer>
 OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, Defer&& defer) {
     const Tri st = MicroTri(it.p0, it.p1, it.p2, index, it.level);
+    if (P.useCoarse) {
+        // SAT pass of the reference first (bake_cpu_impl.cpp:749-801, 861-864).  The hierarchical path is only taken when the
+        // texture's cutoff equals the bake's (SelectHierKernels): a decisive SAT answer then agrees with any region proof, because
+        // the SAT rectangle holds the four texels of p0's cell and a patch whose corners are all on one side cannot have h of the
+        // other sign with margin.
+        const int cs = CoarseState<Cfg>(P, st);
+        if (cs >= 0 && cs != ommOpacityState_UnknownOpaque) return cs;
+    }
     if (P.tex.flatSat) {
         // (H) a micro-triangle of many texels over a constant area: its footprint (A) instead of a walk over every cell
         const float W = (float)m.w, H = (float)m.h, eps = it.epsSingle;

@@ -144,7 +144,7 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
 
 extern "C" __attribute__((visibility("default"))) int hier_host_check(const void* texels, int isFp32, int w, int h, int addrMode, float borderAlpha,
                                                                       float cutoff, int stateGT, int stateLE, int format, int promotion, const float* uvs,
-                                                                      const uint8_t* levels, uint32_t numItems, HierCheckStats* st) {
+                                                                      const uint8_t* levels, uint32_t numItems, HierCheckStats* st, int useSat) {
     memset(st, 0, sizeof(*st));
     BakeParams P{};
     P.tex.texels = texels;
@@ -165,6 +165,20 @@ extern "C" __attribute__((visibility("default"))) int hier_host_check(const void
     P.globalFormat = format;
     P.promotion = promotion;
     P.pow2Mip0 = m.isPow2;
+    // optional SAT pass with the texture's cutoff == the bake's (the only SAT configuration the hierarchical path takes)
+    std::vector<uint32_t> sat;
+    if (useSat) {
+        sat.resize((size_t)w * h);
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const size_t i = (size_t)y * w + x;
+                const float a = isFp32 ? ((const float*)texels)[i] : (float)((const uint8_t*)texels)[i] * (1.f / 255.f);
+                sat[i] = (a > cutoff ? 1u : 0u) + (x ? sat[i - 1] : 0u) + (y ? sat[i - w] : 0u) - ((x && y) ? sat[i - w - 1] : 0u);
+            }
+        P.tex.sat = sat.data();
+        P.useCoarse = 1;
+        P.coarseSameCutoff = 1;
+    }
     // (H) constant-cell table of mip 0, as BuildFlatSat / FlatSatRows + SatCols compute it on the device
     std::vector<uint32_t> flat;
     if (w >= 2 && h >= 2) {

@@ -33,14 +33,14 @@ def lib():
 
 
 def check(lib, tex, uvs, levels, addr=capi.ADDR_WRAP, cutoff=0.5, promotion=capi.PROMOTE_FORCE_OPAQUE, fmt=capi.FORMAT_4_STATE, gt=capi.STATE_O,
-          le=capi.STATE_T, border=0.0):
+          le=capi.STATE_T, border=0.0, use_sat=False):
     tex = np.ascontiguousarray(tex)
     uvs = np.ascontiguousarray(uvs, dtype=np.float32)
     levels = np.ascontiguousarray(levels, dtype=np.uint8)
     st = Stats()
     h, w = tex.shape
     lib.hier_host_check(tex.ctypes.data_as(ctypes.c_void_p), int(tex.dtype == np.float32), w, h, addr, ctypes.c_float(border), ctypes.c_float(cutoff), gt, le,
-                        fmt, promotion, uvs.ctypes.data_as(ctypes.c_void_p), levels.ctypes.data_as(ctypes.c_void_p), len(levels), ctypes.byref(st))
+                        fmt, promotion, uvs.ctypes.data_as(ctypes.c_void_p), levels.ctypes.data_as(ctypes.c_void_p), len(levels), ctypes.byref(st), int(use_sat))
     assert st.mismatches == 0, (f"{st.mismatches} of {st.microTriangles} micro-triangles differ from the reference walk; first: item {st.firstBadItem} "
                                 f"index {st.firstBadIndex} got {st.firstBadGot} want {st.firstBadWant}")
     return st
@@ -135,3 +135,14 @@ def test_constant_areas_and_large_micro_triangles(lib):
     assert st.passes[0] + st.passes[1] + st.passes[2] > 0
     check(lib, tex, tris(rng, 100, 150, 512, -0.3, 1.3), rng.integers(0, 4, 100), addr=capi.ADDR_CLAMP)
     check(lib, (tex * 255).astype(np.uint8), tris(rng, 100, 100, 512, 0.1, 0.9), rng.integers(1, 5, 100))
+
+
+def test_sat_pass_with_the_bake_cutoff(lib):
+    """Textures created with an alpha cutoff equal to the bake's: the reference's SAT pass runs before the fine classification and
+    the hierarchical path must agree with it (leaves apply it first; region proofs are compatible with any decisive SAT answer)."""
+    rng = np.random.default_rng(11)
+    t = textures(rng)
+    check(lib, t["noise"], tris(rng, 200, 6, 1024, -0.3, 1.3), np.full(200, 6), use_sat=True)
+    check(lib, t["checker"], tris(rng, 150, 9, 256, axis_aligned=True), np.full(150, 5), use_sat=True, addr=capi.ADDR_CLAMP)
+    check(lib, t["noise8"], tris(rng, 150, 20, 512), rng.integers(0, 6, 150), use_sat=True, gt=capi.STATE_UO, le=capi.STATE_T)
+    check(lib, t["smooth"], tris(rng, 150, 10, 256, -0.2, 1.2), np.full(150, 6), use_sat=True, promotion=capi.PROMOTE_NEAREST)
