@@ -580,7 +580,9 @@ __global__ void HierPrepare(const BakeParams P, const ItemRec* __restrict__ item
     const uint32_t w = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= itemEnd) return;
     const ItemRec it = items[w];
-    hierItems[w] = MakeHierItem(P.tex.mips[0], it.p0, it.p1, it.p2, it.level, it.degenerate != 0);
+    // one set of constants per mip (they depend on the mip's size), laid out [item][mip]
+    const int M = P.tex.mipCount;
+    for (int k = 0; k < M; ++k) hierItems[(size_t)w * M + k] = MakeHierItem(P.tex.mips[k], it.p0, it.p1, it.p2, it.level, it.degenerate != 0);
 }
 
 __device__ __forceinline__ HierItem LoadHierItem(const HierItem* __restrict__ p) {
@@ -615,15 +617,16 @@ __device__ __forceinline__ void HierFillGlobal(uint32_t* __restrict__ words, uin
 // region has 1 to 16 footprint cells and fails at its first bad one, so evaluating them lane by lane leaves two thirds of the warp
 // idle.  Returns this lane's verdict: +1 / -1 = every micro-triangle of the region is on that side, 0 = split it.
 template <class Cfg>
-__device__ __forceinline__ int WarpTestRegions(const BakeParams& P, const DevMip& m, const HierItem* __restrict__ hierItems, bool valid, uint32_t w,
+__device__ __forceinline__ int WarpTestRegions(const BakeParams& P, const DevMip& m, const HierItem* __restrict__ hierItems, int mip, bool valid, uint32_t w,
                                                const RegionBox& rb) {
+    const int M = P.tex.mipCount;
     const uint32_t lane = threadIdx.x & 31;
     const int fw = rb.cx1 - rb.cx0 + 1, fh = rb.cy1 - rb.cy0 + 1;
     int n = valid ? fw * fh : 0;
     int verdict = 0;
     bool decided = !valid;
     if (valid && P.tex.strongPlus != nullptr) {
-        const HierItem hi = LoadHierItem(hierItems + w);
+        const HierItem hi = LoadHierItem(hierItems + (size_t)w * M + mip);
         if (ItemWithinStrongCaps(hi)) {
             verdict = StrongRectSide(P, m, hi, rb, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (I)
             if (verdict != 0) {
@@ -670,7 +673,7 @@ __device__ __forceinline__ int WarpTestRegions(const BakeParams& P, const DevMip
         int s = 0;
         if (active) {
             const int local = task - oexcl, ly = local / ofw, lx = local - ly * ofw;
-            const HierItem hi = LoadHierItem(hierItems + ow);
+            const HierItem hi = LoadHierItem(hierItems + (size_t)ow * M + mip);
             s = TestRegionCell<Cfg>(P, m, hi, ob, ocx0 + lx, ocy0 + ly, on == 1);
         }
         const uint32_t bp = __ballot_sync(0xFFFFFFFFu, active && s > 0), bm = __ballot_sync(0xFFFFFFFFu, active && s < 0),
@@ -687,6 +690,26 @@ __device__ __forceinline__ int WarpTestRegions(const BakeParams& P, const DevMip
     if (decided) return verdict;
     if (n == 0 || anyFail != 0 || (anyPlus != 0 && anyMinus != 0)) return 0;
     return anyPlus != 0 ? 1 : -1;
+}
+
+// The same for every mip of the texture: a region passes when it passes on every mip with the same side (LeafClassifyMips).
+template <class Cfg>
+__device__ __forceinline__ int WarpTestRegionsAllMips(const BakeParams& P, const HierItem* __restrict__ hierItems, bool valid, uint32_t w, uint32_t idx,
+                                                      uint32_t regionLevelBelow) {
+    const int M = P.tex.mipCount;
+    int verdict = 0;
+    for (int k = 0; k < M; ++k) {
+        RegionBox rb{};
+        bool ok = valid && (k == 0 || verdict != 0);
+        if (ok) {
+            const HierItem hi = LoadHierItem(hierItems + (size_t)w * M + k);
+            ok = MakeRegionBox(P.tex.mips[k], hi, idx, hi.level - regionLevelBelow, rb);  // false: coordinates out of range, the region is split
+        }
+        const int s = WarpTestRegions<Cfg>(P, P.tex.mips[k], hierItems, k, ok, w, rb);
+        if (k == 0) verdict = s;
+        else if (s != verdict) verdict = 0;
+    }
+    return verdict;
 }
 
 // One warp per TASK = 64 consecutive initial regions of the chunk (for items of level 6 that is exactly one work item; a level-12
@@ -723,7 +746,7 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
             // piece = regions [a, b) of item w
             const uint32_t a = (uint32_t)((g0 > ws ? g0 : ws) - ws), b = (uint32_t)((g1 < we ? g1 : we) - ws);
             __syncwarp();
-            const HierItem hi = LoadHierItem(hierItems + w);
+            const HierItem hi = LoadHierItem(hierItems + (size_t)w * P.tex.mipCount);
             const uint32_t L = hi.level;
             const uint32_t e = L < 3 ? L : 3;
             uint32_t* words = stateWords + __ldg(&wordStart[w]);
@@ -743,8 +766,11 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
             RegionBox box;
             bool haveBox = false;
             const bool wholeItem = a == 0 && b == (uint32_t)(we - ws);
-            if (L >= 3 && wholeItem) haveBox = MakeItemBox(m, hi, box);
-            else if (L > 6 && (a & 63u) == 0 && b - a == 64) haveBox = MakeNodeBox(m, hi, a >> 6, L - 6, box);
+            // (the piece-level answers (F), (H), (I) look at mip 0 only: with several mips every region goes to HierTestUnresolved)
+            if (P.tex.mipCount == 1) {
+                if (L >= 3 && wholeItem) haveBox = MakeItemBox(m, hi, box);
+                else if (L > 6 && (a & 63u) == 0 && b - a == 64) haveBox = MakeNodeBox(m, hi, a >> 6, L - 6, box);
+            }
             if (haveBox) {
                 // (H) the whole piece over a constant area: one table query, whatever its size
                 int sFlat = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
@@ -796,9 +822,11 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
                 int s = 0;
                 if (valid) {
                     RegionBox rb;
-                    if (MakeRegionBox(m, hi, idx, L - e, rb)) {
-                        if (strongOk) s = StrongRectSide(P, m, hi, rb, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (I)
-                        if (s == 0) s = LookupCellMap(map, rb);
+                    if (map.fw != 0 || strongOk) {
+                        if (MakeRegionBox(m, hi, idx, L - e, rb)) {
+                            if (strongOk) s = StrongRectSide(P, m, hi, rb, rb.cx0, rb.cy0, rb.cx1, rb.cy1);  // (I)
+                            if (s == 0) s = LookupCellMap(map, rb);
+                        }
                     }
                     if (s != 0) HierFillGlobal(words, e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
                 }
@@ -825,17 +853,14 @@ __global__ void __launch_bounds__(128, 8) HierTestList(const BakeParams P, const
     const unsigned long long rounded = (total + 31ull) & ~31ull;
     const uint32_t e = 2u - (uint32_t)src;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
-        bool valid = t < total;
+        const bool valid = t < total;
         uint32_t w = 0, idx = 0;
-        RegionBox rb{};
         if (valid) {
             const unsigned long long entry = inList[t >> 2];
             w = (uint32_t)(entry >> 32);
             idx = (uint32_t)entry * 4u + (uint32_t)(t & 3ull);
-            const HierItem hi = LoadHierItem(hierItems + w);
-            valid = MakeRegionBox(P.tex.mips[0], hi, idx, hi.level - e, rb);  // false: coordinates out of range, the region is split
         }
-        const int s = WarpTestRegions<Cfg>(P, P.tex.mips[0], hierItems, valid, w, rb);
+        const int s = WarpTestRegionsAllMips<Cfg>(P, hierItems, valid, w, idx, e);
         if (s != 0) HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
         HierAppend(outList, outCount, t < total && s == 0, w, idx);
     }
@@ -848,18 +873,16 @@ __global__ void __launch_bounds__(128, 8) HierTestUnresolved(const BakeParams P,
     const unsigned long long total = lists.count[3];
     const unsigned long long rounded = (total + 31ull) & ~31ull;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < rounded; t += (unsigned long long)gridDim.x * blockDim.x) {
-        bool valid = t < total;
+        const bool valid = t < total;
         uint32_t w = 0, idx = 0, e = 3;
-        RegionBox rb{};
         if (valid) {
             const unsigned long long entry = lists.unresolved[t];
             w = (uint32_t)(entry >> 32);
             idx = (uint32_t)entry;
-            const HierItem hi = LoadHierItem(hierItems + w);
-            e = hi.level < 3 ? hi.level : 3;
-            valid = MakeRegionBox(P.tex.mips[0], hi, idx, hi.level - e, rb);
+            const uint32_t level = __ldg(&hierItems[(size_t)w * P.tex.mipCount].level);
+            e = level < 3 ? level : 3;
         }
-        const int s = WarpTestRegions<Cfg>(P, P.tex.mips[0], hierItems, valid, w, rb);
+        const int s = WarpTestRegionsAllMips<Cfg>(P, hierItems, valid, w, idx, e);
         if (s != 0) {
             HierFillGlobal(stateWords + __ldg(&wordStart[w]), e, idx, (uint32_t)(s > 0 ? P.stateGT : P.stateLE));
             atomicAdd(&uniformVotes[2 * (size_t)w + (s > 0 ? 0 : 1)], 1u);
@@ -892,13 +915,16 @@ __global__ void __launch_bounds__(128, 8) HierLeaves(const BakeParams P, const I
             w = (uint32_t)(entry >> 32);
             region = (uint32_t)entry;
             const uint32_t k = (uint32_t)(t & 3ull), index = region * 4u + k;
-            const HierItem hi = LoadHierItem(hierItems + w);
+            const int M = P.tex.mipCount;
+            const HierItem* its = hierItems + (size_t)w * M;
+            const HierItem hi = LoadHierItem(its);
             uint32_t st = 0;
             if (index < (1u << (2 * hi.level))) {  // a level-0 item has one micro-triangle in its only "4-region"
                 if (hi.ok) {
                     // The edge tests stay in place: queueing them for HierEdgeTests (and a single-micro-triangle TestRegion first)
                     // was measured slower -- both re-derive the vertices and the cell, and the tests diverge just as much there.
-                    st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
+                    if (M == 1) st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
+                    else st = (uint32_t)LeafClassifyMips<Cfg>(P, [&](int k) { return k == 0 ? hi : LoadHierItem(its + k); }, index);
                 }
             }
             bits = st << (2 * k);
@@ -942,7 +968,7 @@ __global__ void __launch_bounds__(128) HierEdgeTests(const BakeParams P, const H
     const uint32_t unknown = (uint32_t)StateFromCoverage(P, 1, 1);
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
         const uint4 e = queue.entries[t];
-        const HierItem hi = LoadHierItem(hierItems + e.x);
+        const HierItem hi = LoadHierItem(hierItems + (size_t)e.x * P.tex.mipCount);
         if (!LeafEdgeTests<Cfg>(P, P.tex.mips[0], hi, e.y, (int)e.z, (int)e.w)) continue;
         uint32_t* word = stateWords + __ldg(&wordStart[e.x]) + (e.y >> 4);
         const uint32_t shift = 2u * (e.y & 15u);
@@ -978,9 +1004,10 @@ static int ClassifierOverride() {
 }
 static bool SelectHierKernels(const BakeParams& P, HierKernels* out) {
     if (ClassifierOverride() != 0) return false;
-    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine && P.tex.mipCount == 1)) return false;
+    if (!(P.filterLinear && !P.disableLevelLine && !P.disableFine)) return false;
     if (P.useCoarse && !P.coarseSameCutoff) return false;  // SAT of another cutoff than the bake's: see LeafClassify
-    const bool pow2 = P.tex.mips[0].isPow2 != 0;
+    bool pow2 = true;
+    for (int i = 0; i < P.tex.mipCount; ++i) pow2 = pow2 && P.tex.mips[i].isPow2 != 0;
     if (P.tex.isFp32) {
         if (P.addrMode == ommTextureAddressMode_Wrap && pow2) *out = MakeHierKernels<KernelCfg<kAddrWrapPow2, true>>();
         else if (P.addrMode == ommTextureAddressMode_Clamp) *out = MakeHierKernels<KernelCfg<kAddrClamp, true>>();
@@ -2202,13 +2229,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
         if (itemEnd > itemBegin && useHier) {
-            GetCellTables(const_cast<TextureObject*>(tex), P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
+            if (P.tex.mipCount == 1) GetCellTables(const_cast<TextureObject*>(tex), P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
             // worst case of a chunk: the nominal number of initial regions plus the rest of its last item (at most 4^9 regions at level 12)
             const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
             const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, hierChunkRegions) + (1ull << 18), regionEnd - regionBegin);
             HierItem* hierItems = nullptr;
             HierLists lists{};
-            CUDA_TRY(scratch.alloc(&hierItems, W));
+            CUDA_TRY(scratch.alloc(&hierItems, (size_t)W * (size_t)P.tex.mipCount));
             CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
             CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
             CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));

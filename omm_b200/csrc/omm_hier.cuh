@@ -622,6 +622,34 @@ OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it
 struct NeverDefer {
     OMM_HD bool operator()(int, int) const { return false; }
 };
+// Several mips (ref: bake_cpu_impl.cpp:866-908): the reference classifies against mip 0, 1, ... and stops as soon as the state is an
+// Unknown one; votes accumulate over the mips.  `itemOfMip(k)` returns the HierItem of the work item for mip k (the constants of the
+// exact skips depend on the mip's size).  The region tests demand the same side on EVERY mip, which gives state(s) whether or not the
+// reference would have stopped early.
+template <class Cfg, class ItemOfMip>
+OMM_HD int LeafClassifyMips(const BakeParams& P, const ItemOfMip& itemOfMip, uint32_t index) {
+    const HierItem it0 = itemOfMip(0);
+    const Tri st = MicroTri(it0.p0, it0.p1, it0.p2, index, it0.level);
+    Coverage cov{0u, 0u};
+    const bool countsMatter = P.promotion == ommUnknownStatePromotion_Nearest;
+    for (int mip = 0; mip < P.tex.mipCount; ++mip) {
+        const DevMip& m = P.tex.mips[mip];
+        const HierItem it = mip == 0 ? it0 : itemOfMip(mip);
+        if (P.cutoff < TexBilinear<Cfg>(P, m, st.p0)) cov.above++;
+        else cov.below++;
+        const RasterSetup rs = MakeRasterSetup(st, m.w, m.h, -0.5f);
+        RasterCursor cur = RasterBegin(rs);
+        int x, y;
+        bool stop = false;
+        while (RasterNext(rs, cur, x, y)) {
+            LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter, NeverDefer());
+            if (!countsMatter && cov.above != 0 && cov.below != 0) { stop = true; break; }  // exact early-out, see ClassifyMicroTriangle
+        }
+        if (stop) break;
+        if (IsUnknownState(StateFromCoverage(P, cov.above, cov.below))) break;
+    }
+    return StateFromCoverage(P, cov.above, cov.below);
+}
 template <class Cfg>
 OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index) {
     return LeafClassify<Cfg>(P, m, it, index, NeverDefer());

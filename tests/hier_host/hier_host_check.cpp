@@ -23,13 +23,15 @@ struct HierCheckStats {
 };
 
 template <class Cfg>
-static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, uint32_t nodeInItem, uint32_t nl, uint32_t e, uint32_t idx, uint8_t* states,
+static void Descend(const BakeParams& P, const DevMip& m, const HierItem* his, uint32_t nodeInItem, uint32_t nl, uint32_t e, uint32_t idx, uint8_t* states,
                     HierCheckStats* st, const float2* uv, bool degenerate, const ItemCellMap* map = nullptr) {
+    const HierItem& hi = his[0];
+    const int M = P.tex.mipCount;
     const uint32_t L = hi.level;
     if (e == 0) {  // leaves: the reference walk with the exact skips of LeafCell (slow path for items the shortcuts do not cover)
         st->fullEvals++;
         const uint32_t index = (nodeInItem << (2 * nl)) + idx;
-        if (hi.ok) {
+        if (hi.ok && M == 1) {
             st->tests[3]++;
             const int s = TestRegion<Cfg>(P, m, hi, index, L);  // quick single-micro-triangle proof, as HierLeaves tries it first
             if (s != 0) {
@@ -46,9 +48,13 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, ui
                 queued.push_back({px, py});
                 return true;
             };
-            int state = LeafClassify<Cfg>(P, m, hi, index, defer);
-            for (auto& q : queued)
-                if (LeafEdgeTests<Cfg>(P, m, hi, index, q.first, q.second)) state = StateFromCoverage(P, 1, 1);
+            int state;
+            if (M == 1) {
+                state = LeafClassify<Cfg>(P, m, hi, index, defer);
+                for (auto& q : queued)
+                    if (LeafEdgeTests<Cfg>(P, m, hi, index, q.first, q.second)) state = StateFromCoverage(P, 1, 1);
+            } else
+                state = LeafClassifyMips<Cfg>(P, [&](int k) { return his[k]; }, index);
             states[idx] = (uint8_t)state;
         } else
             states[idx] = (uint8_t)ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L);
@@ -57,10 +63,17 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, ui
     int s = 0;
     st->tests[3 - e]++;
     if (hi.ok) {
-        RegionBox rb;
-        if (MakeRegionBox(m, hi, (nodeInItem << (2 * (nl - e))) + idx, L - e, rb)) {
-            if (map) s = LookupCellMap(*map, rb);  // initial regions only, like HierTestInitial
-            if (s == 0) s = TestRegionBox<Cfg>(P, m, hi, rb);
+        // every mip must pass with the same side (WarpTestRegionsAllMips)
+        for (int k = 0; k < M; ++k) {
+            RegionBox rb;
+            int sk = 0;
+            if (MakeRegionBox(P.tex.mips[k], his[k], (nodeInItem << (2 * (nl - e))) + idx, L - e, rb)) {
+                if (map && M == 1) sk = LookupCellMap(*map, rb);  // initial regions only, like HierTestInitial
+                if (sk == 0) sk = TestRegionBox<Cfg>(P, P.tex.mips[k], his[k], rb);
+            }
+            if (k == 0) s = sk;
+            else if (sk != s) s = 0;
+            if (s == 0) break;
         }
     }
     if (s != 0) {
@@ -69,7 +82,7 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem& hi, ui
         for (uint32_t i = 0; i < n; ++i) states[idx * n + i] = (uint8_t)(s > 0 ? P.stateGT : P.stateLE);
         return;
     }
-    for (uint32_t k = 0; k < 4; ++k) Descend<Cfg>(P, m, hi, nodeInItem, nl, e - 1, idx * 4 + k, states, st, uv, degenerate);
+    for (uint32_t k = 0; k < 4; ++k) Descend<Cfg>(P, m, his, nodeInItem, nl, e - 1, idx * 4 + k, states, st, uv, degenerate);
 }
 
 template <class Cfg>
@@ -80,7 +93,9 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
         const float2 uv[3] = {make_float2(uvs[6 * it], uvs[6 * it + 1]), make_float2(uvs[6 * it + 2], uvs[6 * it + 3]), make_float2(uvs[6 * it + 4], uvs[6 * it + 5])};
         const uint32_t L = levels[it];
         const bool degenerate = TriIsDegenerate(uv[0], uv[1], uv[2]);
-        const HierItem hi = MakeHierItem(m, uv[0], uv[1], uv[2], L, degenerate);
+        std::vector<HierItem> his;
+        for (int k = 0; k < P.tex.mipCount; ++k) his.push_back(MakeHierItem(P.tex.mips[k], uv[0], uv[1], uv[2], L, degenerate));
+        const HierItem hi = his[0];
         const uint32_t nl = L < 6 ? L : 6;
         const uint32_t nodes = L > 6 ? 1u << (2 * (L - 6)) : 1u;
         const uint32_t e0 = nl < 3 ? nl : 3;
@@ -89,7 +104,7 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
             uint32_t plus[32] = {0}, minus[32] = {0};
             ItemCellMap map{0, 0, 0, 0, plus, minus};
             RegionBox box;
-            const bool haveBox = hi.ok && L >= 3 && (L > 6 ? MakeNodeBox(m, hi, node, L - 6, box) : MakeItemBox(m, hi, box));
+            const bool haveBox = P.tex.mipCount == 1 && hi.ok && L >= 3 && (L > 6 ? MakeNodeBox(m, hi, node, L - 6, box) : MakeItemBox(m, hi, box));
             // piece-level answers of HierTestInitial: constant area (H), then the item-independent tables (I)
             if (haveBox) {
                 int sPiece = FlatRectSide<Cfg>(P, m, box.cx0, box.cy0, box.cx1, box.cy1);
@@ -122,7 +137,7 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
                     }
             }
             const uint32_t nInit = 1u << (2 * (nl - e0));
-            for (uint32_t r = 0; r < nInit; ++r) Descend<Cfg>(P, m, hi, node, nl, e0, r, states.data(), st, uv, degenerate, e0 == 3 ? &map : nullptr);
+            for (uint32_t r = 0; r < nInit; ++r) Descend<Cfg>(P, m, his.data(), node, nl, e0, r, states.data(), st, uv, degenerate, e0 == 3 ? &map : nullptr);
             const uint32_t n = 1u << (2 * nl);
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t index = (node << (2 * nl)) + i;
@@ -144,13 +159,51 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
 
 extern "C" __attribute__((visibility("default"))) int hier_host_check(const void* texels, int isFp32, int w, int h, int addrMode, float borderAlpha,
                                                                       float cutoff, int stateGT, int stateLE, int format, int promotion, const float* uvs,
-                                                                      const uint8_t* levels, uint32_t numItems, HierCheckStats* st, int useSat) {
+                                                                      const uint8_t* levels, uint32_t numItems, HierCheckStats* st, int useSat, int numMips) {
     memset(st, 0, sizeof(*st));
     BakeParams P{};
     P.tex.texels = texels;
     P.tex.sat = nullptr;
     P.tex.isFp32 = isFp32;
     P.tex.mipCount = 1;
+    // optional mip chain (2 x 2 box filter), texels of all mips back to back like the library stores them
+    std::vector<uint8_t> chain;
+    if (numMips > 1) {
+        const size_t spp = isFp32 ? 4 : 1;
+        std::vector<int> ws{w}, hs{h};
+        std::vector<size_t> offs{0};
+        size_t total = (size_t)w * h;
+        for (int k = 1; k < numMips; ++k) {
+            ws.push_back(std::max(1, ws.back() / 2)); hs.push_back(std::max(1, hs.back() / 2));
+            offs.push_back(total);
+            total += (size_t)ws.back() * hs.back();
+        }
+        chain.resize(total * spp);
+        memcpy(chain.data(), texels, (size_t)w * h * spp);
+        for (int k = 1; k < numMips; ++k)
+            for (int y = 0; y < hs[k]; ++y)
+                for (int x = 0; x < ws[k]; ++x) {
+                    auto src = [&](int xx, int yy) { return offs[k - 1] + (size_t)std::min(yy, hs[k - 1] - 1) * ws[k - 1] + std::min(xx, ws[k - 1] - 1); };
+                    const size_t dsti = offs[k] + (size_t)y * ws[k] + x;
+                    if (isFp32) {
+                        const float* f = (const float*)chain.data();
+                        ((float*)chain.data())[dsti] = 0.25f * (f[src(2 * x, 2 * y)] + f[src(2 * x + 1, 2 * y)] + f[src(2 * x, 2 * y + 1)] + f[src(2 * x + 1, 2 * y + 1)]);
+                    } else {
+                        const uint8_t* b8 = chain.data();
+                        chain[dsti] = (uint8_t)((b8[src(2 * x, 2 * y)] + b8[src(2 * x + 1, 2 * y)] + b8[src(2 * x, 2 * y + 1)] + b8[src(2 * x + 1, 2 * y + 1)]) / 4);
+                    }
+                }
+        P.tex.texels = chain.data();
+        P.tex.mipCount = numMips;
+        for (int k = 1; k < numMips; ++k) {
+            DevMip& mk = P.tex.mips[k];
+            mk.w = ws[k]; mk.h = hs[k];
+            mk.log2w = __builtin_ctz((unsigned)mk.w); mk.log2h = __builtin_ctz((unsigned)mk.h);
+            mk.isPow2 = (mk.w & (mk.w - 1)) == 0 && (mk.h & (mk.h - 1)) == 0;
+            mk.rcpw = 1.f / (float)mk.w; mk.rcph = 1.f / (float)mk.h;
+            mk.texelOffset = offs[k]; mk.satOffset = offs[k];
+        }
+    }
     DevMip& m = P.tex.mips[0];
     m.w = w; m.h = h;
     m.log2w = __builtin_ctz((unsigned)w); m.log2h = __builtin_ctz((unsigned)h);
@@ -181,7 +234,7 @@ extern "C" __attribute__((visibility("default"))) int hier_host_check(const void
     }
     // (H) constant-cell table of mip 0, as BuildFlatSat / FlatSatRows + SatCols compute it on the device
     std::vector<uint32_t> flat;
-    if (w >= 2 && h >= 2) {
+    if (w >= 2 && h >= 2 && numMips <= 1) {
         flat.resize((size_t)(w - 1) * (h - 1));
         for (int y = 0; y < h - 1; ++y)
             for (int x = 0; x < w - 1; ++x) {
@@ -197,7 +250,7 @@ extern "C" __attribute__((visibility("default"))) int hier_host_check(const void
     }
     // (I) item-independent whole-cell tables, as StrongSatRows + the column pass compute them
     std::vector<uint32_t> strongP, strongM;
-    if (w >= 2 && h >= 2) {
+    if (w >= 2 && h >= 2 && numMips <= 1) {
         strongP.resize((size_t)(w - 1) * (h - 1));
         strongM.resize((size_t)(w - 1) * (h - 1));
         for (int y = 0; y < h - 1; ++y)

@@ -33,14 +33,14 @@ def lib():
 
 
 def check(lib, tex, uvs, levels, addr=capi.ADDR_WRAP, cutoff=0.5, promotion=capi.PROMOTE_FORCE_OPAQUE, fmt=capi.FORMAT_4_STATE, gt=capi.STATE_O,
-          le=capi.STATE_T, border=0.0, use_sat=False):
+          le=capi.STATE_T, border=0.0, use_sat=False, mips=1):
     tex = np.ascontiguousarray(tex)
     uvs = np.ascontiguousarray(uvs, dtype=np.float32)
     levels = np.ascontiguousarray(levels, dtype=np.uint8)
     st = Stats()
     h, w = tex.shape
     lib.hier_host_check(tex.ctypes.data_as(ctypes.c_void_p), int(tex.dtype == np.float32), w, h, addr, ctypes.c_float(border), ctypes.c_float(cutoff), gt, le,
-                        fmt, promotion, uvs.ctypes.data_as(ctypes.c_void_p), levels.ctypes.data_as(ctypes.c_void_p), len(levels), ctypes.byref(st), int(use_sat))
+                        fmt, promotion, uvs.ctypes.data_as(ctypes.c_void_p), levels.ctypes.data_as(ctypes.c_void_p), len(levels), ctypes.byref(st), int(use_sat), int(mips))
     assert st.mismatches == 0, (f"{st.mismatches} of {st.microTriangles} micro-triangles differ from the reference walk; first: item {st.firstBadItem} "
                                 f"index {st.firstBadIndex} got {st.firstBadGot} want {st.firstBadWant}")
     return st
@@ -146,3 +146,13 @@ def test_sat_pass_with_the_bake_cutoff(lib):
     check(lib, t["checker"], tris(rng, 150, 9, 256, axis_aligned=True), np.full(150, 5), use_sat=True, addr=capi.ADDR_CLAMP)
     check(lib, t["noise8"], tris(rng, 150, 20, 512), rng.integers(0, 6, 150), use_sat=True, gt=capi.STATE_UO, le=capi.STATE_T)
     check(lib, t["smooth"], tris(rng, 150, 10, 256, -0.2, 1.2), np.full(150, 6), use_sat=True, promotion=capi.PROMOTE_NEAREST)
+
+
+def test_mip_chains(lib):
+    """Several mips: a region must pass on every mip with the same side; leaves walk the mips like the reference (stop at Unknown)."""
+    rng = np.random.default_rng(12)
+    t = textures(rng)
+    check(lib, t["noise"], tris(rng, 150, 8, 1024, -0.2, 1.2), np.full(150, 5), mips=4)
+    check(lib, t["smooth"], tris(rng, 150, 12, 256), np.full(150, 6), mips=3, promotion=capi.PROMOTE_NEAREST)
+    check(lib, t["noise8"], tris(rng, 150, 10, 512), rng.integers(0, 6, 150), mips=5, addr=capi.ADDR_MIRROR, le=capi.STATE_UO, gt=capi.STATE_T)
+    check(lib, t["npot"], tris(rng, 120, 9, 200, -0.5, 1.5), np.full(120, 5), mips=3, addr=capi.ADDR_CLAMP)
