@@ -355,7 +355,9 @@ static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* strea
     tm.h2dBytes = staged.h2dBytes;
     tm.hostStageMs = stageMs;
     const auto t0 = std::chrono::steady_clock::now();
-    ommResult rc = BakeOnDevice(b, staged, stream, r, &tm);
+    HostTrace::Mark("result object");
+    ommResult rc = BakeOnDevice(b, staged, stream, r, &tm, download);
+    HostTrace::Mark("BakeOnDevice returned");
     const auto t1 = std::chrono::steady_clock::now();
     if (rc == ommResult_SUCCESS && download) rc = DownloadResult(r, &tm.d2hMs, &tm.d2hBytes);
     const auto t2 = std::chrono::steady_clock::now();
@@ -377,15 +379,23 @@ static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* strea
 
 OMM_API ommResult ommCpuBake(ommBaker baker, const ommCpuBakeInputDesc* d, ommCpuBakeResult* outBakeResult) {  // ref: bake.cpp:103-116
     BakerObject* b = nullptr;
+    HostTrace::Mark("ommCpuBake entry");
     const ommResult v = CheckBakeArgs(baker, d, &b);
     if (v != ommResult_SUCCESS) return v;
+    HostTrace::Mark("args checked");
     StagedInputs staged;
     const auto t0 = std::chrono::steady_clock::now();
     ommResult rc = StageInputs(b, *d, &staged);
     if (rc != ommResult_SUCCESS) return rc;
     const float stageMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    rc = RunBake(b, staged, nullptr, true, stageMs, outBakeResult);
+    HostTrace::Mark("inputs staged");
+    // Sharded bakes leave the complete result in every rank's HBM; the host copy is made by ommCpuGetBakeResultDesc on the ranks
+    // that ask for it (N simultaneous downloads through one host were measured at a quarter of the single-download speed).
+    rc = RunBake(b, staged, nullptr, b->shard.world <= 1, stageMs, outBakeResult);
+    HostTrace::Mark("bake + download");
     DestroyStagedDevice(&staged);
+    HostTrace::Mark("staged inputs freed");
+    HostTrace::Dump();
     return rc;
 }
 
@@ -400,8 +410,19 @@ OMM_API ommResult ommCpuGetBakeResultDesc(ommCpuBakeResult bakeResult, const omm
     BakeResultObject* r = (BakeResultObject*)bakeResult;
     if (desc == nullptr) return r->log.InvalidArg("[Invalid Arg] - No BakeResultDesc provided");  // ref: bake_cpu_impl.h:113-120
     if (!r->downloaded) {
-        const ommResult rc = DownloadResult(r, nullptr, nullptr);
+        float d2hMs = 0.f;
+        uint64_t d2hBytes = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        const ommResult rc = DownloadResult(r, &d2hMs, &d2hBytes);
         if (rc != ommResult_SUCCESS) return rc;
+        const float hostMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (r->baker) {  // a deferred download belongs to the timings of the bake that produced it
+            std::lock_guard<std::mutex> g(r->baker->mu);
+            r->baker->last.d2hMs = d2hMs;
+            r->baker->last.d2hBytes = d2hBytes;
+            r->baker->last.hostDownloadMs = hostMs;
+            r->baker->last.hostTotalMs += hostMs;
+        }
     }
     *desc = &r->desc;
     return ommResult_SUCCESS;

@@ -1321,11 +1321,11 @@ __device__ __forceinline__ uint32_t CompressEvenBits16(uint32_t x) {  // 16 two-
 }
 __global__ void __launch_bounds__(256) WriteDescsAndPack(const uint32_t* __restrict__ sortedItems, const ItemRec* __restrict__ items,
                                                          const unsigned long long* __restrict__ wordStart, const uint32_t* __restrict__ stateWords,
-                                                         const unsigned long long* __restrict__ blockOffset, uint32_t numDescs,
+                                                         const unsigned long long* __restrict__ blockOffset, uint32_t firstDesc, uint32_t endDesc,
                                                          unsigned long long arrayBytes, ommCpuOpacityMicromapDesc* __restrict__ descArray,
                                                          uint8_t* __restrict__ arrayData) {
-    const uint32_t k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (k >= numDescs) return;
+    const uint32_t k = firstDesc + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per descriptor of [firstDesc, endDesc)
+    if (k >= endDesc) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t w = sortedItems[k];
     const ItemRec it = items[w];
@@ -1594,6 +1594,17 @@ void PinnedPoolRelease(void* p) {
         }
 }
 
+// Host memory of arrayData: the library's page-locked pool under the default allocator (full PCIe speed), the user's allocator otherwise.
+static bool AllocHostArrayData(BakeResultObject* res) {
+    if (res->hostArrayData) return true;
+    if (res->usesDefaultAllocator && res->arrayDataSize >= (1u << 20)) {
+        res->hostArrayData = PinnedPoolAcquire(res->arrayDataSize);
+        res->arrayDataFromPinnedPool = res->hostArrayData != nullptr;
+    }
+    if (!res->hostArrayData) res->hostArrayData = res->alloc.alloc(res->arrayDataSize, 64);
+    return res->hostArrayData != nullptr;
+}
+
 static ommResult RequireDevice(const Logger& log, int device) {
     if (DeviceCount() <= 0) {
         log.Log(ommMessageSeverity_Fatal, "[omm-b200] no CUDA device is visible; this library has no CPU fallback");
@@ -1708,25 +1719,21 @@ static bool GetCellTables(TextureObject* tex, BakeParams& P, cudaStream_t stream
 // ---------------------------------------------------------------------------------------------------------------------
 // staging of the per-bake inputs
 // ---------------------------------------------------------------------------------------------------------------------
-static uint32_t MaxIndex(ommIndexFormat fmt, const void* idx, size_t count) {
+// Largest vertex index the triangles use: it sizes the upload of the caller's UV buffer (nothing beyond the last referenced vertex may
+// be read).  Computed on the device from the index buffer that has just been uploaded (a host scan of 3 M indices is ~1 ms of every
+// ommCpuBake; this is one 12 MB pass at HBM speed plus a 4-byte read-back).
+__global__ void MaxIndexKernel(const void* __restrict__ indices, int indexFormat, unsigned long long count, uint32_t* __restrict__ result) {
     uint32_t m = 0;
-    if (fmt == ommIndexFormat_UINT_8) {
-        const uint8_t* p = (const uint8_t*)idx;
-        for (size_t i = 0; i < count; ++i) m = p[i] > m ? p[i] : m;
-    } else if (fmt == ommIndexFormat_UINT_16) {
-        const uint16_t* p = (const uint16_t*)idx;
-        for (size_t i = 0; i < count; ++i) m = p[i] > m ? p[i] : m;
-    } else {
-        // eight independent running maxima: the scalar loop is latency-bound (1 M triangles = 3 M indices = ~1 ms of every ommCpuBake)
-        const uint32_t* p = (const uint32_t*)idx;
-        uint32_t m8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        size_t i = 0;
-        for (; i + 8 <= count; i += 8)
-            for (int k = 0; k < 8; ++k) m8[k] = p[i + k] > m8[k] ? p[i + k] : m8[k];
-        for (; i < count; ++i) m = p[i] > m ? p[i] : m;
-        for (int k = 0; k < 8; ++k) m = m8[k] > m ? m8[k] : m;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        uint32_t v;
+        if (indexFormat == ommIndexFormat_UINT_8) v = ((const uint8_t*)indices)[i];
+        else if (indexFormat == ommIndexFormat_UINT_16) v = ((const uint16_t*)indices)[i];
+        else v = ((const uint32_t*)indices)[i];
+        m = v > m ? v : m;
     }
-    return m;
+    m = __reduce_max_sync(0xFFFFFFFFu, m);
+    if ((threadIdx.x & 31u) == 0 && m != 0) atomicMax(result, m);
 }
 static uint32_t TexCoordSize(ommTexCoordFormat f) { return f == ommTexCoordFormat_UV32_FLOAT ? 8u : 4u; }  // ref: util/texture.h:148-160
 static uint32_t IndexSize(ommIndexFormat f) { return f == ommIndexFormat_UINT_8 ? 1u : (f == ommIndexFormat_UINT_16 ? 2u : 4u); }
@@ -1744,14 +1751,24 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
     {
         const size_t usedIndices = (size_t)out->triangleCount * 3;
         const size_t indexBytes = usedIndices * IndexSize(desc.indexFormat);
-        const uint32_t maxIndex = usedIndices ? MaxIndex(desc.indexFormat, desc.indexBuffer, usedIndices) : 0;
-        out->texCoordBytes = (size_t)maxIndex * out->texCoordStride + TexCoordSize(desc.texCoordFormat);
+        uint32_t maxIndex = 0;
         CUDA_TRY(cudaEventCreate(&e0));
         CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, 0));
-        CUDA_TRY(cudaMallocAsync(&out->devIndices, indexBytes ? indexBytes : 4, 0));
-        CUDA_TRY(cudaMallocAsync(&out->devTexCoords, out->texCoordBytes + 8, 0));
+        CUDA_TRY(cudaMallocAsync(&out->devIndices, (indexBytes ? indexBytes : 4) + 8, 0));  // + the (aligned) max-index word
         CUDA_TRY(cudaMemcpyAsync(out->devIndices, desc.indexBuffer, indexBytes, cudaMemcpyHostToDevice, 0));
+        if (usedIndices) {
+            uint32_t* devMax = (uint32_t*)((uint8_t*)out->devIndices + ((indexBytes + 3) & ~(size_t)3));
+            CUDA_TRY(cudaMemsetAsync(devMax, 0, 4, 0));
+            int sms = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
+            MaxIndexKernel<<<(uint32_t)std::max(sms, 1) * 4u, 256, 0, 0>>>(out->devIndices, (int)desc.indexFormat, (unsigned long long)usedIndices, devMax);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(&maxIndex, devMax, 4, cudaMemcpyDeviceToHost, 0));
+            CUDA_TRY(cudaStreamSynchronize(0));
+        }
+        out->texCoordBytes = (size_t)maxIndex * out->texCoordStride + TexCoordSize(desc.texCoordFormat);
+        CUDA_TRY(cudaMallocAsync(&out->devTexCoords, out->texCoordBytes + 8, 0));
         CUDA_TRY(cudaMemcpyAsync(out->devTexCoords, desc.texCoords, out->texCoordBytes, cudaMemcpyHostToDevice, 0));
         out->h2dBytes = indexBytes + out->texCoordBytes;
         if (desc.subdivisionLevels) {
@@ -1982,7 +1999,7 @@ static const char* SpecialIndexText(int s) {  // ref: log.h:20-31
     }
 }
 
-ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* tm) {
+ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* tm, bool earlyDownload) {
     const Logger& log = baker->log;
     ommResult rc = RequireDevice(log, baker->device);
     if (rc != ommResult_SUCCESS) return rc;
@@ -2000,6 +2017,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     cudaStream_t stream = (cudaStream_t)userStream;
     bool ownStream = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copyStream = nullptr;  // early download of the packed array (see K8)
+    cudaEvent_t copyEv[2] = {nullptr, nullptr}, sliceEv = nullptr;
     Scratch scratch{};
     void* cubTemp = nullptr;
     size_t cubTempBytes = 0;
@@ -2056,6 +2075,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     scratch.stream = stream;
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
     CUDA_TRY(cudaEventRecord(ev[0], stream));
+    HostTrace::Mark("stream + events created");
 
     // ---- parameters ----
     P.tex = tex->dev;
@@ -2220,6 +2240,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
     }
     CUDA_TRY(cudaEventRecord(ev[1], stream));
+    HostTrace::Mark("setup done (host sync 1)");
 
     // ---- K4: classification of this rank's shard of work items ----
     if (W > 0) {
@@ -2352,6 +2373,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
     }
     CUDA_TRY(cudaEventRecord(ev[2], stream));
+    HostTrace::Mark("classify + post launched");
 
     // ---- K5..K7: post ----
     if (W > 0) {
@@ -2448,6 +2470,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
         CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+    HostTrace::Mark("    histograms read (host sync 2)");
     }
 
     // ---- sizes (ref: bake_cpu_impl.cpp:1763-1777) ----
@@ -2495,10 +2518,44 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             size_t tmp = cubTempBytes;
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, blockOffset, (int)numDescs, stream));
             // after a sharded bake the blocks of serializable items live in the compact exchange buffer
-            WriteDescsAndPack<<<(numDescs + 7) / 8, 256, 0, stream>>>(sortValsOut, items, compactWords ? compactStart : wordStart,
-                                                                      compactWords ? compactWords : stateWords, blockOffset, numDescs, arrayBytes,
-                                                                      (ommCpuOpacityMicromapDesc*)res->devDescArray, (uint8_t*)res->devArrayData);
-            launches += 4;
+            // The caller wants the result in host memory (ommCpuBake): pack the array in slices of descriptors and send each slice
+            // over PCIe while the next one is packed; the 8-byte slice boundaries are read back first.  Page-locked destination only
+            // (a pageable one makes the copies synchronous).
+            constexpr uint32_t kPackSlices = 8;
+            unsigned long long sliceOffset[kPackSlices + 1];
+            uint32_t sliceDesc[kPackSlices + 1];
+            uint32_t slices = 1;
+            sliceDesc[0] = 0; sliceOffset[0] = 0;
+            if (earlyDownload && arrayBytes >= ((size_t)8 << 20) && numDescs >= 64 * kPackSlices && AllocHostArrayData(res) && res->arrayDataFromPinnedPool) {
+                slices = kPackSlices;
+                for (uint32_t i = 1; i < slices; ++i) {
+                    sliceDesc[i] = (uint32_t)((unsigned long long)numDescs * i / slices);
+                    CUDA_TRY(cudaMemcpyAsync(&sliceOffset[i], blockOffset + sliceDesc[i], 8, cudaMemcpyDeviceToHost, stream));
+                }
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreate(&copyEv[0]));
+                CUDA_TRY(cudaEventCreate(&copyEv[1]));
+                CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+            }
+            sliceDesc[slices] = numDescs; sliceOffset[slices] = arrayBytes;
+            for (uint32_t i = 0; i < slices; ++i) {
+                const uint32_t k0 = sliceDesc[i], k1 = sliceDesc[i + 1];
+                if (k1 <= k0) continue;
+                WriteDescsAndPack<<<(k1 - k0 + 7) / 8, 256, 0, stream>>>(sortValsOut, items, compactWords ? compactStart : wordStart,
+                                                                         compactWords ? compactWords : stateWords, blockOffset, k0, k1, arrayBytes,
+                                                                         (ommCpuOpacityMicromapDesc*)res->devDescArray, (uint8_t*)res->devArrayData);
+                launches++;
+                if (copyStream) {
+                    CUDA_TRY(cudaEventRecord(sliceEv, stream));
+                    CUDA_TRY(cudaStreamWaitEvent(copyStream, sliceEv, 0));
+                    if (i == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
+                    CUDA_TRY(cudaMemcpyAsync((uint8_t*)res->hostArrayData + sliceOffset[i], (const uint8_t*)res->devArrayData + sliceOffset[i],
+                                             (size_t)(sliceOffset[i + 1] - sliceOffset[i]), cudaMemcpyDeviceToHost, copyStream));
+                }
+            }
+            if (copyStream) CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
+            launches += 3;
         }
         if (T > 0) {
             // no work item at all (every triangle invalid): the per-triangle item table was never written -> all unresolved
@@ -2510,6 +2567,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(ev[3], stream));
+    HostTrace::Mark("pack launched");
 
     // histograms (ref: bake_cpu_impl.cpp:1826-1852): non-zero entries, 2-state before 4-state, level ascending
     {
@@ -2526,6 +2584,15 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     scratch.freeAll();
     CUDA_TRY(cudaStreamSynchronize(stream));
+    HostTrace::Mark("final sync");
+    if (copyStream) {
+        CUDA_TRY(cudaStreamSynchronize(copyStream));
+        HostTrace::Mark("array data on the host");
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, copyEv[0], copyEv[1]);
+        res->arrayDataDownloaded = true;
+        res->earlyD2hMs = ms;
+    }
     {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev[0], ev[1]); tm->setupMs = ms;
@@ -2555,6 +2622,12 @@ cleanup:
         cudaStreamSynchronize(stream);
         cudaStreamDestroy(stream);
     }
+    if (copyStream) {
+        cudaStreamSynchronize(copyStream);
+        cudaStreamDestroy(copyStream);
+    }
+    for (cudaEvent_t e : {copyEv[0], copyEv[1], sliceEv})
+        if (e) cudaEventDestroy(e);
     if (rc != ommResult_SUCCESS) {
         cudaGetLastError();
         DestroyResultDevice(res);
@@ -2573,14 +2646,11 @@ ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, 0));
     if (res->descCount) {
-        if (res->usesDefaultAllocator && res->arrayDataSize >= (1u << 20)) {
-            res->hostArrayData = PinnedPoolAcquire(res->arrayDataSize);
-            res->arrayDataFromPinnedPool = res->hostArrayData != nullptr;
-        }
-        if (!res->hostArrayData) res->hostArrayData = res->alloc.alloc(res->arrayDataSize, 64);
         res->hostDescArray = res->alloc.alloc((size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), 64);
-        if (!res->hostArrayData || !res->hostDescArray) { rc = ommResult_FAILURE; goto cleanup; }
-        CUDA_TRY(cudaMemcpyAsync(res->hostArrayData, res->devArrayData, res->arrayDataSize, cudaMemcpyDeviceToHost, 0));
+        if (!AllocHostArrayData(res) || !res->hostDescArray) { rc = ommResult_FAILURE; goto cleanup; }
+        HostTrace::Mark("host result allocated");
+        if (!res->arrayDataDownloaded)  // else: sent slice by slice while it was packed (BakeOnDevice, K8)
+            CUDA_TRY(cudaMemcpyAsync(res->hostArrayData, res->devArrayData, res->arrayDataSize, cudaMemcpyDeviceToHost, 0));
         CUDA_TRY(cudaMemcpyAsync(res->hostDescArray, res->devDescArray, (size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), cudaMemcpyDeviceToHost, 0));
     }
     res->hostIndexBuffer = res->alloc.alloc((size_t)res->indexCount * 4, 64);
@@ -2588,7 +2658,11 @@ ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes
     CUDA_TRY(cudaMemcpyAsync(res->hostIndexBuffer, res->devIndexBuffer, idxBytes, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaEventRecord(e1, 0));
     CUDA_TRY(cudaEventSynchronize(e1));
-    if (d2hMs) CUDA_TRY(cudaEventElapsedTime(d2hMs, e0, e1));
+    HostTrace::Mark("D2H done");
+    if (d2hMs) {
+        CUDA_TRY(cudaEventElapsedTime(d2hMs, e0, e1));
+        *d2hMs += res->earlyD2hMs;  // the overlapped part, as timed on the copy stream
+    }
     if (d2hBytes) *d2hBytes = (uint64_t)res->arrayDataSize + (uint64_t)res->descCount * 8 + idxBytes;
     res->desc.arrayData = res->hostArrayData;
     res->desc.arrayDataSize = res->descCount ? res->arrayDataSize : 0;

@@ -8,6 +8,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <ctime>
+#include <utility>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -58,6 +61,20 @@ struct Logger {
     ommResult InvalidArg(const char* msg) const {
         Log(ommMessageSeverity_Fatal, msg);
         return ommResult_INVALID_ARGUMENT;
+    }
+};
+
+// ---- host trace (OMM_B200_TRACE=1): wall-clock marks of one ommCpuBake call, printed to stderr when the call returns ----
+struct HostTrace {
+    static bool Enabled() { static const bool on = getenv("OMM_B200_TRACE") != nullptr; return on; }
+    static std::vector<std::pair<const char*, double>>& Marks() { thread_local std::vector<std::pair<const char*, double>> m; return m; }
+    static double Now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    static void Mark(const char* label) { if (Enabled()) Marks().push_back({label, Now()}); }
+    static void Dump() {
+        if (!Enabled()) return;
+        auto& m = Marks();
+        for (size_t i = 1; i < m.size(); ++i) fprintf(stderr, "[omm-b200 trace] %-28s +%8.3f ms  (at %8.3f)\n", m[i].first, m[i].second - m[i - 1].second, m[i].second - m[0].second);
+        m.clear();
     }
 };
 
@@ -134,6 +151,8 @@ struct BakeResultObject {
     uint32_t arrayDataSize = 0, descCount = 0, indexCount = 0;
     ommIndexFormat indexFormat = ommIndexFormat_UINT_32;
     bool downloaded = false;
+    bool arrayDataDownloaded = false;  // hostArrayData was filled slice by slice while the array was packed (ommCpuBake on one GPU)
+    float earlyD2hMs = 0.f;
     bool arrayDataFromPinnedPool = false;  // hostArrayData came from the library's page-locked pool (default allocator only)
     bool usesDefaultAllocator = false;
     struct BakerObject* baker = nullptr;
@@ -200,7 +219,7 @@ void DestroyTextureDevice(TextureObject* tex);
 ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, StagedInputs* out);
 void DestroyStagedDevice(StagedInputs* s);
 // Runs the whole device pipeline.  On success fills res (device buffers; host histograms) and timings.
-ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* t);
+ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* t, bool earlyDownload);
 ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes);
 void DestroyResultDevice(BakeResultObject* res);
 int DeviceCount();
