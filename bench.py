@@ -320,7 +320,7 @@ def run_b200(a):
     cls_ms = sum(classify_ms) / len(classify_ms)
     achieved = classify_bytes / (cls_ms * 1e-3) / 1e9
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1c_stage_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1d_stage_traffic.json")
     if world == 1 and a.tris == 1_000_000 and a.level == 6 and a.tex == 4096 and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)

@@ -5,6 +5,7 @@
 // Reference behaviour restated here: libraries/omm-lib/src/bake.cpp:36-135, 410-479 (entry points),
 // bake_cpu_impl.cpp:97-119, 235-290 (validation + messages), texture_impl.cpp:43-224 (texture validation and copy),
 // std_allocator.h:45-117 (default allocator), omm_handle.h:17-53 (handle tags), debug_impl.cpp:512-641 (stats).
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <map>
@@ -137,6 +138,22 @@ OMM_API ommLibraryDesc ommGetLibraryDesc(void) {
     return d;
 }
 
+// Results outlive nothing in the SDK's contract except their own handle, so a result may be asked for its host copy after its baker
+// is gone; the timings of a deferred download are then simply not recorded (live bakers are looked up here, never dereferenced blindly).
+static std::mutex g_liveBakersMu;
+static std::vector<BakerObject*> g_liveBakers;
+static void RecordDeferredDownload(BakerObject* baker, float d2hMs, uint64_t d2hBytes, float hostMs) {
+    std::lock_guard<std::mutex> live(g_liveBakersMu);
+    if (std::find(g_liveBakers.begin(), g_liveBakers.end(), baker) == g_liveBakers.end()) return;
+    std::lock_guard<std::mutex> g(baker->mu);
+    baker->last.d2hMs = d2hMs;
+    baker->last.d2hBytes = d2hBytes;
+    if (hostMs > 0.f) {
+        baker->last.hostDownloadMs = hostMs;
+        baker->last.hostTotalMs += hostMs;
+    }
+}
+
 OMM_API ommResult ommCreateBaker(const ommBakerCreationDesc* desc, ommBaker* outBaker) {  // ref: bake.cpp:410-455
     if (desc == nullptr) return ommResult_INVALID_ARGUMENT;
     if (desc->type == ommBakerType_GPU) return ommResult_NOT_IMPLEMENTED;  // the SDK's D3D12/VK command-list baker is out of scope
@@ -151,6 +168,10 @@ OMM_API ommResult ommCreateBaker(const ommBakerCreationDesc* desc, ommBaker* out
     b->usesDefaultAllocator = defaultAllocator;
     b->log.sink = desc->messageInterface;
     b->device = g_requestedDevice >= 0 ? g_requestedDevice : CurrentDeviceOr(0);
+    {
+        std::lock_guard<std::mutex> live(g_liveBakersMu);
+        g_liveBakers.push_back(b);
+    }
     *outBaker = MakeHandle<ommBaker>(b, HandleTag::CpuBaker);
     return ommResult_SUCCESS;
 }
@@ -159,6 +180,10 @@ OMM_API ommResult ommDestroyBaker(ommBaker baker) {  // ref: bake.cpp:457-479
     if (baker == 0) return ommResult_INVALID_ARGUMENT;
     if (HandleTagOf(baker) != HandleTag::CpuBaker) return ommResult_FAILURE;
     BakerObject* b = HandlePtr<BakerObject>(baker);
+    {
+        std::lock_guard<std::mutex> live(g_liveBakersMu);
+        g_liveBakers.erase(std::remove(g_liveBakers.begin(), g_liveBakers.end(), b), g_liveBakers.end());
+    }
     DestroySharding(b);
     const HostAllocator alloc = b->alloc;
     FreeObject(alloc, b);
@@ -416,13 +441,7 @@ OMM_API ommResult ommCpuGetBakeResultDesc(ommCpuBakeResult bakeResult, const omm
         const ommResult rc = DownloadResult(r, &d2hMs, &d2hBytes);
         if (rc != ommResult_SUCCESS) return rc;
         const float hostMs = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        if (r->baker) {  // a deferred download belongs to the timings of the bake that produced it
-            std::lock_guard<std::mutex> g(r->baker->mu);
-            r->baker->last.d2hMs = d2hMs;
-            r->baker->last.d2hBytes = d2hBytes;
-            r->baker->last.hostDownloadMs = hostMs;
-            r->baker->last.hostTotalMs += hostMs;
-        }
+        if (r->baker) RecordDeferredDownload(r->baker, d2hMs, d2hBytes, hostMs);  // it belongs to the timings of the bake that produced it
     }
     *desc = &r->desc;
     return ommResult_SUCCESS;
@@ -533,11 +552,7 @@ OMM_API ommResult ommB200DownloadResult(ommCpuBakeResult bakeResult) {
     uint64_t bytes = 0;
     const bool was = r->downloaded;
     const ommResult rc = DownloadResult(r, &ms, &bytes);
-    if (rc == ommResult_SUCCESS && !was && r->baker) {
-        std::lock_guard<std::mutex> g(r->baker->mu);
-        r->baker->last.d2hMs = ms;
-        r->baker->last.d2hBytes = bytes;
-    }
+    if (rc == ommResult_SUCCESS && !was && r->baker) RecordDeferredDownload(r->baker, ms, bytes, 0.f);
     return rc;
 }
 OMM_API ommResult ommB200InitSharding(ommBaker baker, int rank, int worldSize, const void* ncclUniqueIdBytes, size_t idSize) {

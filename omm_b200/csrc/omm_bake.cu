@@ -561,6 +561,13 @@ static unsigned long long HierNominalChunkRegions(int device) {
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
     size_t freeB = 0, totalB = 0;
     unsigned long long regions = kHierChunkRegionsMin;
+    if (const char* e = getenv("OMM_B200_CHUNK_REGIONS")) {  // A/B runs: initial regions per chunk
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= (1ull << 16)) {
+            if (device >= 0 && device < 64) cached[device] = v;
+            return v;
+        }
+    }
     if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
         const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (21ull * 8ull);
         regions = std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));

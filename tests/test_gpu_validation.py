@@ -133,6 +133,33 @@ def test_resident_bake_and_device_result(product_lib):
     assert got.diff(want) == []
 
 
+def test_sliced_download_equals_plain_download(product_lib):
+    """ommCpuBake sends arrayData over PCIe slice by slice while it is packed (results >= 8 MiB into the page-locked pool); the bytes
+    must equal those of the resident bake followed by ommB200DownloadResult, which packs in one launch and copies afterwards.  With
+    a user allocator (pageable destination) the sliced path is not taken: same bytes again."""
+    from omm_b200.baker import _copy_result
+    wl = W.config3(num_tris=60000)
+    with Baker(product_lib) as b:
+        inp, tex = W.make_input(b, wl)
+        sliced = b.bake(inp)
+        assert sliced.array_data.size >= 8 << 20 and sliced.desc_array.size >= 512, "workload too small to take the sliced path"
+        d = inp.to_desc()
+        staged = C.c_void_p()
+        assert product_lib.dll.ommB200StageInputs(b.handle, C.byref(d), C.byref(staged)) == capi.SUCCESS
+        h = C.c_void_p()
+        assert product_lib.dll.ommB200BakeResident(b.handle, staged, None, C.byref(h)) == capi.SUCCESS
+        assert product_lib.dll.ommB200DownloadResult(h) == capi.SUCCESS
+        p = C.POINTER(capi.CpuBakeResultDesc)()
+        assert product_lib.dll.ommCpuGetBakeResultDesc(h, C.byref(p)) == capi.SUCCESS
+        plain = _copy_result(p.contents)
+        product_lib.dll.ommCpuDestroyBakeResult(h)
+        product_lib.dll.ommB200DestroyStagedInputs(staged)
+        again = b.bake(inp)  # the pool block of the first result is reused
+        tex.destroy()
+    assert sliced.diff(plain) == []
+    assert again.diff(plain) == []
+
+
 def test_user_allocator_is_honoured(product_lib):
     """All host memory visible through the ABI comes from ommMemoryAllocatorInterface (ref: omm.h:214-232, bake.cpp:123-124)."""
     live, total = {}, [0]
