@@ -725,6 +725,13 @@ __device__ __forceinline__ int WarpTestRegionsAllMips(const BakeParams& P, const
 // whose cells are all on one side is finished at once (the common case: most triangles do not meet the level line at all).
 constexpr int kHierInitWarps = 4;
 constexpr uint32_t kHierTaskRegions = 64;
+// resident blocks per SM the list / leaf kernels are compiled for (register budget 64 at 8; A/B builds override)
+#ifndef OMM_LIST_MIN_BLOCKS
+#define OMM_LIST_MIN_BLOCKS 8
+#endif
+#ifndef OMM_LEAF_MIN_BLOCKS
+#define OMM_LEAF_MIN_BLOCKS 8
+#endif
 template <class Cfg>
 __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const BakeParams P, const HierItem* __restrict__ hierItems,
                                                                        const unsigned long long* __restrict__ regionStart,
@@ -852,7 +859,7 @@ __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const 
 
 // children of the regions in lists.q[src] (size exponent 3 - src); the children have size exponent 2 - src
 template <class Cfg>
-__global__ void __launch_bounds__(128, 8) HierTestList(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+__global__ void __launch_bounds__(128, OMM_LIST_MIN_BLOCKS) HierTestList(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
                                                      const unsigned long long* __restrict__ inList, const unsigned long long* __restrict__ inCount,
                                                      unsigned long long* __restrict__ outList, unsigned long long* __restrict__ outCount, int src,
                                                      uint32_t* __restrict__ stateWords) {
@@ -875,7 +882,7 @@ __global__ void __launch_bounds__(128, 8) HierTestList(const BakeParams P, const
 
 // Initial regions the whole-cell bitmap left open: the full region test, one region per thread.
 template <class Cfg>
-__global__ void __launch_bounds__(128, 8) HierTestUnresolved(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
+__global__ void __launch_bounds__(128, OMM_LIST_MIN_BLOCKS) HierTestUnresolved(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
                                                            HierLists lists, uint32_t* __restrict__ uniformVotes, uint32_t* __restrict__ stateWords) {
     const unsigned long long total = lists.count[3];
     const unsigned long long rounded = (total + 31ull) & ~31ull;
@@ -910,7 +917,7 @@ struct HierEdgeQueue {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(128, 8) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
+__global__ void __launch_bounds__(128, OMM_LEAF_MIN_BLOCKS) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
                                                    const unsigned long long* __restrict__ wordStart, HierLists lists, HierEdgeQueue queue,
                                                    uint32_t* __restrict__ stateWords) {
     const unsigned long long total = lists.count[2] * 4ull;

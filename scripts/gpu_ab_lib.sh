@@ -1,8 +1,7 @@
 #!/bin/bash
-# same-box A/B of two builds of the library: omm_b200/lib/libomm-b200.so (current) against omm_b200/lib/$VARIANT
+# same-box A/B of builds of the library: omm_b200/lib/libomm-b200.so (current) against omm_b200/lib/variant_<name>.so for each name in $VARIANTS
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/pytest_gpu_all.txt
 run() {
   timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /tmp/b.json 2>/tmp/b.err || { echo FAILED; tail -3 /tmp/b.err; return; }
   python - "$1" <<'PY'
@@ -14,5 +13,6 @@ PY
 cp omm_b200/lib/libomm-b200.so /tmp/current.so
 for rep in 1 2; do
   cp /tmp/current.so omm_b200/lib/libomm-b200.so; run current
-  cp omm_b200/lib/$VARIANT omm_b200/lib/libomm-b200.so; run "$VARIANT"
+  for v in $VARIANTS; do cp omm_b200/lib/variant_$v.so omm_b200/lib/libomm-b200.so; run "$v"; done
 done
+cp /tmp/current.so omm_b200/lib/libomm-b200.so
