@@ -531,7 +531,11 @@ OMM_API ommResult ommB200BakeResident(ommBaker baker, ommB200StagedInputs staged
     BakerObject* b = HandlePtr<BakerObject>(baker);
     StagedInputs* s = (StagedInputs*)staged;
     if (s->baker != b) return b->log.InvalidArg("[omm-b200] staged inputs belong to a different baker");
-    return RunBake(b, *s, cudaStream, false, 0.f, outBakeResult);
+    HostTrace::Mark("ommB200BakeResident entry");
+    const ommResult rc = RunBake(b, *s, cudaStream, false, 0.f, outBakeResult);
+    HostTrace::Mark("bake");
+    HostTrace::Dump();
+    return rc;
 }
 OMM_API ommResult ommB200GetDeviceResultDesc(ommCpuBakeResult bakeResult, ommB200DeviceResultDesc* out) {
     if (bakeResult == 0 || out == nullptr) return ommResult_INVALID_ARGUMENT;

@@ -2033,6 +2033,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copyStream = nullptr;  // early download of the packed array (see K8)
     cudaEvent_t copyEv[2] = {nullptr, nullptr}, sliceEv = nullptr;
+    cudaEvent_t gatherEv[3] = {nullptr, nullptr, nullptr};  // OMM_B200_TRACE: phases of the sharded exchange
     Scratch scratch{};
     void* cubTemp = nullptr;
     size_t cubTempBytes = 0;
@@ -2352,6 +2353,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 }
             }
             ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
+            if (HostTrace::Enabled()) {
+                for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&gatherEv[i]));
+                CUDA_TRY(cudaEventRecord(gatherEv[0], stream));
+            }
             if (ncclOk && !fullBlocks) {
                 // Only blocks of items WITHOUT a special index can reach the output array: every rank packs those of its own items
                 // into a compact buffer laid out by a prefix sum all ranks compute alike, and the all-gather moves just these
@@ -2370,14 +2375,17 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 if (itemEnd > itemBegin)
                     CompactCopy<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(special, itemWords, wordStart, compactStart, stateWords, itemBegin, itemEnd, compactWords);
                 launches += 6;
+                if (gatherEv[1]) CUDA_TRY(cudaEventRecord(gatherEv[1], stream));
                 CUDA_TRY(cudaMemcpyAsync(compactBounds, compactBoundsDev, sizeof(unsigned long long) * (world + 1), cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
+                HostTrace::Mark("    exchange: compact bounds read (host sync)");
                 ncclOk = nccl.GroupStart() == ncclSuccess;
                 for (int r = 0; r < world && ncclOk; ++r) {
                     const size_t count = (size_t)(compactBounds[r + 1] - compactBounds[r]);
                     if (count) ncclOk = nccl.Broadcast(compactWords + compactBounds[r], compactWords + compactBounds[r], count, ncclUint32, r, comm, stream) == ncclSuccess;
                 }
                 ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
+                if (gatherEv[2]) CUDA_TRY(cudaEventRecord(gatherEv[2], stream));
             }
             if (!ncclOk) {
                 log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL all-gather of the state blocks failed");
@@ -2599,6 +2607,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     scratch.freeAll();
     CUDA_TRY(cudaStreamSynchronize(stream));
     HostTrace::Mark("final sync");
+    if (gatherEv[2]) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        cudaEventElapsedTime(&a, ev[5], gatherEv[0]);
+        cudaEventElapsedTime(&b, gatherEv[0], gatherEv[1]);
+        cudaEventElapsedTime(&c, gatherEv[1], gatherEv[2]);
+        fprintf(stderr, "[omm-b200 trace] rank %d exchange: digests + special indices %.3f ms, compaction %.3f ms, bounds read-back + blocks %.3f ms\n", rank, a, b, c);
+    }
     if (copyStream) {
         CUDA_TRY(cudaStreamSynchronize(copyStream));
         HostTrace::Mark("array data on the host");
@@ -2640,7 +2655,7 @@ cleanup:
         cudaStreamSynchronize(copyStream);
         cudaStreamDestroy(copyStream);
     }
-    for (cudaEvent_t e : {copyEv[0], copyEv[1], sliceEv})
+    for (cudaEvent_t e : {copyEv[0], copyEv[1], sliceEv, gatherEv[0], gatherEv[1], gatherEv[2]})
         if (e) cudaEventDestroy(e);
     if (rc != ommResult_SUCCESS) {
         cudaGetLastError();
