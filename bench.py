@@ -78,7 +78,7 @@ class ClockSampler:
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.gpu, self.proc, self.lines, self.skip = gpu_index, None, [], 0
 
     def start(self):
         try:
@@ -92,13 +92,24 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, timeout_s: float = 2.0):
+        """Block until nvidia-smi delivers its first line: its start-up (NVML enumerates every GPU of the box) was seen to stall CUDA calls
+        of all ranks for ~20 ms, so it is started during the last warm-up step and only loops (-lms) through the timed region."""
+        t0 = time.time()
+        while self.proc and not self.lines and time.time() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Samples delivered before this call (warm-up) are not reported."""
+        self.skip = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.skip:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -256,8 +267,11 @@ def run_b200(a):
     for it in range(a.warmup + a.steps):
         flush.fill_(it & 0xFF)  # evict L2 between steps (outside the timed events)
         barrier()
-        if it == a.warmup:
+        if rank == 0 and it == max(a.warmup - 1, 0):
             sampler.start()
+            sampler.wait_first()
+        if it == a.warmup:
+            sampler.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         h = C.c_void_p()

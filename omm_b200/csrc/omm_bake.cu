@@ -1906,23 +1906,50 @@ __host__ __device__ inline uint32_t ShardFirstItem(const unsigned long long* uni
     }
     return lo;
 }
+// Shards.  The work items are cut into `shards` = world x shardsPerRank contiguous, unit-balanced runs and dealt to the ranks in
+// boustrophedon order (0 1 .. N-1, N-1 .. 1 0, ...): the cost of an item follows the level line through it, not its micro-triangle
+// count, and varies slowly over a mesh -- one contiguous run per rank left rank 0 waiting 0.7 of 6.4 ms for rank 1 at config 3 on
+// two GPUs; folded runs average such trends out without a cost model.  One rank: one shard.
+constexpr int kMaxShardsPerRank = 4;
+constexpr int kMaxShards = 64;
+__host__ __device__ inline int ShardOwner(int shard, int world) {
+    const int pass = shard / world, pos = shard % world;
+    return (pass & 1) ? world - 1 - pos : pos;
+}
+static int ShardsPerRank(int world) {
+    if (world <= 1) return 1;
+    // Measured at config 3: two shards per rank win 2.3 % on two GPUs (8.22 -> 8.03 ms: no more waiting, +0.1 ms for the second chunk
+    // sequence); on four the second chunk sequence and the doubled launches cost what the balance gains (5.3-5.4 vs 5.4-5.7 ms), so
+    // the default folds only on two ranks.  OMM_B200_SHARDS_PER_RANK=1..4 overrides (A/B runs, parity tests of the folded layout).
+    static const int requested = [] {
+        const char* e = getenv("OMM_B200_SHARDS_PER_RANK");
+        const int v = e ? atoi(e) : 0;
+        return v < 0 ? 0 : (v > kMaxShardsPerRank ? kMaxShardsPerRank : v);
+    }();
+    const int r = requested > 0 ? requested : (world == 2 ? 2 : 1);
+    return std::max(1, std::min(r, kMaxShards / world));
+}
+struct OwnedShards {
+    int count;
+    int shard[kMaxShardsPerRank];
+};
 __global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart,
-                            const unsigned long long* __restrict__ nodeStart, uint32_t entries, int world, int rank, unsigned long long chunkRegions,
-                            ShardBound* __restrict__ bounds, uint32_t* __restrict__ chunkFirstItem) {
+                            const unsigned long long* __restrict__ nodeStart, uint32_t entries, int world /* number of shards */, OwnedShards owned,
+                            unsigned long long chunkRegions, ShardBound* __restrict__ bounds, uint32_t* __restrict__ chunkFirstItem) {
     const int r = threadIdx.x;
-    {
-        // chunks of the hierarchical classifier: runs of whole work items of this rank holding about `chunkRegions` initial regions each
-        const uint32_t ib = ShardFirstItem(unitStart, entries, world, rank), ie = ShardFirstItem(unitStart, entries, world, rank + 1);
+    for (int k = 0; k < owned.count; ++k) {
+        // chunks of the hierarchical classifier: runs of whole work items of an owned shard holding about `chunkRegions` initial regions each
+        const uint32_t ib = ShardFirstItem(unitStart, entries, world, owned.shard[k]), ie = ShardFirstItem(unitStart, entries, world, owned.shard[k] + 1);
         if (r <= kHierMaxChunks) {
-            chunkRegions = HierChunkRegions(nodeStart[ie] - nodeStart[ib], chunkRegions);
-            const unsigned long long target = nodeStart[ib] + (unsigned long long)r * chunkRegions;
+            const unsigned long long cr = HierChunkRegions(nodeStart[ie] - nodeStart[ib], chunkRegions);
+            const unsigned long long target = nodeStart[ib] + (unsigned long long)r * cr;
             uint32_t lo = ib, hi = ie;  // smallest item in [ib, ie] whose first region is >= target
             while (lo < hi) {
                 const uint32_t mid = lo + ((hi - lo) >> 1);
                 if (nodeStart[mid] >= target) hi = mid;
                 else lo = mid + 1;
             }
-            chunkFirstItem[r] = lo;
+            chunkFirstItem[k * (kHierMaxChunks + 1) + r] = lo;
         }
     }
     if (r > world) return;
@@ -2051,7 +2078,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr, *itemNodes = nullptr, *nodeStart = nullptr;
     ShardBound* boundsDev = nullptr;
     uint32_t* chunkFirstDev = nullptr;
-    uint32_t chunkFirst[kHierMaxChunks + 1];
+    uint32_t chunkFirst[kMaxShardsPerRank][kHierMaxChunks + 1];
+    const int numShards = world * ShardsPerRank(world);  // see ShardOwner
+    OwnedShards owned{};
     const unsigned long long hierChunkRegions = HierNominalChunkRegions(baker->device);
     uint32_t* stateWords = nullptr;
     uint32_t* compactWords = nullptr;                // sharded bakes: blocks of the items without a special index, see the exchange
@@ -2079,7 +2108,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     memset(countersHost, 0, sizeof(countersHost));
     memset(bounds, 0, sizeof(bounds));
 
-    if (world > 64) return ommResult_INVALID_ARGUMENT;
+    if (world > kMaxShards) return ommResult_INVALID_ARGUMENT;
+    for (int v = 0; v < numShards; ++v)
+        if (ShardOwner(v, world) == rank) owned.shard[owned.count++] = v;
     if (!stream) {
         if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
             cudaGetLastError();
@@ -2142,7 +2173,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&triItem, T));
         CUDA_TRY(scratch.alloc(&triFinal, T));
         CUDA_TRY(scratch.alloc(&boundsDev, 65));
-        CUDA_TRY(scratch.alloc(&chunkFirstDev, kHierMaxChunks + 1));
+        CUDA_TRY(scratch.alloc(&chunkFirstDev, (size_t)kMaxShardsPerRank * (kHierMaxChunks + 1)));
         CUDA_TRY(cudaMemsetAsync(counters, 0, 32 * sizeof(uint32_t), stream));
         CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
         SetupTriangles<<<gridT, TPB, 0, stream>>>(sa, triUV, triLevel, triFormat, triDegenerate, fixList, counters);
@@ -2220,10 +2251,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemNodes, nodeStart, (int)T + 1, stream));
             launches += 6;
         }
-        ShardBounds<<<1, 128, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, world, rank, hierChunkRegions, boundsDev, chunkFirstDev);
+        ShardBounds<<<1, 128, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, numShards, owned, hierChunkRegions, boundsDev, chunkFirstDev);
         launches++;
         CUDA_TRY(cudaMemcpyAsync(countersHost, counters, sizeof(countersHost), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (world + 1), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(chunkFirst, chunkFirstDev, sizeof(chunkFirst), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(&totalUnits, unitStart + T, 8, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(&totalWords, wordStart + T, 8, cudaMemcpyDeviceToHost, stream));
@@ -2259,16 +2290,19 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     // ---- K4: classification of this rank's shard of work items ----
     if (W > 0) {
-        const uint32_t itemBegin = bounds[rank].item, itemEnd = bounds[rank + 1].item;
-        const unsigned long long unitBegin = bounds[rank].unit, unitEnd = bounds[rank + 1].unit;
+        uint32_t myItems = 0;
+        for (int k = 0; k < owned.count; ++k) myItems += bounds[owned.shard[k] + 1].item - bounds[owned.shard[k]].item;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
-        if (itemEnd > itemBegin && useHier) {
+        if (myItems > 0 && useHier) {
             if (P.tex.mipCount == 1) GetCellTables(const_cast<TextureObject*>(tex), P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
             // worst case of a chunk: the nominal number of initial regions plus the rest of its last item (at most 4^9 regions at level 12)
-            const unsigned long long regionBegin = bounds[rank].node, regionEnd = bounds[rank + 1].node;
-            const unsigned long long cap = std::min<unsigned long long>(HierChunkRegions(regionEnd - regionBegin, hierChunkRegions) + (1ull << 18), regionEnd - regionBegin);
+            unsigned long long cap = 0;
+            for (int k = 0; k < owned.count; ++k) {
+                const unsigned long long regions = bounds[owned.shard[k] + 1].node - bounds[owned.shard[k]].node;
+                cap = std::max(cap, std::min<unsigned long long>(HierChunkRegions(regions, hierChunkRegions) + (1ull << 18), regions));
+            }
             HierItem* hierItems = nullptr;
             HierLists lists{};
             CUDA_TRY(scratch.alloc(&hierItems, (size_t)W * (size_t)P.tex.mipCount));
@@ -2286,38 +2320,49 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             int sms = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
             const uint32_t listGrid = (uint32_t)std::max(sms, 1) * 16u;
-            HierPrepare<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, itemBegin, itemEnd, hierItems);
-            launches++;
-            for (int c = 0; c < kHierMaxChunks; ++c) {
-                const uint32_t i0 = chunkFirst[c], i1 = chunkFirst[c + 1];
-                if (i0 >= itemEnd) break;
-                if (i1 <= i0) continue;
-                CUDA_TRY(cudaMemsetAsync(lists.count, 0, 8 * sizeof(unsigned long long), stream));
-                hier.initial<<<listGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
-                hier.unresolved<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
-                hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
-                hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
-                hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
-                hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
-                launches += 6;
-            }
-        } else if (itemEnd > itemBegin) {
-            const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
-            const unsigned long long blocks = (unitEnd - unitBegin + unitsPerBlock - 1) / unitsPerBlock;
-            const unsigned long long kMaxGrid = 0x7FFFFFFFull;
-            const ClassifyFn classify = SelectClassifyKernel(P);
-            for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
-                const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
-                classify<<<(uint32_t)nb, kClassifyWarps * 32, 0, stream>>>(P, items, unitStart, wordStart, itemBegin, itemEnd,
-                                                                          unitBegin + b0 * unitsPerBlock, unitEnd, stateWords);
+            for (int k = 0; k < owned.count; ++k) {
+                const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
+                if (itemEnd <= itemBegin) continue;
+                HierPrepare<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, itemBegin, itemEnd, hierItems);
                 launches++;
+                for (int c = 0; c < kHierMaxChunks; ++c) {
+                    const uint32_t i0 = chunkFirst[k][c], i1 = chunkFirst[k][c + 1];
+                    if (i0 >= itemEnd) break;
+                    if (i1 <= i0) continue;
+                    CUDA_TRY(cudaMemsetAsync(lists.count, 0, 8 * sizeof(unsigned long long), stream));
+                    hier.initial<<<listGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
+                    hier.unresolved<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
+                    hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
+                    hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
+                    hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
+                    hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
+                    launches += 6;
+                }
+            }
+        } else if (myItems > 0) {
+            const ClassifyFn classify = SelectClassifyKernel(P);
+            for (int k = 0; k < owned.count; ++k) {
+                const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
+                const unsigned long long unitBegin = bounds[owned.shard[k]].unit, unitEnd = bounds[owned.shard[k] + 1].unit;
+                if (itemEnd <= itemBegin) continue;
+                const unsigned long long unitsPerBlock = (unsigned long long)kClassifyWarps * (UseQueueKernel(P) ? kBatchUnits : 1);
+                const unsigned long long blocks = (unitEnd - unitBegin + unitsPerBlock - 1) / unitsPerBlock;
+                const unsigned long long kMaxGrid = 0x7FFFFFFFull;
+                for (unsigned long long b0 = 0; b0 < blocks; b0 += kMaxGrid) {
+                    const unsigned long long nb = std::min(kMaxGrid, blocks - b0);
+                    classify<<<(uint32_t)nb, kClassifyWarps * 32, 0, stream>>>(P, items, unitStart, wordStart, itemBegin, itemEnd,
+                                                                              unitBegin + b0 * unitsPerBlock, unitEnd, stateWords);
+                    launches++;
+                }
             }
         }
         myMicroTris = microTris;
         CUDA_TRY(cudaEventRecord(ev[4], stream));  // end of the classification kernels proper
         CUDA_TRY(scratch.alloc(&digest, W));
         CUDA_TRY(scratch.alloc(&special, W));
-        if (itemEnd > itemBegin) {
+        for (int k = 0; k < owned.count; ++k) {
+            const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
+            if (itemEnd <= itemBegin) continue;
             // special-index scan + XXH64 of this rank's items (their state words are local already)
             ItemPostKernel<<<(itemEnd - itemBegin + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
                                                                               (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
@@ -2328,7 +2373,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         if (world > 1) {
             // exact share of micro-triangles classified on this rank
             CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
-            if (itemEnd > itemBegin) {
+            for (int k = 0; k < owned.count; ++k) {
+                const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
+                if (itemEnd <= itemBegin) continue;
                 SumMicroTriangles<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(items, itemBegin, itemEnd, workloadDev);
                 launches++;
             }
@@ -2342,14 +2389,15 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             const ncclComm_t comm = (ncclComm_t)baker->shard.ncclComm;
             const bool fullBlocks = HostPassesNeeded(d);  // the host passes read and rewrite every block
             bool ncclOk = nccl.GroupStart() == ncclSuccess;
-            for (int r = 0; r < world && ncclOk; ++r) {
+            for (int r = 0; r < numShards && ncclOk; ++r) {  // one broadcast per shard, rooted at its owner
+                const int root = ShardOwner(r, world);
                 const size_t count = (size_t)(bounds[r + 1].word - bounds[r].word);
                 uint32_t* seg = stateWords + bounds[r].word;
-                if (fullBlocks && count) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint32, r, comm, stream) == ncclSuccess;
+                if (fullBlocks && count) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint32, root, comm, stream) == ncclSuccess;
                 const size_t nItems = bounds[r + 1].item - bounds[r].item;
                 if (ncclOk && nItems) {
-                    ncclOk = nccl.Broadcast(digest + bounds[r].item, digest + bounds[r].item, nItems, ncclUint64, r, comm, stream) == ncclSuccess;
-                    ncclOk = ncclOk && nccl.Broadcast(special + bounds[r].item, special + bounds[r].item, nItems, ncclInt32, r, comm, stream) == ncclSuccess;
+                    ncclOk = nccl.Broadcast(digest + bounds[r].item, digest + bounds[r].item, nItems, ncclUint64, root, comm, stream) == ncclSuccess;
+                    ncclOk = ncclOk && nccl.Broadcast(special + bounds[r].item, special + bounds[r].item, nItems, ncclInt32, root, comm, stream) == ncclSuccess;
                 }
             }
             ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
@@ -2371,18 +2419,22 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 CompactSizes<<<(W + 1 + TPB - 1) / TPB, TPB, 0, stream>>>(special, itemWords, W, compactSizes);
                 size_t tmp = cubTempBytes;
                 CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, compactSizes, compactStart, (int)W + 1, stream));
-                CompactBoundsKernel<<<1, 96, 0, stream>>>(compactStart, boundsDev, world, compactBoundsDev);
-                if (itemEnd > itemBegin)
-                    CompactCopy<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(special, itemWords, wordStart, compactStart, stateWords, itemBegin, itemEnd, compactWords);
+                CompactBoundsKernel<<<1, 96, 0, stream>>>(compactStart, boundsDev, numShards, compactBoundsDev);
+                for (int k = 0; k < owned.count; ++k) {
+                    const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
+                    if (itemEnd > itemBegin)
+                        CompactCopy<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(special, itemWords, wordStart, compactStart, stateWords, itemBegin, itemEnd, compactWords);
+                }
                 launches += 6;
                 if (gatherEv[1]) CUDA_TRY(cudaEventRecord(gatherEv[1], stream));
-                CUDA_TRY(cudaMemcpyAsync(compactBounds, compactBoundsDev, sizeof(unsigned long long) * (world + 1), cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaMemcpyAsync(compactBounds, compactBoundsDev, sizeof(unsigned long long) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
                 HostTrace::Mark("    exchange: compact bounds read (host sync)");
                 ncclOk = nccl.GroupStart() == ncclSuccess;
-                for (int r = 0; r < world && ncclOk; ++r) {
+                for (int r = 0; r < numShards && ncclOk; ++r) {
                     const size_t count = (size_t)(compactBounds[r + 1] - compactBounds[r]);
-                    if (count) ncclOk = nccl.Broadcast(compactWords + compactBounds[r], compactWords + compactBounds[r], count, ncclUint32, r, comm, stream) == ncclSuccess;
+                    if (count)
+                        ncclOk = nccl.Broadcast(compactWords + compactBounds[r], compactWords + compactBounds[r], count, ncclUint32, ShardOwner(r, world), comm, stream) == ncclSuccess;
                 }
                 ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
                 if (gatherEv[2]) CUDA_TRY(cudaEventRecord(gatherEv[2], stream));

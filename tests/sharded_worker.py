@@ -38,12 +38,19 @@ def main():
         "c5_mixed": W.config5(num_tris=4000, tex_size=256, distinct=300, flat_tris=600, max_level=8),
         "c2": W.config2(num_quads=400, tex_size=256, level=4),
         "tiny_levels": PC.cases()["per_triangle_levels"][0](),
+        # the flat classifier (Nearest filter) and the host passes (every state block is exchanged) over several shards per rank
+        "c3_nearest": (W.config3(num_tris=1500, tex_size=256, level=5), dict(filter=capi.FILTER_NEAREST)),
+        "c3_near_duplicates": (W.config3(num_tris=600, tex_size=128, level=4), dict(bake_flags=capi.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION)),
+        "three_items": W.config3(num_tris=3, tex_size=64, level=3),  # fewer work items than shards
     }
     out = {}
     for name, wl in cases.items():
+        over = {}
+        if isinstance(wl, tuple):
+            wl, over = wl
         # single-GPU result on this rank
         with Baker(lib) as b:
-            inp, tex = W.make_input(b, wl)
+            inp, tex = W.make_input(b, wl, **over)
             single = b.bake(inp)
             tex.destroy()
         # sharded result
@@ -56,7 +63,7 @@ def main():
         dist.broadcast(idbuf, 0)
         raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
         assert lib.dll.ommB200InitSharding(b.handle, rank, world, raw, 128) == capi.SUCCESS
-        inp, tex = W.make_input(b, wl)
+        inp, tex = W.make_input(b, wl, **over)
         sharded = b.bake(inp)
         mine = sharded.timings.microTriangles
         tex.destroy()
