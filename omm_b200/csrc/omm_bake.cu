@@ -909,16 +909,9 @@ __global__ void __launch_bounds__(128, OMM_LIST_MIN_BLOCKS) HierTestUnresolved(c
     }
 }
 
-// Queue of deferred edge tests (LeafCell): (item, micro-triangle, cell).  When it is full the tests are evaluated in place.
-struct HierEdgeQueue {
-    uint4* entries;
-    unsigned long long* count;
-    unsigned long long capacity;
-};
-
 template <class Cfg>
 __global__ void __launch_bounds__(128, OMM_LEAF_MIN_BLOCKS) HierLeaves(const BakeParams P, const ItemRec* __restrict__ items, const HierItem* __restrict__ hierItems,
-                                                   const unsigned long long* __restrict__ wordStart, HierLists lists, HierEdgeQueue queue,
+                                                   const unsigned long long* __restrict__ wordStart, HierLists lists,
                                                    uint32_t* __restrict__ stateWords) {
     const unsigned long long total = lists.count[2] * 4ull;
     const unsigned long long rounded = (total + 31ull) & ~31ull;
@@ -935,8 +928,7 @@ __global__ void __launch_bounds__(128, OMM_LEAF_MIN_BLOCKS) HierLeaves(const Bak
             uint32_t st = 0;
             if (index < (1u << (2 * hi.level))) {  // a level-0 item has one micro-triangle in its only "4-region"
                 if (hi.ok) {
-                    // The edge tests stay in place: queueing them for HierEdgeTests (and a single-micro-triangle TestRegion first)
-                    // was measured slower -- both re-derive the vertices and the cell, and the tests diverge just as much there.
+                    // (a single-micro-triangle TestRegion first was measured slower: the leaf's own edge filter (D) does the same work)
                     if (M == 1) st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
                     else st = (uint32_t)LeafClassifyMips<Cfg>(P, [&](int k) { return k == 0 ? hi : LoadHierItem(its + k); }, index);
                 }
@@ -974,35 +966,17 @@ __global__ void __launch_bounds__(128) HierLeavesSlow(const BakeParams P, const 
     }
 }
 
-// The queued edge tests, one per thread.  A hit makes the micro-triangle Unknown (see LeafEdgeTests).
-template <class Cfg>
-__global__ void __launch_bounds__(128) HierEdgeTests(const BakeParams P, const HierItem* __restrict__ hierItems, const unsigned long long* __restrict__ wordStart,
-                                                      HierEdgeQueue queue, uint32_t* __restrict__ stateWords) {
-    const unsigned long long n = *queue.count < queue.capacity ? *queue.count : queue.capacity;
-    const uint32_t unknown = (uint32_t)StateFromCoverage(P, 1, 1);
-    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint4 e = queue.entries[t];
-        const HierItem hi = LoadHierItem(hierItems + (size_t)e.x * P.tex.mipCount);
-        if (!LeafEdgeTests<Cfg>(P, P.tex.mips[0], hi, e.y, (int)e.z, (int)e.w)) continue;
-        uint32_t* word = stateWords + __ldg(&wordStart[e.x]) + (e.y >> 4);
-        const uint32_t shift = 2u * (e.y & 15u);
-        if (unknown != 3u) atomicAnd(word, ~(3u << shift));
-        if (unknown != 0u) atomicOr(word, unknown << shift);
-    }
-}
-
 struct HierKernels {
     void (*initial)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, uint32_t, uint32_t, HierLists, uint32_t*, uint32_t*);
     void (*list)(const BakeParams, const HierItem*, const unsigned long long*, const unsigned long long*, const unsigned long long*, unsigned long long*,
                  unsigned long long*, int, uint32_t*);
-    void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, HierEdgeQueue, uint32_t*);
-    void (*edgeTests)(const BakeParams, const HierItem*, const unsigned long long*, HierEdgeQueue, uint32_t*);
+    void (*leaves)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
     void (*unresolved)(const BakeParams, const HierItem*, const unsigned long long*, HierLists, uint32_t*, uint32_t*);
     void (*leavesSlow)(const BakeParams, const ItemRec*, const HierItem*, const unsigned long long*, HierLists, uint32_t*);
 };
 template <class Cfg>
 static HierKernels MakeHierKernels() {
-    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierEdgeTests<Cfg>, HierTestUnresolved<Cfg>, HierLeavesSlow<Cfg>};
+    return HierKernels{HierTestInitial<Cfg>, HierTestList<Cfg>, HierLeaves<Cfg>, HierTestUnresolved<Cfg>, HierLeavesSlow<Cfg>};
 }
 
 // OMM_B200_CLASSIFIER=flat|queue selects the older kernels (A/B measurements and parity cross-checks); default = hierarchical.
@@ -2311,10 +2285,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
             CUDA_TRY(scratch.alloc(&lists.unresolved, (size_t)cap));
             CUDA_TRY(scratch.alloc(&lists.slow, (size_t)cap * 16));
-            CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [4] queued edge tests (unused)
-            HierEdgeQueue queue{};  // unused: see HierLeaves
-            queue.capacity = 0;
-            queue.count = lists.count + 4;
+            CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
             int sms = 0;
@@ -2334,7 +2305,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     hier.unresolved<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
                     hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                     hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
-                    hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, queue, stateWords);
+                    hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
                     hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
                     launches += 6;
                 }

@@ -466,10 +466,10 @@ OMM_HD int TestRegion(const BakeParams& P, const DevMip& m, const HierItem& it, 
 // (E) Votes that cannot matter.  Unless the promotion is Nearest the state depends only on which counters are non-zero
 //     (bake_kernels_cpu.h:27-50).  In a cell whose four texels are on side s, where side s has been voted already and the
 //     edge filter holds, the corner and flat-patch branches can only vote s again: the whole cell is skipped.
-// `defer(px, py)` may take over the three edge tests of this cell (HierLeaves queues them for HierEdgeTests so that the
-// expensive divisions and square roots run densely packed); it returns false to have them evaluated here.
-template <class Cfg, class Defer>
-OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, const Tri& tri, int px, int py, Coverage& cov, bool countsMatter, Defer&& defer) {
+// (Evaluating the edge tests elsewhere -- queued for a kernel of their own, or parked in a per-warp shared-memory queue and run one
+// edge per lane after the walk -- was built twice and measured slower both times; they stay in place.)
+template <class Cfg>
+OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, const Tri& tri, int px, int py, Coverage& cov, bool countsMatter) {
     const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
     const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
     const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
@@ -547,7 +547,6 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
         return;
     }
     if (edgesCannotHit) return;
-    if (!countsMatter && defer(px, py)) return;
     // (Testing the edges whose end points straddle the level line first was measured: the per-lane order makes the calls diverge
     // and costs more than the skipped tests save.)
     const bool hit = EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d);
@@ -557,34 +556,10 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
     }
 }
 
-// The deferred part of LeafCell: the three edge tests of micro-triangle `index` in cell (px, py), same operands as above.
-// A hit votes for both sides; unless the promotion is Nearest (never deferred) the state then is StateFromCoverage(1, 1)
-// whatever else was voted, so the caller simply overwrites the state LeafClassify stored.
-template <class Cfg>
-OMM_HD bool LeafEdgeTests(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, int px, int py) {
-    const Tri tri = MicroTri(it.p0, it.p1, it.p2, index, it.level);
-    const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
-    const int x0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px, m.w, m.log2w), y0 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py, m.h, m.log2h);
-    const int x1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, px + 1, m.w, m.log2w), y1 = Addr1<Cfg>(P.addrMode, P.pow2Mip0, py + 1, m.h, m.log2h);
-    const float gx = TexFetch<Cfg>(P, m, x0, y0);
-    const float gy = TexFetch<Cfg>(P, m, x0, y1);
-    const float gz = TexFetch<Cfg>(P, m, x1, y1);
-    const float gw = TexFetch<Cfg>(P, m, x1, y0);
-    const float b = gw - gx;
-    const float c = gy - gx;
-    const float d = gx + gz - gy - gw;
-    const float sx = (float)m.w, sy = (float)m.h;
-    const float h0 = gx - P.cutoff;
-    const float2 q0 = make_float2(sx * tri.p0.x - pfx, sy * tri.p0.y - pfy);
-    const float2 q1 = make_float2(sx * tri.p1.x - pfx, sy * tri.p1.y - pfy);
-    const float2 q2 = make_float2(sx * tri.p2.x - pfx, sy * tri.p2.y - pfy);
-    return EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d);
-}
-
 // One micro-triangle of a non-degenerate work item, Linear filter, level-line test, single mip, no SAT pass
 // (ref: bake_cpu_impl.cpp:861-908 with ResampleFine's Normal path).
-template <class Cfg, class Defer>
-OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index, Defer&& defer) {
+template <class Cfg>
+OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index) {
     const Tri st = MicroTri(it.p0, it.p1, it.p2, index, it.level);
     if (P.useCoarse) {
         // SAT pass of the reference first (bake_cpu_impl.cpp:749-801, 861-864).  The hierarchical path is only taken when the
@@ -614,14 +589,11 @@ OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it
     RasterCursor cur = RasterBegin(rs);
     int x, y;
     while (RasterNext(rs, cur, x, y)) {
-        LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter, defer);
+        LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter);
         if (!countsMatter && cov.above != 0 && cov.below != 0) break;  // exact early-out, see ClassifyMicroTriangle
     }
     return StateFromCoverage(P, cov.above, cov.below);
 }
-struct NeverDefer {
-    OMM_HD bool operator()(int, int) const { return false; }
-};
 // Several mips (ref: bake_cpu_impl.cpp:866-908): the reference classifies against mip 0, 1, ... and stops as soon as the state is an
 // Unknown one; votes accumulate over the mips.  `itemOfMip(k)` returns the HierItem of the work item for mip k (the constants of the
 // exact skips depend on the mip's size).  The region tests demand the same side on EVERY mip, which gives state(s) whether or not the
@@ -642,17 +614,13 @@ OMM_HD int LeafClassifyMips(const BakeParams& P, const ItemOfMip& itemOfMip, uin
         int x, y;
         bool stop = false;
         while (RasterNext(rs, cur, x, y)) {
-            LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter, NeverDefer());
+            LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter);
             if (!countsMatter && cov.above != 0 && cov.below != 0) { stop = true; break; }  // exact early-out, see ClassifyMicroTriangle
         }
         if (stop) break;
         if (IsUnknownState(StateFromCoverage(P, cov.above, cov.below))) break;
     }
     return StateFromCoverage(P, cov.above, cov.below);
-}
-template <class Cfg>
-OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it, uint32_t index) {
-    return LeafClassify<Cfg>(P, m, it, index, NeverDefer());
 }
 
 }  // namespace ommb200

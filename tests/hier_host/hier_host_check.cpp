@@ -41,20 +41,7 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem* his, u
             }
         }
         if (hi.ok) {
-            // as HierLeaves + HierEdgeTests: the edge tests are queued and evaluated afterwards; any hit overwrites the state
-            std::vector<std::pair<int, int>> queued;
-            auto defer = [&](int px, int py) {
-                if ((index + (uint32_t)px) % 5u == 0) return false;  // exercise the "queue full -> evaluate in place" path too
-                queued.push_back({px, py});
-                return true;
-            };
-            int state;
-            if (M == 1) {
-                state = LeafClassify<Cfg>(P, m, hi, index, defer);
-                for (auto& q : queued)
-                    if (LeafEdgeTests<Cfg>(P, m, hi, index, q.first, q.second)) state = StateFromCoverage(P, 1, 1);
-            } else
-                state = LeafClassifyMips<Cfg>(P, [&](int k) { return his[k]; }, index);
+            const int state = M == 1 ? LeafClassify<Cfg>(P, m, hi, index) : LeafClassifyMips<Cfg>(P, [&](int k) { return his[k]; }, index);
             states[idx] = (uint8_t)state;
         } else
             states[idx] = (uint8_t)ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L);
