@@ -366,7 +366,7 @@ typedef struct ommB200BakeTimings {
     float setupMs;      /* triangle fetch, level selection, UV pre-dedup               */
     float classifyMs;   /* coarse (SAT) + fine micro-triangle classification kernels   */
     float postMs;       /* special-index scan, XXH64, dedup, sort, scan, pack, indices */
-    float d2hMs;        /* download of the result arrays                               */
+    float d2hMs;        /* download of the result arrays (copy-stream time of the overlapped part included) */
     float totalDeviceMs;/* first event to last event                                   */
     uint64_t microTriangles;     /* sum over work items of 4^level (items classified on this rank) */
     uint32_t workItems;          /* unique UV triangles after pre-dedup (global)        */
@@ -378,8 +378,9 @@ typedef struct ommB200BakeTimings {
     uint32_t reserved;
     /* host wall clock of the same call, milliseconds (std::chrono::steady_clock) */
     float hostStageMs;    /* ommB200StageInputs part: index scan, allocations, H2D      */
-    float hostBakeMs;     /* device pipeline incl. the two small read-backs              */
-    float hostDownloadMs; /* host allocation + D2H of the result arrays                  */
+    float hostBakeMs;     /* device pipeline incl. the small read-backs; in ommCpuBake also the array-data
+                             download, which starts with the first packed slice (d2hMs has its copy time) */
+    float hostDownloadMs; /* host allocation + D2H of what was not sent during the bake  */
     float hostTotalMs;    /* whole ommCpuBake call                                       */
     float itemPostMs;     /* special-index scan + XXH64 of this rank's items (part of postMs) */
     float gatherMs;       /* NCCL all-gather of state blocks / digests (0 on one GPU; part of postMs) */
@@ -421,8 +422,11 @@ OMM_API ommResult ommB200DownloadResult(ommCpuBakeResult bakeResult);
 
 /*
  * Multi-GPU: one process per GPU.  Every rank calls the same bake with the same desc; work items are
- * sharded across ranks; one ncclAllGather of fixed-size per-item records precedes the (replicated)
- * dedup / sort / offset merge.  ncclUniqueIdBytes is the 128-byte ncclUniqueId created by rank 0 and
+ * sharded across ranks (contiguous unit-balanced runs, dealt in boustrophedon order when there are
+ * several per rank); one all-gather of per-item records and of the state blocks that can still be
+ * serialized precedes the (replicated) dedup / sort / offset merge.  Every rank then holds the complete
+ * result in HBM; ommCpuGetBakeResultDesc / ommB200DownloadResult make the host copy on the ranks that
+ * call them.  ncclUniqueIdBytes is the 128-byte ncclUniqueId created by rank 0 and
  * distributed by the launcher (bench.py uses torch.distributed for that).
  */
 OMM_API ommResult ommB200InitSharding(ommBaker baker, int rank, int worldSize, const void* ncclUniqueIdBytes, size_t idSize);
@@ -430,5 +434,9 @@ OMM_API ommResult ommB200GetNcclUniqueId(void* outBytes, size_t idSize);
 /* The partition used by sharded bakes, exposed for tests: unitPrefix is the exclusive prefix sum (entries = items + 1,
  * last entry = total) of per-item warp units (max(4^level / 32, 1)); outFirstItem receives worldSize + 1 item indices. */
 OMM_API ommResult ommB200ComputeShardBounds(const uint64_t* unitPrefix, uint32_t entries, int worldSize, uint32_t* outFirstItem);
+/* How the runs are dealt (exposed for tests): a sharded bake cuts the work items into worldSize x ommB200ShardsPerRank(worldSize)
+ * runs with the partition above (called with that product as its worldSize); run s is classified by rank ommB200ShardOwner(s). */
+OMM_API int ommB200ShardsPerRank(int worldSize);
+OMM_API int ommB200ShardOwner(int shard, int worldSize);
 
 #endif /* OMM_B200_H_ */

@@ -232,7 +232,7 @@ SERIALIZE_SYMBOLS = [
 B200_SYMBOLS = [
     "ommDebugGetStats", "ommB200SetDevice", "ommB200GetDeviceCount", "ommB200GetLastBakeTimings", "ommB200StageInputs",
     "ommB200DestroyStagedInputs", "ommB200BakeResident", "ommB200GetDeviceResultDesc", "ommB200DownloadResult",
-    "ommB200InitSharding", "ommB200GetNcclUniqueId", "ommB200ComputeShardBounds",
+    "ommB200InitSharding", "ommB200GetNcclUniqueId", "ommB200ComputeShardBounds", "ommB200ShardsPerRank", "ommB200ShardOwner",
 ]
 
 
@@ -313,6 +313,10 @@ class OmmLib:
             d.ommB200GetNcclUniqueId.argtypes = [C.c_void_p, C.c_size_t]
             d.ommB200ComputeShardBounds.restype = C.c_int
             d.ommB200ComputeShardBounds.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]
+            d.ommB200ShardsPerRank.restype = C.c_int
+            d.ommB200ShardsPerRank.argtypes = [C.c_int]
+            d.ommB200ShardOwner.restype = C.c_int
+            d.ommB200ShardOwner.argtypes = [C.c_int, C.c_int]
 
     def exported(self, name: str) -> bool:
         return hasattr(self.dll, name)

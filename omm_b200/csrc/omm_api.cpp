@@ -564,6 +564,8 @@ OMM_API ommResult ommB200InitSharding(ommBaker baker, int rank, int worldSize, c
     return InitSharding(HandlePtr<BakerObject>(baker), rank, worldSize, ncclUniqueIdBytes, idSize);
 }
 OMM_API ommResult ommB200GetNcclUniqueId(void* outBytes, size_t idSize) { return GetNcclUniqueId(outBytes, idSize); }
+OMM_API int ommB200ShardsPerRank(int worldSize) { return ShardsPerRankOf(worldSize); }
+OMM_API int ommB200ShardOwner(int shard, int worldSize) { return ShardOwnerOf(shard, worldSize); }
 OMM_API ommResult ommB200ComputeShardBounds(const uint64_t* unitPrefix, uint32_t entries, int worldSize, uint32_t* outFirstItem) {
     return ComputeShardBounds((const unsigned long long*)unitPrefix, entries, worldSize, outFirstItem);
 }

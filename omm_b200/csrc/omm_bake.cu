@@ -1940,6 +1940,9 @@ ommResult ComputeShardBounds(const unsigned long long* unitStart, uint32_t entri
     return ommResult_SUCCESS;
 }
 
+int ShardsPerRankOf(int world) { return world < 1 ? 0 : ShardsPerRank(world); }
+int ShardOwnerOf(int shard, int world) { return (world < 1 || shard < 0) ? -1 : ShardOwner(shard, world); }
+
 // ---- multi-GPU exchange of the state blocks that can still be serialized (items without a special index) ------------------------
 __global__ void CompactSizes(const int32_t* __restrict__ special, const unsigned long long* __restrict__ itemWords, uint32_t numItems,
                              unsigned long long* __restrict__ compactWords) {

@@ -227,6 +227,8 @@ ommResult InitSharding(BakerObject* baker, int rank, int world, const void* id, 
 ommResult GetNcclUniqueId(void* out, size_t size);
 void DestroySharding(BakerObject* baker);
 ommResult ComputeShardBounds(const unsigned long long* unitStart, uint32_t entries, int world, uint32_t* outFirstItem);
+int ShardsPerRankOf(int world);
+int ShardOwnerOf(int shard, int world);
 int CurrentDeviceOr(int fallback);
 // Page-locked host blocks recycled across bakes (used for big result arrays when the caller left the allocator to us).
 void* PinnedPoolAcquire(size_t bytes);

@@ -70,6 +70,24 @@ def test_shard_partition_single_process():
         assert np.all(np.diff(first.astype(np.int64)) >= 0)
 
 
+def test_runs_are_dealt_evenly_and_folded():
+    """Sharded bakes cut the work items into world x shardsPerRank runs; every rank gets the same number of runs, each run exactly one
+    owner, and consecutive passes run in opposite directions (so that a cost trend along the mesh averages out)."""
+    from omm_b200 import capi
+    lib = capi.OmmLib(capi.PRODUCT_LIB)
+    assert lib.dll.ommB200ShardsPerRank(1) == 1
+    for world in (2, 3, 4, 8, 16, 64):
+        per = lib.dll.ommB200ShardsPerRank(world)
+        assert 1 <= per <= 4 and world * per <= 64
+        for per_rank in (1, 2, 3, 4):
+            owners = [lib.dll.ommB200ShardOwner(s, world) for s in range(world * per_rank)]
+            assert sorted(owners) == sorted(list(range(world)) * per_rank)
+            for p in range(per_rank):
+                run = owners[p * world:(p + 1) * world]
+                assert run == (list(range(world)) if p % 2 == 0 else list(range(world - 1, -1, -1)))
+    assert lib.dll.ommB200ShardOwner(-1, 2) == -1 and lib.dll.ommB200ShardOwner(0, 0) == -1
+
+
 def test_world_size_2_gloo(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
