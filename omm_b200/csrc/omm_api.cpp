@@ -59,15 +59,6 @@ static const char* FormatName(ommFormat f) {  // ref: util/util.h:57-68
     default: return "Unknown";
     }
 }
-static const char* SpecialIndexName(ommSpecialIndex s) {  // ref: log.h:20-31
-    switch (s) {
-    case ommSpecialIndex_FullyTransparent: return "Fully Transparent";
-    case ommSpecialIndex_FullyOpaque: return "Fully Opaque";
-    case ommSpecialIndex_FullyUnknownTransparent: return "Fully Unknown Transparent";
-    case ommSpecialIndex_FullyUnknownOpaque: return "Fully Unknown Opaque";
-    default: return "Unknown State";
-    }
-}
 static bool StateCompatible(ommOpacityState s, ommFormat f) {  // ref: util/util.h:27-34
     if (f == ommFormat_OC1_2_State) return s == ommOpacityState_Opaque || s == ommOpacityState_Transparent;
     return true;
