@@ -345,7 +345,7 @@ def run_b200(a):
                 "kernel_ms": cls_ms, "algorithmic_bytes": classify_bytes,
                 "note": "instruction-issue bound, not HBM bound: 0.27 algorithmic bytes per micro-triangle against the bit-exact level-line arithmetic "
                         "(IEEE divisions and square roots) of every micro-triangle the level line touches; the hierarchical classifier removes the "
-                        "arithmetic of provably uniform regions (97 % of the micro-triangles), profiles/r1c_* hold issue utilisation and pipe mix"}
+                        "arithmetic of provably uniform regions (97 % of the micro-triangles), profiles/r1c_HierLeaves_* and r1d_HierTestList_* hold issue utilisation and pipe mix"}
     # whole-path algorithmic bytes per SURVEY 8d: texture + geometry + outputs
     path_bytes = tex_bytes + wl.indices.nbytes + wl.texcoords.nbytes + array_bytes + 8 * desc_count + 4 * a.tris
 
