@@ -57,7 +57,9 @@ namespace ommb200 {
 
 constexpr float kUnitRoundoff = 5.9604645e-8f;  // 2^-24
 #if defined(OMM_HIER_STATS)
-static unsigned long long g_hierStats[16];  // host-only instrumentation of the fuzz harness
+static unsigned long long g_hierStats[16];  // host-only instrumentation (tests/hier_host, scripts/leaf_stats.py): [0] leaf cells, [1] vertex values of one
+                                            // sign, [2] closed by (D), [3] skipped by (E), [4]-[7] region-test failures, [8] cells that run the edge tests,
+                                            // [9] of those with a hit, [10] leaves, [11] leaves crossed by the level line, [12]-[14] why (D) failed
 #define OMM_STAT(i) (g_hierStats[i]++)
 #else
 #define OMM_STAT(i) ((void)0)
@@ -507,6 +509,9 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
             const float margin = fminf(fminf(fabsf(v0), fabsf(v1)), fabsf(v2)) - sag - pad;
             const float gmaxAbs = fmaxf(fmaxf(fabsf(gx), fabsf(gy)), fmaxf(fabsf(gz), fabsf(gw)));
             edgesCannotHit = MarginBeatsEdgeBound(it, margin, al, be, ga, de, gmaxAbs, fabsf(P.cutoff), qx, qy);
+#if defined(OMM_HIER_STATS)
+            if (!edgesCannotHit) g_hierStats[!(margin > 1e-5f) ? 12 : (de < 1e-6f ? 13 : 14)]++;  // near the line / d is rounding noise / other
+#endif
         }
     }
 #if defined(OMM_HIER_STATS)
@@ -549,8 +554,10 @@ OMM_HD void LeafCell(const BakeParams& P, const DevMip& m, const HierItem& it, c
     if (edgesCannotHit) return;
     // (Testing the edges whose end points straddle the level line first was measured: the per-lane order makes the calls diverge
     // and costs more than the skipped tests save.)
+    OMM_STAT(8);
     const bool hit = EdgeHyperbola(q0, q1, h0, b, c, d) || EdgeHyperbola(q1, q2, h0, b, c, d) || EdgeHyperbola(q2, q0, h0, b, c, d);
     if (hit) {
+        OMM_STAT(9);
         cov.above += 1;
         cov.below += 1;
     }
@@ -592,6 +599,8 @@ OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it
         LeafCell<Cfg>(P, m, it, st, x, y, cov, countsMatter);
         if (!countsMatter && cov.above != 0 && cov.below != 0) break;  // exact early-out, see ClassifyMicroTriangle
     }
+    OMM_STAT(10);
+    if (cov.above != 0 && cov.below != 0) OMM_STAT(11);
     return StateFromCoverage(P, cov.above, cov.below);
 }
 // Several mips (ref: bake_cpu_impl.cpp:866-908): the reference classifies against mip 0, 1, ... and stops as soon as the state is an

@@ -31,15 +31,17 @@ static void Descend(const BakeParams& P, const DevMip& m, const HierItem* his, u
     if (e == 0) {  // leaves: the reference walk with the exact skips of LeafCell (slow path for items the shortcuts do not cover)
         st->fullEvals++;
         const uint32_t index = (nodeInItem << (2 * nl)) + idx;
+#if !defined(OMM_HIER_STATS)  // the statistics build mirrors HierLeaves, which goes straight to the leaf walk
         if (hi.ok && M == 1) {
             st->tests[3]++;
-            const int s = TestRegion<Cfg>(P, m, hi, index, L);  // quick single-micro-triangle proof, as HierLeaves tries it first
+            const int s = TestRegion<Cfg>(P, m, hi, index, L);  // quick single-micro-triangle proof (not on the GPU path: measured slower there; kept here as one more exactness check of TestRegion)
             if (s != 0) {
                 st->passes[3]++;
                 states[idx] = (uint8_t)(s > 0 ? P.stateGT : P.stateLE);
                 return;
             }
         }
+#endif
         if (hi.ok) {
             const int state = M == 1 ? LeafClassify<Cfg>(P, m, hi, index) : LeafClassifyMips<Cfg>(P, [&](int k) { return his[k]; }, index);
             states[idx] = (uint8_t)state;
