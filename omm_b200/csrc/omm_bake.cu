@@ -589,7 +589,7 @@ __global__ void HierPrepare(const BakeParams P, const ItemRec* __restrict__ item
     const ItemRec it = items[w];
     // one set of constants per mip (they depend on the mip's size), laid out [item][mip]
     const int M = P.tex.mipCount;
-    for (int k = 0; k < M; ++k) hierItems[(size_t)w * M + k] = MakeHierItem(P.tex.mips[k], it.p0, it.p1, it.p2, it.level, it.degenerate != 0);
+    for (int k = 0; k < M; ++k) hierItems[(size_t)w * M + k] = MakeHierItemFor(P, P.tex.mips[k], it.p0, it.p1, it.p2, it.level, it.degenerate != 0);
 }
 
 __device__ __forceinline__ HierItem LoadHierItem(const HierItem* __restrict__ p) {

@@ -303,6 +303,39 @@ OMM_HD bool MakeItemBox(const DevMip& m, const HierItem& it, RegionBox& box) {
     box.cx0 = (int)floorf(box.lox); box.cy0 = (int)floorf(box.loy); box.cx1 = (int)floorf(box.hix); box.cy1 = (int)floorf(box.hiy);
     return true;
 }
+// (S) The SAT pass and the region proofs.  With a summed-area table (texture created with an alpha cutoff, one mip, Linear) the reference
+//     first decides every micro-triangle whose SAT rectangle is uniform (CoarseState; bake_cpu_impl.cpp:749-801) and only walks the
+//     others.  The rectangle spans the address-mapped texels of the micro-triangle's two bounding-box corners, floor(r_min) and
+//     floor(r_max) + 1.  Where the address mapping is monotone over that texel range the rectangle is exactly the set of texels the
+//     footprint cells use; it then holds the four texels of p0's cell, so a decisive SAT answer t means h has the sign of t all over
+//     that cell and agrees with any region proof (whose side is the sign of h at the region's points in it).  Where the mapping FOLDS
+//     inside the range (Mirror / MirrorOnce across a mirror axis) or wraps all the way round (Wrap across a period boundary: the two
+//     corners can map to one texel column), the rectangle is not that set, the reference's answer is whatever the rectangle holds,
+//     and only the micro-triangle-level evaluation (LeafClassify applies CoarseState first) reproduces it.  A work item is therefore
+//     left to the exact walk (ok = 0) unless its whole texel range lies on one monotone piece of the mapping:
+//       Clamp, Border  always (Clamp is monotone; Border rejects every rectangle that leaves the texture);
+//       Wrap, Mirror   within one period in x and in y (a flipped Mirror period maps decreasingly: the reference rejects ex < sx);
+//       MirrorOnce     entirely at texels >= 0 or entirely at texels <= -1 in x and in y.
+//     Found by the randomized host campaign (MirrorOnce, SAT, UVs straddling 0): the region proofs said "opaque", the reference's
+//     folded rectangle held a single transparent texel column.
+OMM_HD int FloorDivInt(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+OMM_HD bool SatPassCompatible(const BakeParams& P, const DevMip& m, const HierItem& it) {
+    if (!P.useCoarse) return true;
+    if (P.addrMode == ommTextureAddressMode_Clamp || P.addrMode == ommTextureAddressMode_Border) return true;
+    RegionBox box;
+    if (!MakeItemBox(m, it, box)) return false;
+    const int tx0 = box.cx0, tx1 = box.cx1 + 1, ty0 = box.cy0, ty1 = box.cy1 + 1;  // superset of every micro-triangle's texel range
+    if (P.addrMode == ommTextureAddressMode_MirrorOnce) return (tx0 >= 0 || tx1 <= -1) && (ty0 >= 0 || ty1 <= -1);
+    if (P.addrMode == ommTextureAddressMode_Wrap || P.addrMode == ommTextureAddressMode_Mirror)
+        return FloorDivInt(tx0, m.w) == FloorDivInt(tx1, m.w) && FloorDivInt(ty0, m.h) == FloorDivInt(ty1, m.h);
+    return false;
+}
+// The per-item constants as the kernels use them: MakeHierItem plus (S).
+OMM_HD HierItem MakeHierItemFor(const BakeParams& P, const DevMip& m, float2 p0, float2 p1, float2 p2, uint32_t level, bool degenerate) {
+    HierItem it = MakeHierItem(m, p0, p1, p2, level, degenerate);
+    if (it.ok && !SatPassCompatible(P, m, it)) it.ok = 0;
+    return it;
+}
 // Node box: the same for the sub-triangle `index` at `nodeLevel` of the item (an aligned group of initial regions of a large item).
 OMM_HD bool MakeNodeBox(const DevMip& m, const HierItem& it, uint32_t index, uint32_t nodeLevel, RegionBox& box) {
     HierItem whole = it;
@@ -570,9 +603,9 @@ OMM_HD int LeafClassify(const BakeParams& P, const DevMip& m, const HierItem& it
     const Tri st = MicroTri(it.p0, it.p1, it.p2, index, it.level);
     if (P.useCoarse) {
         // SAT pass of the reference first (bake_cpu_impl.cpp:749-801, 861-864).  The hierarchical path is only taken when the
-        // texture's cutoff equals the bake's (SelectHierKernels): a decisive SAT answer then agrees with any region proof, because
-        // the SAT rectangle holds the four texels of p0's cell and a patch whose corners are all on one side cannot have h of the
-        // other sign with margin.
+        // texture's cutoff equals the bake's (SelectHierKernels) and for work items whose texel range the address mapping does not
+        // fold (S): a decisive SAT answer then agrees with any region proof, because the SAT rectangle holds the four texels of
+        // p0's cell and a patch whose corners are all on one side cannot have h of the other sign with margin.
         const int cs = CoarseState<Cfg>(P, st);
         if (cs >= 0 && cs != ommOpacityState_UnknownOpaque) return cs;
     }

@@ -83,7 +83,7 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
         const uint32_t L = levels[it];
         const bool degenerate = TriIsDegenerate(uv[0], uv[1], uv[2]);
         std::vector<HierItem> his;
-        for (int k = 0; k < P.tex.mipCount; ++k) his.push_back(MakeHierItem(P.tex.mips[k], uv[0], uv[1], uv[2], L, degenerate));
+        for (int k = 0; k < P.tex.mipCount; ++k) his.push_back(MakeHierItemFor(P, P.tex.mips[k], uv[0], uv[1], uv[2], L, degenerate));
         const HierItem hi = his[0];
         const uint32_t nl = L < 6 ? L : 6;
         const uint32_t nodes = L > 6 ? 1u << (2 * (L - 6)) : 1u;

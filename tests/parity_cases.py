@@ -40,6 +40,17 @@ def cases():
     c["mips_linear_2state_fo"] = (lambda: W.random_mesh(43, 300, mips=3, format=A.FORMAT_2_STATE), {})
     c["sat_clamp"] = (lambda: W.random_mesh(44, 400, tex_kind="blocky", tex_alpha_cutoff=0.5, addressing_mode=A.ADDR_CLAMP, tri_texels=20, max_subdivision_level=5), {})
     c["sat_wrap_outside"] = (lambda: W.random_mesh(45, 400, tex_kind="blocky", tex_alpha_cutoff=0.5, uv_lo=-1.0, uv_hi=2.0, tri_texels=20, max_subdivision_level=5), {})
+    # SAT pass where the address mapping folds inside a micro-triangle's texel range (Mirror / MirrorOnce across a mirror axis): the SDK's
+    # SAT rectangle is then not the set of texels the micro-triangle uses, and only its own evaluation order reproduces the result
+    # (omm_hier.cuh (S); found by the host campaign, see tests/test_hier_host.py::test_sat_pass_where_the_address_mapping_folds)
+    c["sat_mirror_once_outside"] = (lambda: W.random_mesh(47, 500, tex_kind="noise", unorm8=True, tex_alpha_cutoff=0.5, uv_lo=-0.6, uv_hi=1.6, tri_texels=14,
+                                                          addressing_mode=A.ADDR_MIRROR_ONCE, max_subdivision_level=5), {})
+    c["sat_mirror_outside"] = (lambda: W.random_mesh(48, 500, tex_kind="noise", tex_alpha_cutoff=0.5, uv_lo=-1.2, uv_hi=2.2, tri_texels=14,
+                                                     addressing_mode=A.ADDR_MIRROR, max_subdivision_level=5, unknown_state_promotion=A.PROMOTE_NEAREST), {})
+    c["sat_mirror_once_axis"] = (lambda: W.random_mesh(49, 300, tex_size=(128, 128), tex_kind="noise", unorm8=True, tex_alpha_cutoff=0.5, uv_lo=-0.08, uv_hi=0.08,
+                                                       tri_texels=9, addressing_mode=A.ADDR_MIRROR_ONCE, max_subdivision_level=4, format=A.FORMAT_2_STATE), {})
+    c["sat_wrap_tiny_texture"] = (lambda: W.random_mesh(50, 200, tex_size=(8, 8), tex_kind="noise", tex_alpha_cutoff=0.5, uv_lo=-1.0, uv_hi=2.0, tri_texels=6,
+                                                        max_subdivision_level=2), {})
     c["sat_disable_zorder"] = (lambda: W.random_mesh(46, 200, tex_kind="circle", tex_alpha_cutoff=0.5, tex_flags=A.TEXFLAG_DISABLE_ZORDER), {})
     c["degenerate_and_nan"] = (lambda: W.random_mesh(51, 400, degenerate_frac=0.3, nan_frac=0.1, tri_texels=30), {})
     c["all_triangles_invalid"] = (lambda: W.random_mesh(59, 64, nan_frac=1.0, bake_flags=A.BAKE_DISABLE_SPECIAL_INDICES | A.BAKE_DISABLE_DUPLICATE_DETECTION), {})

@@ -148,6 +148,25 @@ def test_sat_pass_with_the_bake_cutoff(lib):
     check(lib, t["smooth"], tris(rng, 150, 10, 256, -0.2, 1.2), np.full(150, 6), use_sat=True, promotion=capi.PROMOTE_NEAREST)
 
 
+def test_sat_pass_where_the_address_mapping_folds(lib):
+    """(S): the SDK's SAT rectangle spans the address-mapped texels of a micro-triangle's two bounding-box corners; where the mapping
+    folds inside the range (Mirror / MirrorOnce across a mirror axis) it is not the set of texels the micro-triangle uses, and the
+    region proofs must leave such work items to the exact walk.  First the case the randomized campaign found (MirrorOnce, UVs
+    straddling u = 0: the proofs said "opaque", the folded rectangle held one transparent texel column), then every address mode
+    with triangles across the axes and period boundaries."""
+    tex = W.noise_texture(512, as_unorm8=True)
+    uv = np.array([[0.00641006, 1.0755265, -0.0430925, 1.0589049, 0.00442714, 1.0566009]], dtype=np.float32)
+    check(lib, tex, uv, np.array([4]), addr=capi.ADDR_MIRROR_ONCE, cutoff=0.5000001, promotion=capi.PROMOTE_NEAREST, fmt=capi.FORMAT_2_STATE, use_sat=True)
+    rng = np.random.default_rng(13)
+    t = textures(rng)
+    for addr in (capi.ADDR_WRAP, capi.ADDR_MIRROR, capi.ADDR_CLAMP, capi.ADDR_BORDER, capi.ADDR_MIRROR_ONCE):
+        for lo, hi in ((-0.06, 0.06), (0.94, 1.06), (-1.05, -0.95), (1.95, 2.05)):
+            check(lib, t["noise8"], tris(rng, 60, 10, 512, lo, hi), rng.integers(2, 6, 60), addr=addr, use_sat=True, border=0.3)
+            check(lib, t["npot"], tris(rng, 60, 7, 200, lo, hi), rng.integers(2, 6, 60), addr=addr, use_sat=True, promotion=capi.PROMOTE_NEAREST)
+    small = W.noise_texture(256)[:8, :8].copy()
+    check(lib, small, tris(rng, 150, 6, 8, -1.0, 2.0), rng.integers(0, 3, 150), addr=capi.ADDR_WRAP, use_sat=True)   # micro-triangles wider than the texture
+
+
 def test_mip_chains(lib):
     """Several mips: a region must pass on every mip with the same side; leaves walk the mips like the reference (stop at Unknown)."""
     rng = np.random.default_rng(12)
