@@ -22,6 +22,12 @@ struct HierCheckStats {
     int32_t firstBadGot, firstBadWant;
 };
 
+// optional sink for the plain reference walk's states, one byte per micro-triangle in item / bird-curve order
+// (tests/test_hier_host.py::test_plain_walk_equals_the_sdk_build compares them with the SDK build's blocks)
+static uint8_t* g_wantSink = nullptr;
+static uint64_t g_wantPos = 0;
+extern "C" __attribute__((visibility("default"))) void hier_host_set_state_sink(uint8_t* sink) { g_wantSink = sink; g_wantPos = 0; }
+
 template <class Cfg>
 static void Descend(const BakeParams& P, const DevMip& m, const HierItem* his, uint32_t nodeInItem, uint32_t nl, uint32_t e, uint32_t idx, uint8_t* states,
                     HierCheckStats* st, const float2* uv, bool degenerate, const ItemCellMap* map = nullptr) {
@@ -102,6 +108,7 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
                     const uint32_t n = 1u << (2 * nl);
                     for (uint32_t i = 0; i < n; ++i) {
                         const int want = ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, (node << (2 * nl)) + i, L);
+                        if (g_wantSink) g_wantSink[g_wantPos++] = (uint8_t)want;
                         st->microTriangles++;
                         if (want != (sPiece > 0 ? P.stateGT : P.stateLE)) {
                             if (st->mismatches == 0) { st->firstBadItem = it; st->firstBadIndex = (node << (2 * nl)) + i; st->firstBadGot = sPiece; st->firstBadWant = want; }
@@ -131,6 +138,7 @@ static void CheckItems(const BakeParams& P, const float* uvs, const uint8_t* lev
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t index = (node << (2 * nl)) + i;
                 const int want = ClassifyMicroTriangle<Cfg>(P, uv[0], uv[1], uv[2], degenerate, index, L);
+                if (g_wantSink) g_wantSink[g_wantPos++] = (uint8_t)want;
                 st->microTriangles++;
                 if (want != (int)states[i]) {
                     if (st->mismatches == 0) {

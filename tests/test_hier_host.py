@@ -175,3 +175,63 @@ def test_mip_chains(lib):
     check(lib, t["smooth"], tris(rng, 150, 12, 256), np.full(150, 6), mips=3, promotion=capi.PROMOTE_NEAREST)
     check(lib, t["noise8"], tris(rng, 150, 10, 512), rng.integers(0, 6, 150), mips=5, addr=capi.ADDR_MIRROR, le=capi.STATE_UO, gt=capi.STATE_T)
     check(lib, t["npot"], tris(rng, 120, 9, 200, -0.5, 1.5), np.full(120, 5), mips=3, addr=capi.ADDR_CLAMP)
+
+
+def _sdk_states(ref_lib, tex, uv, lv, addr, cutoff, promotion, fmt, gt, le, border, use_sat):
+    """Per-triangle micro-triangle states of the SDK build for the same inputs (every triangle keeps its own block)."""
+    from omm_b200 import Baker
+    n = len(lv)
+    wl = W.Workload(name="plain-walk pin", mips=[np.ascontiguousarray(tex)], indices=np.arange(3 * n, dtype=np.uint32),
+                    texcoords=np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2), tex_alpha_cutoff=cutoff if use_sat else -1.0,
+                    subdivision_levels=np.ascontiguousarray(lv, dtype=np.uint8),
+                    desc=dict(addressing_mode=addr, filter=capi.FILTER_LINEAR, border_alpha=border, alpha_cutoff=cutoff, alpha_cutoff_gt=gt, alpha_cutoff_le=le,
+                              format=fmt, unknown_state_promotion=promotion, max_subdivision_level=12, dynamic_subdivision_scale=0.0,
+                              bake_flags=capi.BAKE_DISABLE_SPECIAL_INDICES | capi.BAKE_DISABLE_DUPLICATE_DETECTION))
+    with Baker(ref_lib) as b:
+        inp, t = W.make_input(b, wl)
+        res = b.bake(inp)
+        t.destroy()
+    out = []
+    for tri in range(n):
+        d = res.desc_array[int(res.index_buffer[tri])]
+        level, off = int(d["subdivisionLevel"]), int(d["offset"])
+        m = 1 << (2 * level)
+        i = np.arange(m)
+        if fmt == capi.FORMAT_4_STATE:
+            out.append((res.array_data[off + (i >> 2)] >> ((i & 3) * 2)) & 3)
+        else:
+            out.append((res.array_data[off + (i >> 3)] >> (i & 7)) & 1)
+    return np.concatenate(out).astype(np.uint8)
+
+
+def test_plain_walk_equals_the_sdk_build(lib):
+    """Closes the loop on the CPU: the reference walk of omm_device_math.cuh (host build; the very code the flat kernels and the leaves run,
+    and the yardstick of every test above) against the SDK build, micro-triangle by micro-triangle, on random configurations.  On the GPU
+    box the same link is the byte-level parity suite."""
+    ref_path = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libomm-lib.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    ref = capi.OmmLib(ref_path)
+    rng = np.random.default_rng(77)
+    t = textures(rng)
+    lib.hier_host_set_state_sink.argtypes = [ctypes.c_void_p]
+    for k in range(40):
+        tex = t[["noise", "noise8", "smooth", "ramp", "checker", "npot", "nearcut"][k % 7]]
+        n = 40
+        lv = rng.integers(0, 6, n)
+        addr = int(rng.choice([capi.ADDR_WRAP, capi.ADDR_MIRROR, capi.ADDR_CLAMP, capi.ADDR_MIRROR_ONCE]))  # Border: the SDK reads out of bounds
+        lo = float(rng.choice([0.0, -0.5, -1.2]))
+        uv = tris(rng, n, float(rng.choice([3, 8, 25])), max(tex.shape), lo, lo + float(rng.choice([1.0, 2.0])), axis_aligned=bool(k % 3 == 1), skinny=bool(k % 5 == 2))
+        fmt = int(rng.choice([capi.FORMAT_4_STATE, capi.FORMAT_2_STATE]))
+        promo = int(rng.integers(3))
+        cutoff = float(rng.choice([0.5, 0.3, 0.5000001]))
+        use_sat = bool(rng.random() < 0.4)
+        sink = np.zeros(int((4 ** lv).sum()), dtype=np.uint8)
+        lib.hier_host_set_state_sink(sink.ctypes.data_as(ctypes.c_void_p))
+        try:
+            check(lib, tex, uv, lv, addr=addr, cutoff=cutoff, promotion=promo, fmt=fmt, use_sat=use_sat)
+        finally:
+            lib.hier_host_set_state_sink(None)
+        want = _sdk_states(ref, tex, uv, lv, addr, cutoff, promo, fmt, capi.STATE_O, capi.STATE_T, 0.0, use_sat)
+        bad = np.nonzero(sink != want)[0]
+        assert bad.size == 0, f"run {k}: {bad.size} of {want.size} micro-triangles differ from the SDK build (first at {bad[:5]}, got {sink[bad[:5]]}, SDK {want[bad[:5]]})"
