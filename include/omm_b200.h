@@ -392,6 +392,11 @@ OMM_API ommResult ommB200SetDevice(int cudaDevice);
 /* Number of CUDA devices visible; 0 means the library cannot run (there is no CPU fallback). */
 OMM_API int ommB200GetDeviceCount(void);
 
+/* Big result arrays are downloaded into page-locked host blocks that the library recycles across bakes (default allocator only).
+ * At most OMM_B200_PINNED_CACHE_MB (environment, default 4096) stay cached; everything cached is freed when the last baker is destroyed.
+ * ommB200TrimHostPool frees cached blocks until at most keepBytes remain and returns the bytes still cached. */
+OMM_API size_t ommB200TrimHostPool(size_t keepBytes);
+
 /* Timings of the most recent successful ommCpuBake / ommB200BakeResident on this baker. */
 OMM_API ommResult ommB200GetLastBakeTimings(ommBaker baker, ommB200BakeTimings* out);
 

@@ -233,6 +233,7 @@ B200_SYMBOLS = [
     "ommDebugGetStats", "ommB200SetDevice", "ommB200GetDeviceCount", "ommB200GetLastBakeTimings", "ommB200StageInputs",
     "ommB200DestroyStagedInputs", "ommB200BakeResident", "ommB200GetDeviceResultDesc", "ommB200DownloadResult",
     "ommB200InitSharding", "ommB200GetNcclUniqueId", "ommB200ComputeShardBounds", "ommB200ShardsPerRank", "ommB200ShardOwner",
+    "ommB200TrimHostPool",
 ]
 
 
@@ -317,6 +318,8 @@ class OmmLib:
             d.ommB200ShardsPerRank.argtypes = [C.c_int]
             d.ommB200ShardOwner.restype = C.c_int
             d.ommB200ShardOwner.argtypes = [C.c_int, C.c_int]
+            d.ommB200TrimHostPool.restype = C.c_size_t
+            d.ommB200TrimHostPool.argtypes = [C.c_size_t]
 
     def exported(self, name: str) -> bool:
         return hasattr(self.dll, name)

@@ -17,21 +17,31 @@ using namespace ommb200;
 namespace ommb200 {
 
 // ---- default allocator: aligned malloc with the original pointer stored in front (ref: std_allocator.h:45-94) ----
+// Two words sit in front of every block: the malloc pointer and the requested size (the latter makes reallocate a real one).
 static void* DefaultAllocate(void*, size_t size, size_t alignment) {
     if (alignment < sizeof(void*)) alignment = sizeof(void*);
-    uint8_t* raw = (uint8_t*)std::malloc(size + sizeof(void*) + alignment - 1);
+    const size_t header = 2 * sizeof(void*);
+    uint8_t* raw = (uint8_t*)std::malloc(size + header + alignment - 1);
     if (!raw) return nullptr;
-    uint8_t* aligned = (uint8_t*)(((uintptr_t)(raw + sizeof(void*)) + alignment - 1) & ~(uintptr_t)(alignment - 1));
+    uint8_t* aligned = (uint8_t*)(((uintptr_t)(raw + header) + alignment - 1) & ~(uintptr_t)(alignment - 1));
     ((void**)aligned)[-1] = raw;
+    ((size_t*)aligned)[-2] = size;
     return aligned;
 }
 static void DefaultFree(void*, void* memory) {
     if (memory) std::free(((void**)memory)[-1]);
 }
-static void* DefaultReallocate(void* user, void* memory, size_t size, size_t alignment) {
-    // only used by callers that hand the interface on; this library never reallocates
+static void* DefaultReallocate(void* user, void* memory, size_t size, size_t alignment) {  // ref: std_allocator.h:96-117 (realloc semantics)
+    if (!memory) return DefaultAllocate(user, size, alignment);
+    if (size == 0) {
+        DefaultFree(user, memory);
+        return nullptr;
+    }
     void* fresh = DefaultAllocate(user, size, alignment);
-    (void)memory;
+    if (!fresh) return nullptr;  // the old block stays valid, like realloc
+    const size_t old = ((size_t*)memory)[-2];
+    memcpy(fresh, memory, old < size ? old : size);
+    DefaultFree(user, memory);
     return fresh;
 }
 void SetDefaultAllocatorIfUnset(ommMemoryAllocatorInterface& iface) {
@@ -171,13 +181,16 @@ OMM_API ommResult ommDestroyBaker(ommBaker baker) {  // ref: bake.cpp:457-479
     if (baker == 0) return ommResult_INVALID_ARGUMENT;
     if (HandleTagOf(baker) != HandleTag::CpuBaker) return ommResult_FAILURE;
     BakerObject* b = HandlePtr<BakerObject>(baker);
+    bool lastBaker = false;
     {
         std::lock_guard<std::mutex> live(g_liveBakersMu);
         g_liveBakers.erase(std::remove(g_liveBakers.begin(), g_liveBakers.end(), b), g_liveBakers.end());
+        lastBaker = g_liveBakers.empty();
     }
     DestroySharding(b);
     const HostAllocator alloc = b->alloc;
     FreeObject(alloc, b);
+    if (lastBaker) PinnedPoolTrim(0);  // page-locked memory is a system resource: nothing stays cached once the last baker is gone
     return ommResult_SUCCESS;
 }
 
@@ -352,6 +365,9 @@ static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, Bak
         return ommResult_FAILURE;
     const ommResult v = ValidateBakeDesc(b->log, *d);
     if (v != ommResult_SUCCESS) return v;
+    // The SDK only asserts on the format (bake_cpu_impl.cpp:328-333, 365: compiled out in its release build, then it indexes its
+    // histograms with format - 1); here anything but the two OC1 formats is refused before any work is done.
+    if (d->format != ommFormat_OC1_2_State && d->format != ommFormat_OC1_4_State) return b->log.InvalidArg("[Invalid Argument] - format is not set");
     const uint32_t flags = (uint32_t)d->bakeFlags;
     if ((flags & (1u << 7)) && !(flags & (1u << 8)))  // ref: bake_cpu_impl.cpp:718-719
         return b->log.InvalidArg("[Invalid Arg] - EnableAABBTesting can't be used without also setting DisableLevelLineIntersection");
@@ -484,6 +500,7 @@ OMM_API ommResult ommB200SetDevice(int cudaDevice) {
     return ommResult_SUCCESS;
 }
 OMM_API int ommB200GetDeviceCount(void) { return DeviceCount(); }
+OMM_API size_t ommB200TrimHostPool(size_t keepBytes) { return PinnedPoolTrim(keepBytes); }
 
 OMM_API ommResult ommB200GetLastBakeTimings(ommBaker baker, ommB200BakeTimings* out) {
     if (baker == 0 || out == nullptr || HandleTagOf(baker) != HandleTag::CpuBaker) return ommResult_INVALID_ARGUMENT;

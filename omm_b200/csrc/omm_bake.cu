@@ -1548,11 +1548,24 @@ struct PinnedBlock {
 static std::mutex g_pinnedMu;
 static std::vector<PinnedBlock> g_pinned;
 static size_t g_pinnedTotal = 0;
+// cached (not in use) bytes above which a released block is freed at once: OMM_B200_PINNED_CACHE_MB, default 4 GiB (one arrayData of
+// the largest legal size); the pool is emptied when the last baker goes away (ommDestroyBaker) or on request (ommB200TrimHostPool)
+static size_t PinnedCacheLimit() {
+    static const size_t limit = [] {
+        const char* e = getenv("OMM_B200_PINNED_CACHE_MB");
+        const unsigned long long mb = e ? strtoull(e, nullptr, 10) : 4096ull;
+        return (size_t)mb << 20;
+    }();
+    return limit;
+}
 void* PinnedPoolAcquire(size_t bytes) {
     std::lock_guard<std::mutex> g(g_pinnedMu);
+    // best fit, but never a block more than twice the request (a 1 MiB result must not pin down a multi-GB block)
     int best = -1;
     for (int i = 0; i < (int)g_pinned.size(); ++i)
-        if (!g_pinned[i].inUse && g_pinned[i].bytes >= bytes && (best < 0 || g_pinned[i].bytes < g_pinned[best].bytes)) best = i;
+        if (!g_pinned[i].inUse && g_pinned[i].bytes >= bytes && g_pinned[i].bytes <= 2 * bytes + ((size_t)4 << 20) &&
+            (best < 0 || g_pinned[i].bytes < g_pinned[best].bytes))
+            best = i;
     if (best >= 0) {
         g_pinned[best].inUse = true;
         return g_pinned[best].ptr;
@@ -1567,19 +1580,41 @@ void* PinnedPoolAcquire(size_t bytes) {
     g_pinnedTotal += rounded;
     return p;
 }
+static size_t PinnedCachedLocked() {
+    size_t cached = 0;
+    for (const PinnedBlock& b : g_pinned)
+        if (!b.inUse) cached += b.bytes;
+    return cached;
+}
+static size_t PinnedTrimLocked(size_t keepBytes) {
+    size_t cached = PinnedCachedLocked();
+    // largest blocks go first
+    while (cached > keepBytes) {
+        int victim = -1;
+        for (int i = 0; i < (int)g_pinned.size(); ++i)
+            if (!g_pinned[i].inUse && (victim < 0 || g_pinned[i].bytes > g_pinned[victim].bytes)) victim = i;
+        if (victim < 0) break;
+        cudaFreeHost(g_pinned[victim].ptr);
+        cached -= g_pinned[victim].bytes;
+        g_pinnedTotal -= g_pinned[victim].bytes;
+        g_pinned.erase(g_pinned.begin() + victim);
+    }
+    cudaGetLastError();
+    return cached;
+}
 void PinnedPoolRelease(void* p) {
     if (!p) return;
     std::lock_guard<std::mutex> g(g_pinnedMu);
     for (size_t i = 0; i < g_pinned.size(); ++i)
         if (g_pinned[i].ptr == p) {
             g_pinned[i].inUse = false;
-            if (g_pinnedTotal > ((size_t)12 << 30)) {  // keep at most 12 GiB cached
-                cudaFreeHost(p);
-                g_pinnedTotal -= g_pinned[i].bytes;
-                g_pinned.erase(g_pinned.begin() + i);
-            }
+            PinnedTrimLocked(PinnedCacheLimit());
             return;
         }
+}
+size_t PinnedPoolTrim(size_t keepBytes) {
+    std::lock_guard<std::mutex> g(g_pinnedMu);
+    return PinnedTrimLocked(keepBytes);
 }
 
 // Host memory of arrayData: the library's page-locked pool under the default allocator (full PCIe speed), the user's allocator otherwise.
@@ -1636,24 +1671,28 @@ cleanup:
     if (rc != ommResult_SUCCESS) DestroyTextureDevice(tex);
     return rc;
 }
+static void FreeCellTables(CellTables* t) {
+    if (t->flatSat) cudaFree(t->flatSat);
+    if (t->strongPlus) cudaFree(t->strongPlus);
+    if (t->strongMinus) cudaFree(t->strongMinus);
+    delete t;
+}
 void DestroyTextureDevice(TextureObject* tex) {
-    if (tex->devTexels || tex->devSat || tex->devFlatSat) cudaSetDevice(tex->device);
+    if (tex->devTexels || tex->devSat || !tex->cellTables.empty()) cudaSetDevice(tex->device);
     if (tex->devTexels) cudaFree(tex->devTexels);
     if (tex->devSat) cudaFree(tex->devSat);
-    if (tex->devFlatSat) cudaFreeAsync(tex->devFlatSat, 0);
-    if (tex->devStrongPlus) cudaFreeAsync(tex->devStrongPlus, 0);
-    if (tex->devStrongMinus) cudaFreeAsync(tex->devStrongMinus, 0);
-    tex->devStrongPlus = tex->devStrongMinus = nullptr;
+    for (CellTables* t : tex->cellTables) FreeCellTables(t);
+    tex->cellTables.clear();
     tex->devTexels = nullptr;
     tex->devSat = nullptr;
-    tex->devFlatSat = nullptr;
-    tex->flatValid = false;
 }
 
-// (H) The constant-cell table of mip 0 for `cutoff`: built on the first bake that needs it and kept with the texture (a texture is
-// normally baked with one cutoff; another cutoff rebuilds it).  Returns nullptr when the texture is too small or memory is short --
-// the classifier then simply has no O(1) answer for large footprints.  The build is ordered before the caller's later work on
-// `stream` by running on that stream; concurrent bakes serialise on the texture's mutex.
+// (H) The constant-cell table of mip 0 for the bake's cutoff.  A texture keeps one immutable set of tables per cutoff it has been baked
+// with: the SDK treats textures as read-only objects shared by concurrent bakes (docs/integration_guide.md:434), so a published set is
+// never rewritten -- a bake with another cutoff builds another set.  Sets are reference-counted by the bakes using them; idle sets
+// beyond kIdleCellTables are freed, least recently used first (a texture is normally baked with one cutoff).  The build runs on the
+// bake's stream and is complete before the set is published, so bakes on other streams may use it at once.  Returns nullptr when the
+// texture is too small or memory is short -- the classifier then simply has no O(1) answer for large footprints.
 // (I) is OFF by default: measured on B200 at config 3, answering region tests from the two 64 MB tables (four to eight scattered
 // 4-byte loads each) is 7 % SLOWER than the per-item bitmap, whose texel gathers are coalesced and shared (13.0 vs 12.2 ms).  The
 // code stays for textures / workloads where it may pay; OMM_B200_STRONG_TABLES=1 enables it.
@@ -1661,47 +1700,66 @@ static bool UseStrongTables() {
     static const bool on = getenv("OMM_B200_STRONG_TABLES") != nullptr;
     return on;
 }
-static bool GetCellTables(TextureObject* tex, BakeParams& P, cudaStream_t stream, uint32_t* launches) {
+constexpr int kIdleCellTables = 2;
+static CellTables* AcquireCellTables(TextureObject* tex, BakeParams& P, cudaStream_t stream, uint32_t* launches) {
     const DevMip& m = tex->dev.mips[0];
     P.tex.flatSat = P.tex.strongPlus = P.tex.strongMinus = nullptr;
-    if (m.w < 2 || m.h < 2) return false;
+    if (m.w < 2 || m.h < 2) return nullptr;
     const float cutoff = P.cutoff;
+    const int numTables = UseStrongTables() ? 3 : 1;
     std::lock_guard<std::mutex> g(tex->flatMu);
-    if (!(tex->flatValid && tex->flatCutoff == cutoff)) {
-        if (tex->flatValid) {
-            // another bake may still be reading the tables of the previous cutoff
-            cudaDeviceSynchronize();
-            tex->flatValid = false;
+    CellTables* set = nullptr;
+    for (CellTables* t : tex->cellTables)
+        if (FloatAsUint(t->cutoff) == FloatAsUint(cutoff)) set = t;
+    if (!set) {
+        // evict idle sets first (nobody reads them: refs == 0 means every bake that used them has drained its stream)
+        while (true) {
+            int idle = 0, victim = -1;
+            for (int i = 0; i < (int)tex->cellTables.size(); ++i)
+                if (tex->cellTables[i]->refs == 0) {
+                    ++idle;
+                    if (victim < 0 || tex->cellTables[i]->lastUse < tex->cellTables[victim]->lastUse) victim = i;
+                }
+            if (idle < kIdleCellTables) break;
+            FreeCellTables(tex->cellTables[victim]);
+            tex->cellTables.erase(tex->cellTables.begin() + victim);
         }
+        set = new (std::nothrow) CellTables();
+        if (!set) return nullptr;
+        set->cutoff = cutoff;
         const size_t bytes = sizeof(uint32_t) * (size_t)(m.w - 1) * (size_t)(m.h - 1);
-        uint32_t** bufs[3] = {&tex->devFlatSat, &tex->devStrongPlus, &tex->devStrongMinus};
-        const int numTables = UseStrongTables() ? 3 : 1;
-        for (int i = 0; i < numTables; ++i)
-            if (!*bufs[i] && cudaMallocAsync((void**)bufs[i], bytes, stream) != cudaSuccess) {
-                cudaGetLastError();
-                *bufs[i] = nullptr;
-                return false;
+        uint32_t** bufs[3] = {&set->flatSat, &set->strongPlus, &set->strongMinus};
+        bool ok = true;
+        for (int i = 0; i < numTables && ok; ++i) ok = cudaMalloc((void**)bufs[i], bytes) == cudaSuccess;
+        if (ok) {
+            FlatSatRows<<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(tex->devTexels, tex->dev.isFp32, m.w, m.h, cutoff, set->flatSat);
+            if (numTables == 3) {
+                if (tex->dev.isFp32) StrongSatRows<true><<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(P, set->strongPlus, set->strongMinus);
+                else StrongSatRows<false><<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(P, set->strongPlus, set->strongMinus);
             }
-        FlatSatRows<<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(tex->devTexels, tex->dev.isFp32, m.w, m.h, cutoff, tex->devFlatSat);
-        if (numTables == 3) {
-            if (tex->dev.isFp32) StrongSatRows<true><<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(P, tex->devStrongPlus, tex->devStrongMinus);
-            else StrongSatRows<false><<<(m.h - 1 + 7) / 8, 256, 0, stream>>>(P, tex->devStrongPlus, tex->devStrongMinus);
+            for (int i = 0; i < numTables && ok; ++i) ok = SatColumnPass(m.w - 1, m.h - 1, *bufs[i], stream) == cudaSuccess;
+            *launches += numTables == 3 ? 11 : 4;
+            // bakes on other streams may pick the set up as soon as it is in the list
+            ok = ok && cudaStreamSynchronize(stream) == cudaSuccess;
         }
-        for (int i = 0; i < numTables; ++i)
-            if (SatColumnPass(m.w - 1, m.h - 1, *bufs[i], stream) != cudaSuccess) {
-                cudaGetLastError();
-                return false;
-            }
-        *launches += numTables == 3 ? 11 : 4;
-        // later bakes may run on other streams: make the tables visible to them before they are published
-        cudaStreamSynchronize(stream);
-        tex->flatCutoff = cutoff;
-        tex->flatValid = true;
+        if (!ok) {
+            cudaGetLastError();
+            FreeCellTables(set);
+            return nullptr;
+        }
+        tex->cellTables.push_back(set);
     }
-    P.tex.flatSat = tex->devFlatSat;
-    P.tex.strongPlus = UseStrongTables() ? tex->devStrongPlus : nullptr;
-    P.tex.strongMinus = UseStrongTables() ? tex->devStrongMinus : nullptr;
-    return true;
+    set->refs++;
+    set->lastUse = ++tex->cellTableClock;
+    P.tex.flatSat = set->flatSat;
+    P.tex.strongPlus = UseStrongTables() ? set->strongPlus : nullptr;
+    P.tex.strongMinus = UseStrongTables() ? set->strongMinus : nullptr;
+    return set;
+}
+static void ReleaseCellTables(TextureObject* tex, CellTables* set) {
+    if (!set) return;
+    std::lock_guard<std::mutex> g(tex->flatMu);
+    set->refs--;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1765,6 +1823,16 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
             out->h2dBytes += out->triangleCount;
         }
         if (desc.formats) {
+            // The SDK sizes its arrays from desc.format alone and then serializes every item (bake_cpu_impl.cpp:1763-1771): a per-triangle
+            // format that differs from it overruns there.  Refused here, before any device work.
+            for (uint32_t t = 0; t < out->triangleCount; ++t) {
+                const int32_t f = (int32_t)desc.formats[t];
+                if (f != (int32_t)ommFormat_INVALID && f != (int32_t)desc.format) {
+                    log.Log(ommMessageSeverity_Fatal, "[omm-b200] per-triangle formats that differ from desc.format are not supported");
+                    rc = ommResult_FAILURE;
+                    goto cleanup;
+                }
+            }
             CUDA_TRY(cudaMallocAsync((void**)&out->devFormats, (size_t)(out->triangleCount ? out->triangleCount : 1) * 4, 0));
             CUDA_TRY(cudaMemcpyAsync(out->devFormats, desc.formats, (size_t)out->triangleCount * 4, cudaMemcpyHostToDevice, 0));
             out->h2dBytes += (uint64_t)out->triangleCount * 4;
@@ -2022,7 +2090,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     ommResult rc = RequireDevice(log, baker->device);
     if (rc != ommResult_SUCCESS) return rc;
     const ommCpuBakeInputDesc& d = in.desc;
-    const TextureObject* tex = HandlePtr<TextureObject>(d.texture);
+    // the texture's texels are read-only here; only its cache of cell tables (internally locked) is touched through this pointer
+    TextureObject* tex = HandlePtr<TextureObject>(d.texture);
+    CellTables* cellTables = nullptr;  // released after the final stream synchronisation
     const uint32_t flags = (uint32_t)d.bakeFlags;
     const uint32_t T = in.triangleCount;
     const int disableDup = (flags & ommCpuBakeFlags_DisableDuplicateDetection) != 0;
@@ -2273,7 +2343,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
         if (myItems > 0 && useHier) {
-            if (P.tex.mipCount == 1) GetCellTables(const_cast<TextureObject*>(tex), P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
+            if (P.tex.mipCount == 1) cellTables = AcquireCellTables(tex, P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
             // worst case of a chunk: the nominal number of initial regions plus the rest of its last item (at most 4^9 regions at level 12)
             unsigned long long cap = 0;
             for (int k = 0; k < owned.count; ++k) {
@@ -2673,6 +2743,10 @@ cleanup:
     scratch.freeAll();
     for (int i = 0; i < 6; ++i)
         if (ev[i]) cudaEventDestroy(ev[i]);
+    if (cellTables) {
+        if (rc != ommResult_SUCCESS) cudaStreamSynchronize(stream);  // kernels of a failed bake may still be reading the tables
+        ReleaseCellTables(tex, cellTables);
+    }
     if (ownStream) {
         cudaStreamSynchronize(stream);
         cudaStreamDestroy(stream);

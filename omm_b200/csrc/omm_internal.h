@@ -109,6 +109,15 @@ struct DevTexture {
     DevMip mips[kMaxMips];
 };
 
+struct CellTables {
+    float cutoff = 0.f;
+    uint32_t* flatSat = nullptr;
+    uint32_t* strongPlus = nullptr;
+    uint32_t* strongMinus = nullptr;
+    int refs = 0;          // bakes between AcquireCellTables and ReleaseCellTables
+    uint64_t lastUse = 0;  // TextureObject::cellTableClock at the last acquire (eviction order of idle sets)
+};
+
 struct TextureObject {
     HostAllocator alloc;
     ommCpuTextureFormat format = ommCpuTextureFormat_MAX_NUM;
@@ -120,13 +129,11 @@ struct TextureObject {
     size_t hostBytes = 0;
     void* devTexels = nullptr;
     uint32_t* devSat = nullptr;
-    // constant-cell table of the hierarchical classifier, built on first use for a given alpha cutoff and kept with the texture
+    // constant-cell tables of the hierarchical classifier: one immutable set per alpha cutoff the texture has been baked with, built on
+    // first use, shared by concurrent bakes (reference-counted) and never rewritten once published (see AcquireCellTables, omm_bake.cu)
     std::mutex flatMu;
-    uint32_t* devFlatSat = nullptr;
-    uint32_t* devStrongPlus = nullptr;
-    uint32_t* devStrongMinus = nullptr;
-    float flatCutoff = 0.f;
-    bool flatValid = false;
+    std::vector<struct CellTables*> cellTables;
+    uint64_t cellTableClock = 0;
     bool hasSerializedSat = false;  // deserialized textures: the blob carried a summed-area table (ref: texture_impl.h:105-108)
     DevTexture dev{};
     bool HasAlphaCutoff() const { return alphaCutoff >= 0.f; }
@@ -233,5 +240,7 @@ int CurrentDeviceOr(int fallback);
 // Page-locked host blocks recycled across bakes (used for big result arrays when the caller left the allocator to us).
 void* PinnedPoolAcquire(size_t bytes);
 void PinnedPoolRelease(void* p);
+// Frees cached (not in use) blocks until at most keepBytes stay cached; returns the bytes still cached.
+size_t PinnedPoolTrim(size_t keepBytes);
 
 }  // namespace ommb200

@@ -210,14 +210,19 @@ bool ReadTexture(Reader& r, int version, const HostAllocator& alloc, TextureObje
     (void)satData;  // the summed-area table is rebuilt on the device from the texels
     t->mipCount = (uint32_t)numMips;
     t->dev.mipCount = numMips;
+    // every mip must lie inside the texel payload the blob really carries -- checked BEFORE anything is sized from the header fields
+    // (a forged header could otherwise ask for 17 x 16 GiB)
+    for (int i = 0; i < numMips; ++i) {
+        const DevMip& m = t->dev.mips[i];
+        const uint64_t need = tiling == 0 ? (uint64_t)m.w * m.h : (uint64_t)Morton((uint32_t)m.w - 1, (uint32_t)m.h - 1) + 1;
+        if (lay[i].dataOffset > dataSize || need * spp > dataSize - lay[i].dataOffset) return false;
+    }
     t->hostBytes = totalTexels * spp;
     t->hostTexels = alloc.alloc(t->hostBytes, 64);
     if (!t->hostTexels) return false;
     for (int i = 0; i < numMips; ++i) {
         const DevMip& m = t->dev.mips[i];
         uint8_t* dst = (uint8_t*)t->hostTexels + m.texelOffset * spp;
-        const uint64_t need = tiling == 0 ? (uint64_t)m.w * m.h : (uint64_t)Morton((uint32_t)m.w - 1, (uint32_t)m.h - 1) + 1;
-        if (lay[i].dataOffset > dataSize || need * spp > dataSize - lay[i].dataOffset) return false;
         const uint8_t* src = data + lay[i].dataOffset;
         if (tiling == 0) memcpy(dst, src, spp * (size_t)m.w * m.h);
         else
@@ -425,7 +430,19 @@ static ommCpuBakeInputDesc DefaultInputDesc() {  // ref: omm.h:462-490
     return v;
 }
 
+static ommResult DeserializeChecked(BakerObject* b, const ommCpuBlobDesc& blob, DeserializedResultObject*& r, DeserializedResultObject** out);
+// The header digest is an integrity check, not an authentication: the contents are validated field by field, and an allocation
+// failure while following them (std::bad_alloc from the containers) ends as FAILURE instead of crossing the C ABI.
 ommResult DeserializeImpl(BakerObject* b, const ommCpuBlobDesc& blob, DeserializedResultObject** out) {
+    DeserializedResultObject* r = nullptr;
+    try {
+        return DeserializeChecked(b, blob, r, out);
+    } catch (...) {
+        if (r) DestroyDeserialized(r);
+        return ommResult_FAILURE;
+    }
+}
+static ommResult DeserializeChecked(BakerObject* b, const ommCpuBlobDesc& blob, DeserializedResultObject*& r, DeserializedResultObject** out) {
     const Logger& log = b->log;
     if (blob.data == nullptr) return log.InvalidArg("data must be non-null");
     if (blob.size == 0) return log.InvalidArg("size must be non-zero");
@@ -453,11 +470,13 @@ ommResult DeserializeImpl(BakerObject* b, const ommCpuBlobDesc& blob, Deserializ
     Reader rd{hdr.p, bytes + blob.size};
     if (decompressedSize != 0) {
         if (decompressedSize < 0) return ommResult_FAILURE;
+        // an LZ4 block cannot expand by more than 255x (one length byte per 255 output bytes)
+        if ((uint64_t)decompressedSize > 255ull * (uint64_t)(bytes + blob.size - hdr.p) + 64ull) return ommResult_FAILURE;
         inflated.resize((size_t)decompressedSize);
         if (!Lz4Decode(hdr.p, (size_t)(bytes + blob.size - hdr.p), inflated.data(), inflated.size())) return ommResult_FAILURE;
         rd = Reader{inflated.data(), inflated.data() + inflated.size()};
     }
-    DeserializedResultObject* r = AllocObject<DeserializedResultObject>(b->alloc);
+    r = AllocObject<DeserializedResultObject>(b->alloc);
     if (!r) return ommResult_FAILURE;
     r->alloc = b->alloc;
     r->log = b->log;
@@ -501,6 +520,25 @@ ommResult DeserializeImpl(BakerObject* b, const ommCpuBlobDesc& blob, Deserializ
         d.subdivisionLevels = (const uint8_t*)ReadOwned(rd, r, (size_t)numLevels);
         d.maxWorkloadSize = rd.get<uint64_t>();
         if (!rd.ok) { rc = ommResult_FAILURE; break; }
+        // A bake of this desc reads texCoords[index], formats[t] and subdivisionLevels[t] for every triangle: the arrays the blob
+        // carries must cover what its own index buffer references.
+        {
+            const uint32_t isz = IndexSize(d.indexFormat);
+            if ((uint32_t)d.indexFormat >= (uint32_t)ommIndexFormat_MAX_NUM || (uint32_t)d.texCoordFormat >= (uint32_t)ommTexCoordFormat_MAX_NUM) { rc = ommResult_FAILURE; break; }
+            uint64_t maxIndex = 0;
+            const uint8_t* ib = (const uint8_t*)d.indexBuffer;
+            for (uint32_t k = 0; k < d.indexCount; ++k) {
+                uint32_t v = 0;
+                memcpy(&v, ib + (size_t)k * isz, isz);
+                maxIndex = v > maxIndex ? v : maxIndex;
+            }
+            const uint64_t uvSize = d.texCoordFormat == ommTexCoordFormat_UV32_FLOAT ? 8 : 4;
+            const uint64_t stride = d.texCoordStrideInBytes ? d.texCoordStrideInBytes : uvSize;
+            const uint64_t tris = d.indexCount / 3;
+            if (d.indexCount && texCoordBytes < maxIndex * stride + uvSize) { rc = ommResult_FAILURE; break; }
+            if (numFormats && numFormats < tris) { rc = ommResult_FAILURE; break; }
+            if (numLevels && numLevels < tris) { rc = ommResult_FAILURE; break; }
+        }
         // ref: serialize_impl.cpp:463-468 -- blobs older than v3 did not store the texture's alpha cutoff although they stored its SAT
         if (t->hasSerializedSat && version < 3) t->alphaCutoff = d.alphaCutoff;
         rc = UploadTexture(t, log);
@@ -533,6 +571,7 @@ ommResult DeserializeImpl(BakerObject* b, const ommCpuBlobDesc& blob, Deserializ
     }
     if (rc != ommResult_SUCCESS) {
         DestroyDeserialized(r);
+        r = nullptr;
         return rc;
     }
     r->desc.flags = (ommCpuSerializeFlags)flags;
