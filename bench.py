@@ -14,7 +14,12 @@ A "step" is one complete bake of the synthetic config-3 input: UV
           blocks, merge replicated (launched with torch.distributed.run, one rank per GPU).  In the e2e arm every rank stages
           the inputs and takes part in the bake; the host copy of the result is read on rank 0.
   --impl reference   the SDK's own CPU baker (oracle/_ref/libomm-lib.so, OpenMP, all host cores) on a bounded slice of
-          the same workload per step (rank 0 only).
+          the same workload per step (rank 0 only), sized so that the K + W steps take about --ref-budget-s seconds.
+  parity  the metric says "bit-exact vs CPU baker", so the run proves it: at N=1 the cpu_baseline leg bakes the FULL config once with the
+          SDK build and the five result arrays of the GPU bake are compared with it byte for byte; at every N the sha256 of the result
+          (all ranks) is printed and compared with the committed digest of the SDK's result (tests/golden/full_size_digests.json), so
+          the N = 2 / 4 / 8 lines show the same digest as N = 1.
+  secondary  BASELINE configs 2 and 5 (config.secondary): device-resident and end-to-end times, digest against the SDK's.
 
 Prints ONE JSON line (rank 0).
 """
@@ -56,6 +61,10 @@ def parse_args():
     ap.add_argument("--level", type=int, default=6)
     ap.add_argument("--cpu-sample-tris", type=int, default=0, help="triangles in the bounded CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=float(os.environ.get("OMM_BENCH_CPU_BUDGET_S", "330")),
+                    help="the full-config SDK bake of the cpu_baseline leg is replaced by a slice when a probe predicts it would take longer than this")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: target duration of all K + W steps together")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs 2 and 5")
     return ap.parse_args()
 
 
@@ -134,23 +143,62 @@ def pinned_like(arr: np.ndarray):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def run_reference(a):
-    """The SDK's CPU baker on a bounded slice of the same workload, all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def golden_digests():
+    p = os.path.join(ROOT, "tests", "golden", "full_size_digests.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
+def is_full_c3(a):
+    return a.tris == 1_000_000 and a.tex == 4096 and a.level == 6
+
+
+def cpu_library():
+    """(lib, kind, threads) of the CPU checker: the unmodified SDK build when it travelled with the repo, else the scalar port."""
     cores = os.cpu_count() or 1
     if os.path.exists(REF_LIB):
         os.environ["OMP_NUM_THREADS"] = str(cores)
         os.environ.setdefault("OMP_PROC_BIND", "spread")
-        lib, kind, used = capi.OmmLib(REF_LIB), "reference", cores
-        sample = a.cpu_sample_tris or max(1024, a.tris // 64)
-    else:
-        if not os.path.exists(PORT_LIB):
-            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
-        lib, kind, used = capi.OmmLib(PORT_LIB), "port", 1
-        sample = a.cpu_sample_tris or max(256, a.tris // 1024)
-    sample = min(sample, a.tris)
+        return capi.OmmLib(REF_LIB), "reference", cores
+    if not os.path.exists(PORT_LIB):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+    return capi.OmmLib(PORT_LIB), "port", 1
+
+
+def cpu_bake(lib, wl, keep_result=False):
+    """One ommCpuBake on the CPU library; returns (seconds of the ommCpuBake call, BakeResult or None)."""
+    from omm_b200.baker import _copy_result
+    with Baker(lib) as b:
+        inp, tex = W.make_input(b, wl, bake_flags=capi.BAKE_ENABLE_INTERNAL_THREADS)
+        desc = inp.to_desc()
+        t0 = time.perf_counter()
+        rc, h = b.bake_raw(desc)
+        dt = time.perf_counter() - t0
+        assert rc == capi.SUCCESS, rc
+        res = None
+        if keep_result:
+            pdesc = C.POINTER(capi.CpuBakeResultDesc)()
+            assert lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc)) == capi.SUCCESS
+            res = _copy_result(pdesc.contents)
+        lib.dll.ommCpuDestroyBakeResult(h)
+        tex.destroy()
+    return dt, res
+
+
+def run_reference(a):
+    """The SDK's CPU baker on a bounded slice of the same workload per step, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, kind, used = cpu_library()
+    # probe: a small slice gives the rate; the per-step sample is sized so that all K + W steps fit the budget
+    probe = min(a.tris, 2048 if kind == "reference" else 128)
+    dt_probe, _ = cpu_bake(lib, W.config3(num_tris=probe, tex_size=a.tex, level=a.level))
+    per_tri = dt_probe / probe
+    sample = a.cpu_sample_tris or int(a.ref_budget_s / ((a.steps + a.warmup) * per_tri))
+    sample = max(256, min(sample, a.tris))
     wl = W.config3(num_tris=sample, tex_size=a.tex, level=a.level)
     utris = sample * 4 ** a.level
     times = []
@@ -168,12 +216,14 @@ def run_reference(a):
         tex.destroy()
     total = sum(times)
     value = utris * len(times) / total
-    sample_txt = f"first {sample} of {a.tris} triangles of the same grid/texture ({utris:.3e} micro-triangles) per step"
+    sample_txt = (f"all {a.tris} triangles" if sample == a.tris else f"first {sample} of {a.tris} triangles of the same grid/texture") + \
+                 f" ({utris:.3e} micro-triangles) per step, one ommCpuBake call each"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": sample_txt},
+        "config": {"workload": workload_name(a), "sample": sample_txt,
+                   "note": "rate per micro-triangle; the b200 arm's cpu_baseline leg times the FULL config once on the same cores (and compares the bytes)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": kind, "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,37 +231,34 @@ def run_reference(a):
     print(json.dumps(out), flush=True)
 
 
-def cpu_baseline(a):
-    cores = os.cpu_count() or 1
-    if os.path.exists(REF_LIB):
-        os.environ["OMP_NUM_THREADS"] = str(cores)
-        os.environ.setdefault("OMP_PROC_BIND", "spread")
-        lib, kind, used = capi.OmmLib(REF_LIB), "reference", cores
-        sample = a.cpu_sample_tris or max(1024, a.tris // 32)
-    elif os.path.exists(PORT_LIB):
-        lib, kind, used = capi.OmmLib(PORT_LIB), "port", 1
-        sample = a.cpu_sample_tris or max(256, a.tris // 512)
-    else:
-        return None
+def cpu_baseline(a, gpu_result):
+    """The SDK build on the FULL config (one ommCpuBake call on all host cores), and the byte comparison with the GPU result.  When a probe predicts
+    more than --cpu-budget-s the largest slice that fits is timed instead and parity rests on the committed digest of the SDK's full result."""
+    from omm_b200.baker import result_sha256
+    lib, kind, used = cpu_library()
+    probe = min(a.tris, 4096 if kind == "reference" else 128)
+    dt_probe, _ = cpu_bake(lib, W.config3(num_tris=probe, tex_size=a.tex, level=a.level))
+    predicted = dt_probe / probe * a.tris
+    sample = a.cpu_sample_tris or (a.tris if predicted <= a.cpu_budget_s else max(256, int(a.tris * a.cpu_budget_s / predicted)))
     sample = min(sample, a.tris)
-    wl = W.config3(num_tris=sample, tex_size=a.tex, level=a.level)
-    with Baker(lib) as b:
-        inp, tex = W.make_input(b, wl, bake_flags=capi.BAKE_ENABLE_INTERNAL_THREADS)
-        desc = inp.to_desc()
-        t0 = time.perf_counter()
-        rc, h = b.bake_raw(desc)
-        dt = time.perf_counter() - t0
-        assert rc == capi.SUCCESS
-        lib.dll.ommCpuDestroyBakeResult(h)
-        tex.destroy()
+    full = sample == a.tris
+    dt, res = cpu_bake(lib, W.config3(num_tris=sample, tex_size=a.tex, level=a.level), keep_result=full)
     utris = sample * 4 ** a.level
-    return {"value": utris / dt, "unit": UNIT, "cores": used, "kind": kind, "seconds": dt,
-            "sample": f"first {sample} of {a.tris} triangles of the same grid/texture, one ommCpuBake call ({utris:.3e} micro-triangles)"}
+    base = {"value": utris / dt, "unit": UNIT, "cores": used, "kind": kind, "seconds": dt,
+            "sample": (f"FULL config: all {a.tris} triangles" if full else f"first {sample} of {a.tris} triangles of the same grid/texture") +
+                      f", one ommCpuBake call ({utris:.3e} micro-triangles)"}
+    parity = None
+    if full and gpu_result is not None:
+        d = gpu_result.diff(res)
+        parity = {"arrays_identical": d == [], "compared": "arrayData, descArray, descArrayHistogram, indexBuffer (+ format), indexHistogram of the GPU ommCpuBake result "
+                  f"vs one full ommCpuBake of the {kind} library in this run", "oracle_sha256": result_sha256(res), "diff": d}
+    return base, parity
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 def run_b200(a):
     import torch
+    from omm_b200.baker import _copy_result, result_sha256
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,12 +277,6 @@ def run_b200(a):
     assert lib.dll.ommB200GetDeviceCount() > 0, "no CUDA device visible"
     assert lib.dll.ommB200SetDevice(local) == capi.SUCCESS
 
-    wl = W.config3(num_tris=a.tris, tex_size=a.tex, level=a.level)
-    utris_total = a.tris * 4 ** a.level
-    idx_pinned, _k1 = pinned_like(wl.indices)
-    uv_pinned, _k2 = pinned_like(wl.texcoords)
-    wl.indices, wl.texcoords = idx_pinned, uv_pinned
-
     baker = Baker(lib)
     if world > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8)
@@ -247,136 +288,231 @@ def run_b200(a):
         dist.broadcast(idbuf, 0)
         raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
         assert lib.dll.ommB200InitSharding(baker.handle, rank, world, raw, 128) == capi.SUCCESS
-    inp, tex = W.make_input(baker, wl)
-    desc = inp.to_desc()
     stream = torch.cuda.current_stream()
     stream_ptr = C.c_void_p(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    tm = capi.B200BakeTimings()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ----
-    staged = C.c_void_p()
-    assert lib.dll.ommB200StageInputs(baker.handle, C.byref(desc), C.byref(staged)) == capi.SUCCESS
-    tm = capi.B200BakeTimings()
-    step_ms, classify_ms, launches, last = [], [], 0, None
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def resident_steps(desc, warmup, steps, sampler=None):
+        """W + K device-resident bakes of staged inputs; returns per-step ms (max over ranks), per-step classify ms, launches, timings of the last."""
+        staged = C.c_void_p()
+        assert lib.dll.ommB200StageInputs(baker.handle, C.byref(desc), C.byref(staged)) == capi.SUCCESS
+        step_ms, classify_ms, launches, last = [], [], 0, None
+        for it in range(warmup + steps):
+            flush.fill_(it & 0xFF)  # evict L2 between steps (outside the timed events)
+            barrier()
+            if sampler is not None and rank == 0 and it == max(warmup - 1, 0):
+                sampler.start()
+                sampler.wait_first()
+            if sampler is not None and it == warmup:
+                sampler.mark()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            h = C.c_void_p()
+            rc = lib.dll.ommB200BakeResident(baker.handle, staged, stream_ptr, C.byref(h))
+            e1.record(stream)
+            assert rc == capi.SUCCESS, f"ommB200BakeResident -> {rc}"
+            barrier()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            lib.dll.ommB200GetLastBakeTimings(baker.handle, C.byref(tm))
+            if it >= warmup:
+                step_ms.append(ms)
+                classify_ms.append(tm.classifyMs)
+                launches += tm.kernelLaunches
+            last = dict(work_items=tm.workItems, array_bytes=tm.arrayDataBytes, desc_count=tm.descCount, my_utris=tm.microTriangles, setup_ms=tm.setupMs,
+                        post_ms=tm.postMs, item_post_ms=tm.itemPostMs, gather_ms=tm.gatherMs)
+            lib.dll.ommCpuDestroyBakeResult(h)
+        lib.dll.ommB200DestroyStagedInputs(staged)
+        return step_ms, classify_ms, launches, last
+
+    def e2e_steps(desc, warmup, steps, keep_last=False, every_rank_downloads=False):
+        """W + K drop-in calls ommCpuBake + ommCpuGetBakeResultDesc (host buffers in, host arrays out); wall seconds per step (max over ranks)."""
+        secs, launches, info, kept = [], 0, None, None
+        for it in range(warmup + steps):
+            barrier()
+            t0 = time.perf_counter()
+            h = C.c_void_p()
+            rc = lib.dll.ommCpuBake(baker.handle, C.byref(desc), C.byref(h))
+            pdesc = C.POINTER(capi.CpuBakeResultDesc)()
+            # the host copy of the result is materialised where it is consumed: on rank 0
+            rc2 = lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc)) if (rank == 0 or every_rank_downloads) else capi.SUCCESS
+            dt = time.perf_counter() - t0
+            assert rc == capi.SUCCESS and rc2 == capi.SUCCESS, (rc, rc2)
+            dt = max_over_ranks(dt)
+            lib.dll.ommB200GetLastBakeTimings(baker.handle, C.byref(tm))
+            info = {"h2d": int(tm.h2dBytes), "d2h": int(tm.d2hBytes),
+                    "breakdown": {"stage_ms": tm.hostStageMs, "bake_ms": tm.hostBakeMs, "download_ms": tm.hostDownloadMs, "h2d_ms": tm.h2dMs, "d2h_ms": tm.d2hMs,
+                                  "device_total_ms": tm.totalDeviceMs}}
+            if it >= warmup:
+                secs.append(dt)
+                launches += tm.kernelLaunches
+            if keep_last and it == warmup + steps - 1 and (rank == 0 or every_rank_downloads):
+                kept = _copy_result(pdesc.contents)
+            lib.dll.ommCpuDestroyBakeResult(h)
+        return secs, launches, info, kept
+
+    # ================= headline: BASELINE config 3 =================
+    wl = W.config3(num_tris=a.tris, tex_size=a.tex, level=a.level)
+    utris_total = a.tris * 4 ** a.level
+    pageable_idx, pageable_uv = wl.indices, wl.texcoords
+    idx_pinned, _k1 = pinned_like(wl.indices)
+    uv_pinned, _k2 = pinned_like(wl.texcoords)
+    wl.indices, wl.texcoords = idx_pinned, uv_pinned
+    inp, tex = W.make_input(baker, wl)
+    desc = inp.to_desc()
+
     sampler = ClockSampler(local)
-    for it in range(a.warmup + a.steps):
-        flush.fill_(it & 0xFF)  # evict L2 between steps (outside the timed events)
-        barrier()
-        if rank == 0 and it == max(a.warmup - 1, 0):
-            sampler.start()
-            sampler.wait_first()
-        if it == a.warmup:
-            sampler.mark()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        h = C.c_void_p()
-        rc = lib.dll.ommB200BakeResident(baker.handle, staged, stream_ptr, C.byref(h))
-        e1.record(stream)
-        assert rc == capi.SUCCESS, f"ommB200BakeResident -> {rc}"
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        lib.dll.ommB200GetLastBakeTimings(baker.handle, C.byref(tm))
-        if it >= a.warmup:
-            step_ms.append(ms)
-            classify_ms.append(tm.classifyMs)
-            launches += tm.kernelLaunches
-        last = (tm.workItems, tm.arrayDataBytes, tm.descCount, tm.microTriangles, tm.setupMs, tm.postMs, tm.itemPostMs, tm.gatherMs)
-        lib.dll.ommCpuDestroyBakeResult(h)
+    step_ms, classify_ms, launches, last = resident_steps(desc, a.warmup, a.steps, sampler)
     clocks = sampler.stop()
-    lib.dll.ommB200DestroyStagedInputs(staged)
     total_ms = sum(step_ms)
     value = utris_total * len(step_ms) / (total_ms * 1e-3)
 
-    # ---- end-to-end arm: the drop-in ommCpuBake with host buffers ----
-    e2e_s, h2d, d2h = [], 0, 0
-    for it in range(a.warmup + a.steps):
-        barrier()
-        t0 = time.perf_counter()
-        h = C.c_void_p()
-        rc = lib.dll.ommCpuBake(baker.handle, C.byref(desc), C.byref(h))
-        pdesc = C.POINTER(capi.CpuBakeResultDesc)()
-        # the host copy of the result is materialised where it is consumed: on rank 0 (every rank holds the complete result in HBM and
-        # could download it; N simultaneous 290 MB downloads through one host only measure the host's memory system)
-        rc2 = lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc)) if rank == 0 else capi.SUCCESS
-        dt = time.perf_counter() - t0
-        assert rc == capi.SUCCESS and rc2 == capi.SUCCESS
-        if dist is not None:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        lib.dll.ommB200GetLastBakeTimings(baker.handle, C.byref(tm))
-        h2d, d2h = int(tm.h2dBytes), int(tm.d2hBytes)
-        host_break = {"stage_ms": tm.hostStageMs, "bake_ms": tm.hostBakeMs, "download_ms": tm.hostDownloadMs, "h2d_ms": tm.h2dMs, "d2h_ms": tm.d2hMs,
-                      "device_total_ms": tm.totalDeviceMs}
-        if it >= a.warmup:
-            e2e_s.append(dt)
-            launches += tm.kernelLaunches
-        lib.dll.ommCpuDestroyBakeResult(h)
+    # ---- end-to-end arm: the drop-in ommCpuBake with host buffers (page-locked by the caller) ----
+    e2e_s, l2, e2e_info, _ = e2e_steps(desc, a.warmup, a.steps)
+    launches += l2
     e2e_value = utris_total * len(e2e_s) / sum(e2e_s)
+    # ---- the same call with PAGEABLE caller buffers (what a stock SDK caller passes) ----
+    wl.indices, wl.texcoords = pageable_idx, pageable_uv
+    inp_pg = BakeInputFrom(inp, pageable_idx, pageable_uv)
+    desc_pg = inp_pg.to_desc()
+    pg_s, _, _, _ = e2e_steps(desc_pg, 1, max(2, min(3, a.steps)))
+    # ---- verification bake (outside every timed region): every rank downloads its copy of the result; digests must agree ----
+    _, _, _, mine = e2e_steps(desc_pg, 0, 1, keep_last=True, every_rank_downloads=True)
+    my_sha = result_sha256(mine)
+    shas = [my_sha]
+    if dist is not None:
+        shas = [None] * world
+        dist.all_gather_object(shas, my_sha)
+    golden = golden_digests()
+    parity = {"config": "C3 full" if is_full_c3(a) else f"C3 variant ({a.tris} triangles, {a.tex}^2, level {a.level})", "result_sha256": shas[0],
+              "ranks_identical": len(set(shas)) == 1, "ranks": world}
+    if is_full_c3(a) and "C3" in golden:
+        parity["golden_sha256"] = golden["C3"]["sha256"]
+        parity["matches_golden"] = shas[0] == golden["C3"]["sha256"] and len(set(shas)) == 1
+        parity["golden_source"] = "tests/golden/full_size_digests.json: sha256 of the unmodified SDK build's result for this config (tests/golden/make_full_size_digests.py)"
 
-    # ---- roofline of the dominant stage: classification (the Hier* kernels, >= 80 % of the device time of a step) ----
+    # ================= secondary: BASELINE configs 2 and 5 =================
+    secondary = {}
+    if not a.no_secondary and is_full_c3(a):
+        tex.destroy()
+        tex = None
+        for name, swl in (("C2", W.config2()), ("C5", W.config5())):
+            sinp, stex = W.make_input(baker, swl)
+            sdesc = sinp.to_desc()
+            sms, scl, sl, slast = resident_steps(sdesc, 2, 3)
+            ss, sl2, _, sres = e2e_steps(sdesc, 1, 3, keep_last=True, every_rank_downloads=True)
+            launches += sl + sl2
+            sha = result_sha256(sres)
+            sshas = [sha]
+            if dist is not None:
+                sshas = [None] * world
+                dist.all_gather_object(sshas, sha)
+            sutris = int(slast["my_utris"]) if world == 1 else None
+            entry = {"workload": swl.name, "ms_per_step": statistics.median(sms), "classify_ms": statistics.median(scl), "item_post_ms": slast["item_post_ms"],
+                     "post_ms": slast["post_ms"], "setup_ms": slast["setup_ms"], "gather_ms": slast["gather_ms"], "e2e_ms_per_step": 1e3 * statistics.median(ss),
+                     "work_items": slast["work_items"], "array_data_bytes": slast["array_bytes"], "result_sha256": sshas[0], "ranks_identical": len(set(sshas)) == 1}
+            if sutris:
+                entry["micro_triangles"] = sutris
+                entry["micro_triangles_per_s"] = sutris / (statistics.median(sms) * 1e-3)
+            if name in golden:
+                entry["matches_golden"] = sshas[0] == golden[name]["sha256"] and len(set(sshas)) == 1
+            if name == "C2" and rank == 0 and world == 1 and not a.no_cpu_baseline:
+                clib, ckind, _ = cpu_library()
+                cdt, cres = cpu_bake(clib, swl, keep_result=True)
+                entry["arrays_identical"] = sres.diff(cres) == []
+                entry["cpu_seconds"] = cdt
+            secondary[name] = entry
+            stex.destroy()
+
+    # ---- roofline (SURVEY 8d): B_alg = texture + geometry + the outputs the result really holds; duration = the whole device-resident bake ----
     peaks, peak_kind = measured_peaks()
-    work_items, array_bytes, desc_count, my_utris, setup_ms, post_ms, item_post_ms, gather_ms = last
     tex_bytes = a.tex * a.tex * 4
-    # algorithmic bytes of one classification pass on this rank: the texture once, one 32-byte item record per work item,
-    # 2 bits written per micro-triangle (DESIGN.md "Kernels").  Duration: CUDA events recorded by the library on the bake's
-    # stream around the stage (ommB200BakeTimings.classifyMs), averaged over the timed steps.
-    classify_bytes = tex_bytes + 32 * (work_items // world) + my_utris // 4
+    b_alg = tex_bytes + wl.indices.nbytes + wl.texcoords.nbytes + int(last["array_bytes"]) + 8 * int(last["desc_count"]) + 4 * a.tris
+    ms_step = total_ms / len(step_ms)
     cls_ms = sum(classify_ms) / len(classify_ms)
-    achieved = classify_bytes / (cls_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1d_stage_traffic.json")
-    if world == 1 and a.tris == 1_000_000 and a.level == 6 and a.tex == 4096 and os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic = tj["dram_bytes_read_per_bake"] + tj["dram_bytes_written_per_bake"]  # ncu capture of this very command, see the file
-    roofline = {"bound": "hbm", "kernel": "classification stage = HierTestInitial + HierTestUnresolved + 2x HierTestList + HierLeaves per chunk (HierLeaves ~55 % of it)",
-                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                "kernel_ms": cls_ms, "algorithmic_bytes": classify_bytes,
-                "note": "instruction-issue bound, not HBM bound: 0.27 algorithmic bytes per micro-triangle against the bit-exact level-line arithmetic "
-                        "(IEEE divisions and square roots) of every micro-triangle the level line touches; the hierarchical classifier removes the "
-                        "arithmetic of provably uniform regions (97 % of the micro-triangles), profiles/r1c_HierLeaves_* and r1d_HierTestList_* hold issue utilisation and pipe mix"}
-    # whole-path algorithmic bytes per SURVEY 8d: texture + geometry + outputs
-    path_bytes = tex_bytes + wl.indices.nbytes + wl.texcoords.nbytes + array_bytes + 8 * desc_count + 4 * a.tris
+    achieved = b_alg / (ms_step * 1e-3) / 1e9
+    traffic, issue = None, None
+    if world == 1 and is_full_c3(a):
+        tj = latest_profile_json("stage_traffic")
+        if tj is not None:
+            traffic = tj["dram_bytes_read_per_bake"] + tj["dram_bytes_written_per_bake"]
+        issue = latest_profile_json("issue")
+    roofline = {"bound": "hbm", "kernel": "whole bake (classification stage = the Hier* kernels is %.0f %% of it)" % (100.0 * cls_ms / ms_step),
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "algorithmic_bytes": b_alg, "algorithmic_bytes_def": "SURVEY 8d B_alg = texture + index buffer + UV buffer + arrayData + 8*descs + 4*triangles",
+                "kernel_ms": ms_step, "classify_stage_ms": cls_ms, "frac_classify_stage_only": b_alg / (cls_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "traffic": traffic, "traffic_ratio": (traffic / b_alg) if traffic else None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "issue": issue,
+                "note": "the path is instruction-issue bound, not HBM bound: B_alg is 0.1 byte per micro-triangle against the bit-exact level-line arithmetic (IEEE divisions, "
+                        "square roots) of the micro-triangles the level line touches; `issue` holds the ncu counters of the dominant kernels of this build (profiles/)"}
 
     if rank == 0:
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
-            cpu = cpu_baseline(a)
+            cpu, full_parity = cpu_baseline(a, mine)
+            if full_parity is not None:
+                parity.update(full_parity)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": total_ms / len(step_ms), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "l2": "256 MiB buffer written between steps (outside the timed events)",
-                       "work_items": work_items, "array_data_bytes": array_bytes, "desc_count": desc_count,
-                       "path_algorithmic_bytes": path_bytes, "step_ms": [round(x, 3) for x in step_ms], "setup_ms": setup_ms, "classify_ms": cls_ms, "post_ms": post_ms, "item_post_ms": item_post_ms, "gather_ms": gather_ms,
-                       "sharding": "none" if world == 1 else f"work items split over {world} ranks, 1 NCCL all-gather of state blocks"},
+                       "work_items": last["work_items"], "array_data_bytes": last["array_bytes"], "desc_count": last["desc_count"],
+                       "step_ms": [round(x, 3) for x in step_ms], "setup_ms": last["setup_ms"], "classify_ms": cls_ms, "post_ms": last["post_ms"],
+                       "item_post_ms": last["item_post_ms"], "gather_ms": last["gather_ms"],
+                       "sharding": "none" if world == 1 else f"work items split over {world} ranks; one NCCL all-gather of 12-byte per-item records, blocks written to their final place over NVLink",
+                       "secondary": secondary},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_info["h2d"], "d2h_bytes_per_step": e2e_info["d2h"],
                     "ms_per_step": 1e3 * sum(e2e_s) / len(e2e_s),
-                    "call": "ommCpuBake + ommCpuGetBakeResultDesc, pinned host inputs -> host result" + ("" if world == 1 else " (downloaded on rank 0)"),
-                    "last_step_breakdown": host_break},
+                    "call": "ommCpuBake + ommCpuGetBakeResultDesc, page-locked caller buffers -> host result" + ("" if world == 1 else " (read on rank 0)"),
+                    "pageable_ms_per_step": 1e3 * sum(pg_s) / len(pg_s), "pageable_value": utris_total * len(pg_s) / sum(pg_s),
+                    "last_step_breakdown": e2e_info["breakdown"]},
             "gpu_launches": launches,
             "roofline": roofline,
+            "parity": parity,
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
-    tex.destroy()
+    if tex is not None:
+        tex.destroy()
     baker.destroy()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def BakeInputFrom(inp, indices, texcoords):
+    """A copy of a BakeInput with other host buffers."""
+    import copy
+    c = copy.copy(inp)
+    c.indices, c.texcoords = indices, texcoords
+    return c
+
+
+def latest_profile_json(kind):
+    """profiles/r<round><letter>_<kind>.json of the newest round present (written by scripts/ncu_summary.py from an ncu capture of this build)."""
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kind}.json")))
+    if not cands:
+        return None
+    with open(cands[-1]) as f:
+        j = json.load(f)
+    j["file"] = os.path.relpath(cands[-1], ROOT)
+    return j
 
 
 def main():

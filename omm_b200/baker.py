@@ -57,6 +57,17 @@ class BakeResult:
         return out
 
 
+def result_sha256(res: BakeResult) -> str:
+    """One digest over everything ommCpuBakeResultDesc exposes: the five arrays in the order of the SDK's serialize round-trip comparison
+    (test_omm_bake_cpu.cpp:323-344) plus the index format."""
+    import hashlib
+    h = hashlib.sha256()
+    for k in ("array_data", "desc_array", "desc_histogram", "index_buffer", "index_histogram"):
+        h.update(np.ascontiguousarray(getattr(res, k)).tobytes())
+    h.update(bytes([res.index_format]))
+    return h.hexdigest()
+
+
 class Texture:
     def __init__(self, baker: "Baker", handle: int, keepalive):
         self.baker, self.handle, self._keepalive = baker, handle, keepalive

@@ -1,7 +1,9 @@
-"""BASELINE config 3 at FULL size (1 M triangles, 4096^2 alpha, level 6 = 4.1e9 micro-triangles) on the GPU, tied to the oracle by a
-size-independent property: classification is per work item, so the block (or special index) a triangle ends up with in the full
-bake must be byte-identical with what the SDK's CPU baker produces for the same triangle in a bake of only the first few thousand
-triangles of the same sequence (layout differs -- dedup survivors, sort order, offsets -- content per triangle does not)."""
+"""BASELINE configs 3 and 5 at FULL size on the GPU against the SDK's CPU baker at FULL size: all five result arrays byte for byte -- dedup
+survivors, sort order, offsets, descriptors, index buffer and both histograms included (the comparison support/tests/test_omm_bake_cpu.cpp:323-344
+makes).  Config 3 is 4.1e9 micro-triangles: about three minutes and 10 GB of host memory on the box's cores for the SDK build (BASELINE.md section 3 asks
+for the full run when it fits in 30 minutes).  Without oracle/_ref (the scalar port would need hours) the test falls back to the size-independent
+property of round 1: per-triangle block content against a bake of a subset of the same triangle sequence."""
+import copy
 import os
 
 import numpy as np
@@ -42,13 +44,9 @@ def _blocks(res, tris):
     return out
 
 
-def test_config3_full_size_matches_the_oracle_per_triangle():
-    lib = load_product_library()
-    oracle_path = REF if os.path.exists(REF) else PORT
-    sample = 6000 if oracle_path == REF else 400
-    full = _bake(lib, W.config3())
-    assert full.index_buffer.size == 1_000_000
-    # structural invariants of the result (ref: bake_cpu_impl.cpp:1756-1920)
+def _structure(full, num_tris):
+    """structural invariants of a result (ref: bake_cpu_impl.cpp:1756-1920)"""
+    assert full.index_buffer.size == num_tris
     descs = full.desc_array
     sizes = np.maximum(1, ((1 << (2 * descs["subdivisionLevel"].astype(np.int64))) * descs["format"].astype(np.int64)) // 8)
     assert np.array_equal(descs["offset"].astype(np.int64), np.concatenate([[0], np.cumsum(sizes)[:-1]]))
@@ -57,33 +55,54 @@ def test_config3_full_size_matches_the_oracle_per_triangle():
     assert idx.min() >= -4 and idx.max() == descs.size - 1
     assert int(full.desc_histogram["count"].sum()) == descs.size
     assert int(full.index_histogram["count"].sum()) == int((idx >= 0).sum())
-    # determinism: a second bake is byte-identical
-    assert not full.diff(_bake(lib, W.config3()))
-    # per-triangle content against the CPU oracle on the first `sample` triangles of the same sequence
-    oracle = _bake(capi.OmmLib(oracle_path), W.config3(num_tris=sample), bake_flags=capi.BAKE_ENABLE_INTERNAL_THREADS)
-    tris = range(sample)
-    assert _blocks(full, tris) == _blocks(oracle, tris)
 
 
-def test_config5_full_size_matches_the_oracle_per_triangle():
-    """BASELINE config 5 (1 M triangles drawn from 4096 distinct UV triangles + 65 k large triangles over constant areas, per-triangle
-    levels 0..12): the full bake on the GPU against the CPU oracle on a subset of its triangles (those of level <= 7, so that the
-    CPU finishes in seconds)."""
-    import copy
+def _sdk():
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    return capi.OmmLib(REF)
+
+
+def test_config3_full_size_is_byte_identical_with_the_sdk_bake():
     lib = load_product_library()
-    oracle_path = REF if os.path.exists(REF) else PORT
+    wl = W.config3()
+    full = _bake(lib, wl)
+    _structure(full, 1_000_000)
+    assert not full.diff(_bake(lib, wl)), "second bake differs (determinism)"
+    if os.path.exists(REF):
+        want = _bake(_sdk(), wl, bake_flags=capi.BAKE_ENABLE_INTERNAL_THREADS)   # the full 1 M-triangle bake on the host cores
+        assert full.diff(want) == []
+    else:
+        sample = 400
+        oracle = _bake(capi.OmmLib(PORT), W.config3(num_tris=sample))
+        assert _blocks(full, range(sample)) == _blocks(oracle, range(sample))
+
+
+def test_config5_full_size_is_byte_identical_with_the_sdk_bake():
+    """BASELINE config 5: 1 M triangles drawn from 4096 distinct UV triangles + 65 k large triangles over constant areas, per-triangle levels 0..12."""
+    lib = load_product_library()
     wl = W.config5()
     full = _bake(lib, wl)
-    assert full.index_buffer.size == wl.num_triangles
-    rng = np.random.default_rng(5)
-    lv = wl.subdivision_levels
-    cand = np.nonzero((lv <= 7) & (np.arange(lv.size) >= 65536))[0]
-    flat = np.nonzero(np.arange(lv.size) < 65536)[0]
-    pick = np.sort(np.concatenate([rng.choice(cand, 1500 if oracle_path == REF else 150, replace=False), rng.choice(flat, 4, replace=False)]))
-    sub = copy.copy(wl)
-    uv = wl.texcoords.reshape(-1, 3, 2)
-    sub.texcoords = np.ascontiguousarray(uv[pick].reshape(-1, 2))
-    sub.indices = np.arange(3 * pick.size, dtype=np.uint32)
-    sub.subdivision_levels = np.ascontiguousarray(lv[pick])
-    oracle = _bake(capi.OmmLib(oracle_path), sub, bake_flags=capi.BAKE_ENABLE_INTERNAL_THREADS)
-    assert _blocks(full, pick) == _blocks(oracle, range(pick.size))
+    _structure(full, wl.num_triangles)
+    if os.path.exists(REF):
+        want = _bake(_sdk(), wl, bake_flags=capi.BAKE_ENABLE_INTERNAL_THREADS)
+        assert full.diff(want) == []
+    else:
+        rng = np.random.default_rng(5)
+        lv = wl.subdivision_levels
+        cand = np.nonzero((lv <= 7) & (np.arange(lv.size) >= 65536))[0]
+        flat = np.nonzero(np.arange(lv.size) < 65536)[0]
+        pick = np.sort(np.concatenate([rng.choice(cand, 150, replace=False), rng.choice(flat, 4, replace=False)]))
+        sub = copy.copy(wl)
+        uv = wl.texcoords.reshape(-1, 3, 2)
+        sub.texcoords = np.ascontiguousarray(uv[pick].reshape(-1, 2))
+        sub.indices = np.arange(3 * pick.size, dtype=np.uint32)
+        sub.subdivision_levels = np.ascontiguousarray(lv[pick])
+        oracle = _bake(capi.OmmLib(PORT), sub)
+        assert _blocks(full, pick) == _blocks(oracle, range(pick.size))
+
+
+def test_config2_full_size_is_byte_identical_with_the_checker(checker_lib):
+    """BASELINE config 2 (10 k triangles, 1024^2, level 4, 25 % UV reuse) in full."""
+    lib = load_product_library()
+    wl = W.config2()
+    assert _bake(lib, wl).diff(_bake(checker_lib, wl)) == []

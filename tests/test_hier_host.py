@@ -235,3 +235,20 @@ def test_plain_walk_equals_the_sdk_build(lib):
         want = _sdk_states(ref, tex, uv, lv, addr, cutoff, promo, fmt, capi.STATE_O, capi.STATE_T, 0.0, use_sat)
         bad = np.nonzero(sink != want)[0]
         assert bad.size == 0, f"run {k}: {bad.size} of {want.size} micro-triangles differ from the SDK build (first at {bad[:5]}, got {sink[bad[:5]]}, SDK {want[bad[:5]]})"
+
+
+def test_random_campaign_slice(lib):
+    """A bounded, seeded slice of scripts/host_campaign.py inside the CPU suite, so that a regression in one of the exactness bounds of
+    omm_hier.cuh (the constants of (A)-(G), (S)) is caught by `pytest -m "not gpu"` and not only by a hand-run campaign.  ~25 s; the
+    generator is tests/campaign.py::host_campaign_step (random textures, address modes, cutoffs on texel values, levels 0-9, mips, SAT)."""
+    import time
+
+    import campaign
+    rng = np.random.default_rng(20261017)
+    fixed = textures(rng)
+    t0, runs, total = time.time(), 0, 0
+    while runs < 400 and time.time() - t0 < 25.0:
+        st, _ = campaign.host_campaign_step(__import__("test_hier_host"), lib, rng, fixed)
+        total += st.microTriangles
+        runs += 1
+    assert runs >= 20 and total > 1_000_000, (runs, total)
