@@ -118,11 +118,20 @@ static ommResult ValidateBakeDesc(const Logger& log, const ommCpuBakeInputDesc& 
     return ommResult_SUCCESS;
 }
 
+// Results outlive nothing in the SDK's contract except their own handle, so a result may be asked for its host copy (or destroyed) after
+// its baker is gone: live bakers are looked up here, never dereferenced blindly.
+static std::mutex g_liveBakersMu;
+static std::vector<BakerObject*> g_liveBakers;
+
 static void DestroyResult(BakeResultObject* r) {
     if (!r) return;
     DestroyResultDevice(r);
     const HostAllocator alloc = r->alloc;
-    if (r->arrayDataFromPinnedPool) PinnedPoolRelease(r->hostArrayData);
+    if (r->sharedWindowId >= 0) {
+        // the array lives in a shared window of the baker's sharding (unmapped with the sharding if the baker went first)
+        std::lock_guard<std::mutex> live(g_liveBakersMu);
+        if (std::find(g_liveBakers.begin(), g_liveBakers.end(), r->baker) != g_liveBakers.end()) ReleaseSharedWindow(r->baker, r->sharedWindowId);
+    } else if (r->arrayDataFromPinnedPool) PinnedPoolRelease(r->hostArrayData);
     else alloc.release(r->hostArrayData);
     alloc.release(r->hostDescArray);
     alloc.release(r->hostIndexBuffer);
@@ -139,10 +148,7 @@ OMM_API ommLibraryDesc ommGetLibraryDesc(void) {
     return d;
 }
 
-// Results outlive nothing in the SDK's contract except their own handle, so a result may be asked for its host copy after its baker
-// is gone; the timings of a deferred download are then simply not recorded (live bakers are looked up here, never dereferenced blindly).
-static std::mutex g_liveBakersMu;
-static std::vector<BakerObject*> g_liveBakers;
+// the timings of a deferred download of a result whose baker is gone are simply not recorded
 static void RecordDeferredDownload(BakerObject* baker, float d2hMs, uint64_t d2hBytes, float hostMs) {
     std::lock_guard<std::mutex> live(g_liveBakersMu);
     if (std::find(g_liveBakers.begin(), g_liveBakers.end(), baker) == g_liveBakers.end()) return;
@@ -375,7 +381,9 @@ static ommResult CheckBakeArgs(ommBaker baker, const ommCpuBakeInputDesc* d, Bak
     return ommResult_SUCCESS;
 }
 
-static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* stream, bool download, float stageMs, ommCpuBakeResult* out) {
+// download: make the host copy before returning; early: the caller will want the host copy (ommCpuBake), so the device pipeline may
+// start sending the array while it is still packing (and, sharded, every rank sends its own shards to the root's host memory)
+static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* stream, bool download, bool early, float stageMs, ommCpuBakeResult* out) {
     BakeResultObject* r = AllocObject<BakeResultObject>(b->alloc);
     if (!r) return ommResult_FAILURE;
     r->alloc = b->alloc;
@@ -388,7 +396,7 @@ static ommResult RunBake(BakerObject* b, const StagedInputs& staged, void* strea
     tm.hostStageMs = stageMs;
     const auto t0 = std::chrono::steady_clock::now();
     HostTrace::Mark("result object");
-    ommResult rc = BakeOnDevice(b, staged, stream, r, &tm, download);
+    ommResult rc = BakeOnDevice(b, staged, stream, r, &tm, early);
     HostTrace::Mark("BakeOnDevice returned");
     const auto t1 = std::chrono::steady_clock::now();
     if (rc == ommResult_SUCCESS && download) rc = DownloadResult(r, &tm.d2hMs, &tm.d2hBytes);
@@ -423,7 +431,7 @@ OMM_API ommResult ommCpuBake(ommBaker baker, const ommCpuBakeInputDesc* d, ommCp
     HostTrace::Mark("inputs staged");
     // Sharded bakes leave the complete result in every rank's HBM; the host copy is made by ommCpuGetBakeResultDesc on the ranks
     // that ask for it (N simultaneous downloads through one host were measured at a quarter of the single-download speed).
-    rc = RunBake(b, staged, nullptr, b->shard.world <= 1, stageMs, outBakeResult);
+    rc = RunBake(b, staged, nullptr, b->shard.world <= 1, true, stageMs, outBakeResult);
     HostTrace::Mark("bake + download");
     DestroyStagedDevice(&staged);
     HostTrace::Mark("staged inputs freed");
@@ -540,7 +548,7 @@ OMM_API ommResult ommB200BakeResident(ommBaker baker, ommB200StagedInputs staged
     StagedInputs* s = (StagedInputs*)staged;
     if (s->baker != b) return b->log.InvalidArg("[omm-b200] staged inputs belong to a different baker");
     HostTrace::Mark("ommB200BakeResident entry");
-    const ommResult rc = RunBake(b, *s, cudaStream, false, 0.f, outBakeResult);
+    const ommResult rc = RunBake(b, *s, cudaStream, false, false, 0.f, outBakeResult);
     HostTrace::Mark("bake");
     HostTrace::Dump();
     return rc;

@@ -16,7 +16,14 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types only: the library is bound at run time (see NcclApi) so single-GPU use needs no libnccl
 
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 
 #include "omm_device_math.cuh"
@@ -36,6 +43,39 @@ namespace ommb200 {
 
 constexpr int kMaxLevel = 12;
 constexpr uint32_t kNoItem = 0xFFFFFFFFu;
+
+// NVTX ranges around the stages of a bake (visible in Nsight Systems / Compute timelines).  libnvToolsExt is bound at run time like
+// NCCL: when it is not installed the ranges are no-ops.
+struct NvtxApi {
+    int (*push)(const char*) = nullptr;
+    int (*pop)() = nullptr;
+};
+static NvtxApi& Nvtx() {
+    static NvtxApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (getenv("OMM_B200_NO_NVTX")) return;
+        const char* names[] = {"libnvToolsExt.so.1", "libnvToolsExt.so"};
+        for (const char* n : names)
+            if (void* lib = dlopen(n, RTLD_NOW | RTLD_LOCAL)) {
+                api.push = (int (*)(const char*))dlsym(lib, "nvtxRangePushA");
+                api.pop = (int (*)())dlsym(lib, "nvtxRangePop");
+                if (api.push && api.pop) break;
+                api.push = nullptr;
+                api.pop = nullptr;
+            }
+    });
+    return api;
+}
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char* name) : on(Nvtx().push != nullptr) {
+        if (on) Nvtx().push(name);
+    }
+    ~NvtxRange() {
+        if (on) Nvtx().pop();
+    }
+};
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Work item record (one per unique UV triangle).
@@ -285,13 +325,13 @@ __global__ void UvTableResolve(const int8_t* __restrict__ triLevel, const uint64
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __restrict__ triLevel, const uint8_t* __restrict__ triFormat,
                            const uint8_t* __restrict__ triDegenerate, const uint32_t* __restrict__ isItem, const uint32_t* __restrict__ itemScan,
-                           uint32_t triCount, ItemRec* __restrict__ items, unsigned long long* __restrict__ itemUnits,
-                           unsigned long long* __restrict__ itemWords, unsigned long long* __restrict__ itemNodes, uint32_t* __restrict__ levelHist) {
+                           uint32_t triCount, ItemRec* __restrict__ itemsW, uint32_t* __restrict__ levelHist, uint32_t* __restrict__ numItemsOut) {
     __shared__ uint32_t sh[16];
     if (threadIdx.x < 16) sh[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = t < triCount && isItem[t];
+    if (t + 1 == triCount) *numItemsOut = itemScan[t] + (isItem[t] ? 1u : 0u);
     if (active) atomicAdd(&sh[triLevel[t]], 1u);
     __syncthreads();
     if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&levelHist[threadIdx.x], sh[threadIdx.x]);
@@ -306,18 +346,65 @@ __global__ void BuildItems(const float2* __restrict__ triUV, const int8_t* __res
     it.format = triFormat[t];
     it.degenerate = triDegenerate[t];
     it.hashLevel = it.level;
-    items[w] = it;
-    const unsigned long long n = 1ull << (2 * it.level);
-    itemUnits[w] = n >= 32 ? n / 32 : 1;
-    itemWords[w] = n >= 64 ? n / 16 : 4;  // blocks start 16-byte aligned so the warp stores and the pack copies can be vectorised
-    itemNodes[w] = it.level > 3 ? 1ull << (2 * (it.level - 3)) : 1ull;  // initial regions of the hierarchical classifier (HierTestInitial)
+    itemsW[w] = it;
 }
 
-__global__ void MapTrianglesToItems(const uint32_t* __restrict__ triFirst, const uint32_t* __restrict__ itemScan, uint32_t triCount, uint32_t* __restrict__ triItem) {
+// ---------------------------------------------------------------------------------------------------------------------
+// K3b: work items in OUTPUT order.  The SDK serializes the surviving work items sorted by (key, index) descending, key = level and
+// Morton code of the quantised UV centroid (ref: bake_cpu_impl.cpp:1707-1754) -- a function of the geometry alone.  So the order is
+// fixed BEFORE classification: the first-seen items (index w) are sorted once and every later stage works on positions s of that
+// order.  What this buys: the survivors of any contiguous run of positions occupy a contiguous range of descriptors and of
+// arrayData bytes, so a classifier chunk (one GPU) or a shard (several GPUs) can be packed -- and sent to the host, or to the other
+// GPUs -- as soon as ITS items are classified, and the final "sort" is a prefix sum over survivor flags.  Exact-dedup winners are
+// still "lowest first-seen index" (ItemRec::tri is monotone in w).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ItemSortKey(const ItemRec& it) {
+    // ref: bake_cpu_impl.cpp:1734-1747 -- level, then Morton code of the 13-bit quantised, MirrorOnce-folded UV centroid
+    const float cx = (it.p0.x + it.p1.x + it.p2.x) / 3.f, cy = (it.p0.y + it.p1.y + it.p2.y) / 3.f;
+    const int qx = f2i(8192.f * cx), qy = f2i(8192.f * cy);
+    const int mx = clampi(f2i(fabsf((float)qx + 0.5f)), 0, 8191), my = clampi(f2i(fabsf((float)qy + 0.5f)), 0, 8191);
+    uint32_t x = (uint32_t)mx, y = (uint32_t)my;
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+    y = (y | (y << 8)) & 0x00FF00FFu; y = (y | (y << 4)) & 0x0F0F0F0Fu; y = (y | (y << 2)) & 0x33333333u; y = (y | (y << 1)) & 0x55555555u;
+    return (((uint32_t)it.level << 26) | x | (y << 1)) + 1u;
+}
+// Keys of all `slots` entries (slots = triangle count; entries beyond the item count get key 0 and sort last).  The SDK sorts
+// (key, index) pairs descending (std::greater, :1751): a stable descending radix sort fed in reversed index order yields the same
+// order -- equal keys keep the higher index first.
+__global__ void ItemKeysAll(const ItemRec* __restrict__ itemsW, const uint32_t* __restrict__ numItemsPtr, uint32_t slots, uint32_t* __restrict__ sortKeys,
+                            uint32_t* __restrict__ sortVals) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= slots) return;
+    const uint32_t pos = slots - 1 - w;
+    sortKeys[pos] = w < *numItemsPtr ? ItemSortKey(itemsW[w]) : 0u;
+    sortVals[pos] = w;
+}
+// items[s] = itemsW[perm[s]]; sizes of the state blocks / warp units / initial regions in the new order (zero beyond the item count)
+__global__ void PermuteItems(const ItemRec* __restrict__ itemsW, const uint32_t* __restrict__ perm, const uint32_t* __restrict__ numItemsPtr, uint32_t slots,
+                             ItemRec* __restrict__ items, uint32_t* __restrict__ posOfOrig, unsigned long long* __restrict__ itemUnits,
+                             unsigned long long* __restrict__ itemWords, unsigned long long* __restrict__ itemNodes) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > slots) return;
+    if (s >= *numItemsPtr) {
+        itemUnits[s] = itemWords[s] = itemNodes[s] = 0ull;
+        return;
+    }
+    const uint32_t w = perm[s];
+    const ItemRec it = itemsW[w];
+    items[s] = it;
+    posOfOrig[w] = s;
+    const unsigned long long n = 1ull << (2 * it.level);
+    itemUnits[s] = n >= 32 ? n / 32 : 1;
+    itemWords[s] = n >= 64 ? n / 16 : 4;  // blocks start 16-byte aligned so the warp stores and the pack copies can be vectorised
+    itemNodes[s] = it.level > 3 ? 1ull << (2 * (it.level - 3)) : 1ull;  // initial regions of the hierarchical classifier (HierTestInitial)
+}
+
+__global__ void MapTrianglesToItems(const uint32_t* __restrict__ triFirst, const uint32_t* __restrict__ itemScan, const uint32_t* __restrict__ posOfOrig,
+                                    uint32_t triCount, uint32_t* __restrict__ triItem) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= triCount) return;
     const uint32_t first = triFirst[t];
-    triItem[t] = first == kNoItem ? kNoItem : itemScan[first];
+    triItem[t] = first == kNoItem ? kNoItem : posOfOrig[itemScan[first]];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1214,58 +1301,88 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
 // ---------------------------------------------------------------------------------------------------------------------
 // K6: exact dedup on digests: the lowest item index with a digest survives (ref: bake_cpu_impl.cpp:1043-1063).
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void DigestInsert(const uint64_t* __restrict__ digest, uint32_t numItems, uint64_t* keys, uint32_t* vals, uint64_t mask) {
+// Table value = the item's first triangle: monotone in the SDK's work-item index, which the output order of the items (K3b) is not.
+__global__ void DigestInsert(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, uint32_t itemBegin, uint32_t itemEnd, uint64_t* keys,
+                             uint32_t* vals, uint64_t mask) {
     // Most items of a typical bake are uniform and share a handful of digests: lanes with equal digests elect the lowest
-    // item index among themselves first, so the table sees one atomic per distinct digest per warp.
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = w < numItems;
-    const uint64_t d = valid ? digest[w] : 0ull;
+    // first triangle among themselves first, so the table sees one atomic per distinct digest per warp.
+    const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < itemEnd;
+    const uint64_t d = valid ? digest[s] : 0ull;
+    uint32_t tri = valid ? items[s].tri : 0xFFFFFFFFu;
     const uint32_t active = __ballot_sync(0xFFFFFFFFu, valid);
     if (!valid) return;
     const uint32_t peers = __match_any_sync(active, d);
-    if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) TableInsertMin(keys, vals, mask, d, w);  // lowest lane = lowest item index
+    if (__reduce_min_sync(peers, tri) == tri) TableInsertMin(keys, vals, mask, d, tri);  // first triangles are unique per item: one lane per group
 }
-__global__ void DigestResolve(const uint64_t* __restrict__ digest, uint32_t numItems, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                              uint64_t mask, int disableDup, uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= numItems) return;
-    const uint32_t s = disableDup ? w : TableFind(keys, vals, mask, digest[w]);
-    survivor[w] = s;
-    if (s != w) special[w] = -1;  // donated its primitives; never serialized (ref: :1059-1060)
+__global__ void DigestResolve(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, const uint32_t* __restrict__ triItem, uint32_t itemBegin,
+                              uint32_t itemEnd, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask, int disableDup,
+                              uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
+    const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= itemEnd) return;
+    const uint32_t v = disableDup ? s : triItem[TableFind(keys, vals, mask, digest[s])];
+    survivor[s] = v;
+    if (v != s) special[s] = -1;  // donated its primitives; never serialized (ref: :1059-1060)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K7: histograms + sort keys
+// K7: which items are serialized, where.  The items already are in output order (K3b), so the descriptor slot of an item is the
+// number of serialized items before it and its byte offset the sum of their block sizes: two prefix sums.
 // ---------------------------------------------------------------------------------------------------------------------
 // hist layout: [0..25] array histogram (format-1)*13+level, [26..51] index histogram
-__global__ void ItemHistogramAndKeys(const ItemRec* __restrict__ items, const int32_t* __restrict__ special, uint32_t numItems, uint32_t* __restrict__ hist,
-                                     uint32_t* __restrict__ sortKeys, uint32_t* __restrict__ sortVals) {
+// emit[s] / blockBytes[s] for s in [itemBegin, itemEnd]; entry itemEnd is written as zero when `closeRange` (it receives the totals of the scans)
+__global__ void EmitInfo(const ItemRec* __restrict__ items, const int32_t* __restrict__ special, uint32_t itemBegin, uint32_t itemEnd, int closeRange,
+                         int globalBitCount, uint32_t* __restrict__ hist, uint32_t* __restrict__ emit, unsigned long long* __restrict__ blockBytes) {
     __shared__ uint32_t sh[26];
     if (threadIdx.x < 26) sh[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < numItems) {
-        const ItemRec it = items[w];
-        uint32_t key = 0;  // special / merged items sort last and are never serialized
-        if (special[w] == 0) {
+    const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < itemEnd) {
+        const bool e = special[s] == 0;
+        unsigned long long bytes = 0;
+        if (e) {
+            const ItemRec it = items[s];
             atomicAdd(&sh[(it.format - 1) * 13 + it.level], 1u);
-            // ref: bake_cpu_impl.cpp:1734-1747 -- level, then Morton code of the 13-bit quantised, MirrorOnce-folded UV centroid
-            const float cx = (it.p0.x + it.p1.x + it.p2.x) / 3.f, cy = (it.p0.y + it.p1.y + it.p2.y) / 3.f;
-            const int qx = f2i(8192.f * cx), qy = f2i(8192.f * cy);
-            const int mx = clampi(f2i(fabsf((float)qx + 0.5f)), 0, 8191), my = clampi(f2i(fabsf((float)qy + 0.5f)), 0, 8191);
-            uint32_t x = (uint32_t)mx, y = (uint32_t)my;
-            x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
-            y = (y | (y << 8)) & 0x00FF00FFu; y = (y | (y << 4)) & 0x0F0F0F0Fu; y = (y | (y << 2)) & 0x33333333u; y = (y | (y << 1)) & 0x55555555u;
-            key = (((uint32_t)it.level << 26) | x | (y << 1)) + 1u;
+            // ref: bake_cpu_impl.cpp:1819 -- the global format's bit count, at least one byte
+            bytes = ((1ull << (2 * it.level)) * (unsigned long long)globalBitCount) >> 3;
+            bytes = bytes > 1 ? bytes : 1;
         }
-        // The SDK sorts (key, index) pairs descending (std::greater, :1751).  A stable descending radix sort fed in
-        // reversed index order yields the same order: equal keys keep the higher index first.
-        const uint32_t pos = numItems - 1 - w;
-        sortKeys[pos] = key;
-        sortVals[pos] = w;
+        emit[s] = e ? 1u : 0u;
+        blockBytes[s] = bytes;
+    } else if (s == itemEnd && closeRange) {
+        emit[s] = 0u;
+        blockBytes[s] = 0ull;
     }
     __syncthreads();
     if (threadIdx.x < 26 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+// Only after Compress (a18) changed the level of work items -- the level is the leading part of the sort key -- the serialized items
+// are sorted again: keys of the items without a special index, fed in reversed FIRST-SEEN order (origOf) for the SDK's tie rule.
+__global__ void ResortKeys(const ItemRec* __restrict__ items, const int32_t* __restrict__ special, const uint32_t* __restrict__ origOf, uint32_t numItems,
+                           uint32_t* __restrict__ sortKeys, uint32_t* __restrict__ sortVals) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= numItems) return;
+    const uint32_t pos = numItems - 1 - origOf[s];
+    sortKeys[pos] = special[s] == 0 ? ItemSortKey(items[s]) : 0u;  // special / merged items sort last and are never serialized
+    sortVals[pos] = s;
+}
+__global__ void ResortBlockSizes(const uint32_t* __restrict__ sortedItems, const ItemRec* __restrict__ items, uint32_t numDescs, int globalBitCount,
+                                 unsigned long long* __restrict__ blockBytes) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > numDescs) return;
+    unsigned long long bytes = 0;
+    if (k < numDescs) {
+        bytes = ((1ull << (2 * items[sortedItems[k]].level)) * (unsigned long long)globalBitCount) >> 3;
+        bytes = bytes > 1 ? bytes : 1;
+    }
+    blockBytes[k] = bytes;
+}
+__global__ void ResortScatter(const uint32_t* __restrict__ sortedItems, const unsigned long long* __restrict__ blockOffset, uint32_t numDescs,
+                              uint32_t* __restrict__ descOfItem, unsigned long long* __restrict__ offsetOfItem) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= numDescs) return;
+    descOfItem[sortedItems[k]] = k;
+    offsetOfItem[sortedItems[k]] = blockOffset[k];
 }
 
 __global__ void TriangleFinalItems(const uint32_t* __restrict__ triItem, const uint32_t* __restrict__ survivor, const uint32_t* __restrict__ mergeRoot,
@@ -1289,69 +1406,73 @@ __global__ void TriangleFinalItems(const uint32_t* __restrict__ triItem, const u
     if (threadIdx.x < 26 && sh[threadIdx.x]) atomicAdd(&hist[26 + threadIdx.x], sh[threadIdx.x]);
 }
 
-// sizes of the serialized blocks in sorted order (ref: bake_cpu_impl.cpp:1819: global format's bit count, at least one byte)
-__global__ void SortedBlockSizes(const uint32_t* __restrict__ sortedItems, const ItemRec* __restrict__ items, uint32_t numDescs, int globalBitCount,
-                                 unsigned long long* __restrict__ blockBytes, uint32_t* __restrict__ descOfItem) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= numDescs) return;
-    const uint32_t w = sortedItems[k];
-    const unsigned long long n = 1ull << (2 * items[w].level);
-    const unsigned long long bytes = (n * (unsigned long long)globalBitCount) >> 3;
-    blockBytes[k] = bytes > 1 ? bytes : 1;
-    descOfItem[w] = k;
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// K8: serialization (ref: bake_cpu_impl.cpp:1788-1821, 1856-1902).  One warp per descriptor copies / repacks the block.
+// K8: serialization (ref: bake_cpu_impl.cpp:1788-1821, 1856-1902).  One warp per work item of [itemBegin, itemEnd) that is
+// serialized: its descriptor, and its block copied / repacked (2-state = even-bit compress) to its final place.  `arrayData2`, when
+// given, receives the same bytes: the caller's host copy of the array, page-locked and mapped, written straight from here over PCIe
+// (ommCpuBake) so that the "download" of a chunk or shard runs while other items are still being classified.
 // ---------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t CompressEvenBits16(uint32_t x) {  // 16 two-bit fields -> their low bits, 16 bits
     return ExtractEvenBits(x);
 }
-__global__ void __launch_bounds__(256) WriteDescsAndPack(const uint32_t* __restrict__ sortedItems, const ItemRec* __restrict__ items,
-                                                         const unsigned long long* __restrict__ wordStart, const uint32_t* __restrict__ stateWords,
-                                                         const unsigned long long* __restrict__ blockOffset, uint32_t firstDesc, uint32_t endDesc,
-                                                         unsigned long long arrayBytes, ommCpuOpacityMicromapDesc* __restrict__ descArray,
-                                                         uint8_t* __restrict__ arrayData) {
-    const uint32_t k = firstDesc + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per descriptor of [firstDesc, endDesc)
-    if (k >= endDesc) return;
+__global__ void __launch_bounds__(256) PackItems(const ItemRec* __restrict__ items, const int32_t* __restrict__ special,
+                                                 const unsigned long long* __restrict__ wordStart, const uint32_t* __restrict__ stateWords,
+                                                 const uint32_t* __restrict__ descOfItem, const unsigned long long* __restrict__ offsetOfItem,
+                                                 const uint32_t* __restrict__ descBase, const unsigned long long* __restrict__ byteBase, uint32_t itemBegin,
+                                                 uint32_t itemEnd, unsigned long long arrayCapacity, uint8_t* __restrict__ arrayData,
+                                                 uint8_t* __restrict__ arrayData2) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t w = sortedItems[k];
-    const ItemRec it = items[w];
-    const unsigned long long off = blockOffset[k];
-    if (lane == 0) {
-        ommCpuOpacityMicromapDesc d;
-        d.offset = (uint32_t)off;
-        d.subdivisionLevel = it.level;
-        d.format = it.format;
-        descArray[k] = d;
-    }
-    const uint32_t n = 1u << (2 * it.level);
-    const uint32_t* src = stateWords + wordStart[w];
-    uint8_t* dst = arrayData + off;
-    if (it.format == ommFormat_OC1_4_State) {
-        if (n >= 16 && (off & 3) == 0) {
-            const uint32_t numWords = n >> 4;
-            if (numWords >= 4 && (off & 15) == 0 && ((wordStart[w] & 3) == 0)) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(src);
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
-                for (uint32_t i = lane; i < (numWords >> 2); i += 32) d4[i] = __ldg(s4 + i);
+    for (uint32_t w = itemBegin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < itemEnd; w += gridDim.x * (blockDim.x >> 5)) {
+        if (special[w] != 0) continue;
+        const ItemRec it = items[w];
+        const unsigned long long off = offsetOfItem[w] + (byteBase ? *byteBase : 0ull);
+        const uint32_t n = 1u << (2 * it.level);
+        const uint32_t* src = stateWords + wordStart[w];
+        uint8_t* dst = arrayData + off;
+        uint8_t* dst2 = arrayData2 ? arrayData2 + off : nullptr;
+        if (it.format == ommFormat_OC1_4_State) {
+            if (n >= 16 && (off & 3) == 0) {
+                const uint32_t numWords = n >> 4;
+                if (numWords >= 4 && (off & 15) == 0 && ((wordStart[w] & 3) == 0)) {
+                    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+                    uint4* d4 = reinterpret_cast<uint4*>(dst);
+                    uint4* e4 = reinterpret_cast<uint4*>(dst2);
+                    for (uint32_t i = lane; i < (numWords >> 2); i += 32) {
+                        const uint4 v = __ldg(s4 + i);
+                        d4[i] = v;
+                        if (e4) e4[i] = v;
+                    }
+                } else {
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+                    uint32_t* e32 = reinterpret_cast<uint32_t*>(dst2);
+                    for (uint32_t i = lane; i < numWords; i += 32) {
+                        const uint32_t v = __ldg(src + i);
+                        d32[i] = v;
+                        if (e32) e32[i] = v;
+                    }
+                }
             } else {
-                uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-                for (uint32_t i = lane; i < numWords; i += 32) d32[i] = __ldg(src + i);
+                const uint32_t numBytes = n >= 4 ? n >> 2 : 1;
+                const uint32_t byteMask = n >= 4 ? 0xFFu : ((1u << (2 * n)) - 1u);  // level 0: one 2-bit state in the byte
+                for (uint32_t b = lane; b < numBytes; b += 32)
+                    if (off + b < arrayCapacity) {
+                        const uint8_t v = (uint8_t)((__ldg(src + (b >> 2)) >> ((b & 3) * 8)) & byteMask);
+                        dst[b] = v;
+                        if (dst2) dst2[b] = v;
+                    }
             }
         } else {
-            const uint32_t numBytes = n >= 4 ? n >> 2 : 1;
-            const uint32_t byteMask = n >= 4 ? 0xFFu : ((1u << (2 * n)) - 1u);  // level 0: one 2-bit state in the byte
-            for (uint32_t b = lane; b < numBytes; b += 32)
-                if (off + b < arrayBytes) dst[b] = (uint8_t)((__ldg(src + (b >> 2)) >> ((b & 3) * 8)) & byteMask);
-        }
-    } else {
-        // 2-state: one bit per micro-triangle (the state's low bit)
-        const uint32_t numBytes = n >= 8 ? n >> 3 : 1;
-        const uint32_t byteMask = n >= 8 ? 0xFFu : ((1u << n) - 1u);  // levels 0/1: 1 or 4 one-bit states in the byte
-        for (uint32_t b = lane; b < numBytes; b += 32) {
-            const uint32_t bits = CompressEvenBits16(__ldg(src + (b >> 1)));
-            if (off + b < arrayBytes) dst[b] = (uint8_t)((bits >> ((b & 1) * 8)) & byteMask);
+            // 2-state: one bit per micro-triangle (the state's low bit)
+            const uint32_t numBytes = n >= 8 ? n >> 3 : 1;
+            const uint32_t byteMask = n >= 8 ? 0xFFu : ((1u << n) - 1u);  // levels 0/1: 1 or 4 one-bit states in the byte
+            for (uint32_t b = lane; b < numBytes; b += 32) {
+                const uint32_t bits = CompressEvenBits16(__ldg(src + (b >> 1)));
+                if (off + b < arrayCapacity) {
+                    const uint8_t v = (uint8_t)((bits >> ((b & 1) * 8)) & byteMask);
+                    dst[b] = v;
+                    if (dst2) dst2[b] = v;
+                }
+            }
         }
     }
 }
@@ -2011,30 +2132,6 @@ ommResult ComputeShardBounds(const unsigned long long* unitStart, uint32_t entri
 int ShardsPerRankOf(int world) { return world < 1 ? 0 : ShardsPerRank(world); }
 int ShardOwnerOf(int shard, int world) { return (world < 1 || shard < 0) ? -1 : ShardOwner(shard, world); }
 
-// ---- multi-GPU exchange of the state blocks that can still be serialized (items without a special index) ------------------------
-__global__ void CompactSizes(const int32_t* __restrict__ special, const unsigned long long* __restrict__ itemWords, uint32_t numItems,
-                             unsigned long long* __restrict__ compactWords) {
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w <= numItems) compactWords[w] = (w < numItems && special[w] == 0) ? itemWords[w] : 0ull;
-}
-__global__ void CompactBoundsKernel(const unsigned long long* __restrict__ compactStart, const ShardBound* __restrict__ bounds, int world,
-                                    unsigned long long* __restrict__ out) {
-    const int r = threadIdx.x;
-    if (r <= world) out[r] = compactStart[bounds[r].item];
-}
-// one warp per item of this rank: copy the block of a non-special item to its place in the compact buffer
-__global__ void __launch_bounds__(256) CompactCopy(const int32_t* __restrict__ special, const unsigned long long* __restrict__ itemWords,
-                                                   const unsigned long long* __restrict__ wordStart, const unsigned long long* __restrict__ compactStart,
-                                                   const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, uint32_t* __restrict__ compact) {
-    const uint32_t w = itemBegin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= itemEnd || special[w] != 0) return;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint4* src = reinterpret_cast<const uint4*>(stateWords + wordStart[w]);
-    uint4* dst = reinterpret_cast<uint4*>(compact + compactStart[w]);
-    const unsigned long long n16 = itemWords[w] >> 2;  // blocks are multiples of four words
-    for (unsigned long long i = lane; i < n16; i += 32) dst[i] = __ldg(src + i);
-}
-
 // workload metric of the SDK (ref: bake_cpu_impl.cpp:662-680): sum over work items of int(aabb.x*texW) * int(aabb.y*texH)
 __global__ void WorkloadKernel(const ItemRec* __restrict__ items, uint32_t numItems, float texW, float texH, unsigned long long* __restrict__ total) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2085,6 +2182,136 @@ static const char* SpecialIndexText(int s) {  // ref: log.h:20-31
     }
 }
 
+// ---- host side of a sharding on one box: a control block and result windows in POSIX shared memory -------------------------------
+struct ShmControl {
+    std::atomic<uint32_t> barCount, barGen;  // sense-reversing barrier of the ranks' host threads
+    std::atomic<unsigned long long> failSeq; // bakeSeq of the last bake in which some rank could not write its part of the window
+    std::atomic<unsigned long long> winSeq;  // bakeSeq for which winId / winCapacity were published by the root
+    int winId;
+    unsigned long long winCapacity;
+};
+static_assert(std::atomic<uint32_t>::is_always_lock_free && std::atomic<unsigned long long>::is_always_lock_free, "atomics in shared memory must be address-free");
+static void ShmName(char* out, size_t n, unsigned long long idHash, const char* what, int id) { snprintf(out, n, "/ommb200_%016llx_%s%d", idHash, what, id); }
+static bool HostBarrier(ShardState& sh, double timeoutSeconds = 120.0) {
+    ShmControl* c = sh.ctl;
+    if (!c) return false;
+    const uint32_t gen = c->barGen.load(std::memory_order_acquire);
+    if (c->barCount.fetch_add(1, std::memory_order_acq_rel) + 1 == (uint32_t)sh.world) {
+        c->barCount.store(0, std::memory_order_relaxed);
+        c->barGen.store(gen + 1, std::memory_order_release);
+        return true;
+    }
+    const double t0 = HostTrace::Now();
+    for (uint32_t spins = 0; c->barGen.load(std::memory_order_acquire) == gen; ++spins) {
+        if ((spins & 1023u) == 1023u) {
+            sched_yield();
+            if (HostTrace::Now() - t0 > timeoutSeconds * 1e3) return false;  // a rank died: fail instead of hanging
+        }
+    }
+    return true;
+}
+static void* MapShm(const char* name, size_t bytes, bool create) {
+    const int fd = shm_open(name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    if (create && ftruncate(fd, (off_t)bytes) != 0) {
+        close(fd);
+        return nullptr;
+    }
+    if (!create) {  // the creator may not have sized it yet
+        struct stat st;
+        for (int i = 0; i < 20000 && (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes); ++i) usleep(100);
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    return p == MAP_FAILED ? nullptr : p;
+}
+// The window the root's host copy of this bake's arrayData lives in (every rank returns its own mapping of the same memory).
+static SharedHostWindow* AcquireSharedWindow(ShardState& sh, size_t bytes, const Logger& log) {
+    ShmControl* c = sh.ctl;
+    if (!c) return nullptr;
+    char name[96];
+    if (sh.rank == 0) {
+        SharedHostWindow* best = nullptr;
+        for (SharedHostWindow& w : sh.windows)
+            if (!w.inUse && w.capacity >= bytes && (!best || w.capacity < best->capacity)) best = &w;
+        if (!best) {
+            SharedHostWindow w;
+            w.id = (int)sh.windows.size();
+            w.capacity = (bytes + (bytes >> 3) + ((size_t)2 << 20)) & ~(((size_t)2 << 20) - 1);
+            ShmName(name, sizeof(name), sh.idHash, "w", w.id);
+            shm_unlink(name);
+            w.ptr = MapShm(name, w.capacity, true);
+            if (w.ptr && cudaHostRegister(w.ptr, w.capacity, cudaHostRegisterPortable) != cudaSuccess) {
+                cudaGetLastError();
+                munmap(w.ptr, w.capacity);
+                shm_unlink(name);
+                w.ptr = nullptr;
+            }
+            if (!w.ptr) log.Log(ommMessageSeverity_Fatal, "[omm-b200] could not create the shared page-locked result window (shm_open / cudaHostRegister)");
+            else {
+                sh.windows.push_back(w);
+                best = &sh.windows.back();
+            }
+        }
+        // publish (id -1: no window; the ranks then fall back to the root's own download)
+        c->winId = best ? best->id : -1;
+        c->winCapacity = best ? best->capacity : 0;
+        c->winSeq.store(sh.bakeSeq, std::memory_order_release);
+        if (best) best->inUse = true;
+        return best;
+    }
+    const double t0 = HostTrace::Now();
+    for (uint32_t spins = 0; c->winSeq.load(std::memory_order_acquire) != sh.bakeSeq; ++spins)
+        if ((spins & 1023u) == 1023u) {
+            sched_yield();
+            if (HostTrace::Now() - t0 > 120e3) return nullptr;
+        }
+    const int id = c->winId;
+    const size_t capacity = (size_t)c->winCapacity;
+    if (id < 0) return nullptr;
+    for (SharedHostWindow& w : sh.windows)
+        if (w.id == id) return &w;
+    SharedHostWindow w;
+    w.id = id;
+    w.capacity = capacity;
+    ShmName(name, sizeof(name), sh.idHash, "w", id);
+    w.ptr = MapShm(name, capacity, false);
+    if (w.ptr && cudaHostRegister(w.ptr, capacity, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        munmap(w.ptr, capacity);
+        w.ptr = nullptr;
+    }
+    if (!w.ptr) {
+        log.Log(ommMessageSeverity_Fatal, "[omm-b200] could not map the shared page-locked result window");
+        return nullptr;
+    }
+    sh.windows.push_back(w);
+    return &sh.windows.back();
+}
+void ReleaseSharedWindow(BakerObject* baker, int windowId) {
+    std::lock_guard<std::mutex> g(baker->mu);
+    for (SharedHostWindow& w : baker->shard.windows)
+        if (w.id == windowId) w.inUse = false;
+}
+
+__global__ void WriteDescs(const ItemRec* __restrict__ items, const int32_t* __restrict__ special, const uint32_t* __restrict__ descOfItem,
+                           const unsigned long long* __restrict__ offsetOfItem, uint32_t itemBegin, uint32_t itemEnd,
+                           ommCpuOpacityMicromapDesc* __restrict__ descArray) {
+    const uint32_t w = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= itemEnd || special[w] != 0) return;
+    ommCpuOpacityMicromapDesc d;
+    d.offset = (uint32_t)offsetOfItem[w];
+    d.subdivisionLevel = items[w].level;
+    d.format = items[w].format;
+    descArray[descOfItem[w]] = d;
+}
+// byte offset in arrayData at which the blocks of shard r start (r = 0..shards; the last entry is the array size)
+__global__ void ShardByteOffsets(const unsigned long long* __restrict__ offsetOfItem, const ShardBound* __restrict__ bounds, int shards,
+                                 unsigned long long* __restrict__ out) {
+    const int r = threadIdx.x;
+    if (r <= shards) out[r] = offsetOfItem[bounds[r].item];
+}
+
 ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* tm, bool earlyDownload) {
     const Logger& log = baker->log;
     ommResult rc = RequireDevice(log, baker->device);
@@ -2099,6 +2326,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     const bool validation = (flags & ommCpuBakeFlags_EnableValidation) != 0;
     const bool limitWorkload = d.maxWorkloadSize != 0xFFFFFFFFFFFFFFFFull;
     const int world = baker->shard.world, rank = baker->shard.rank;
+    const bool hostPasses = HostPassesNeeded(d);
     const int TPB = 256;
     uint32_t launches = 0;
 
@@ -2117,11 +2345,12 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     int8_t* triLevel = nullptr;
     uint8_t *triFormat = nullptr, *triDegenerate = nullptr;
     HostLevelFix* fixList = nullptr;
-    uint32_t* counters = nullptr;  // [0] edge-heuristic fix count, [1] disabled triangles, [8..23] work items per level
+    uint32_t* counters = nullptr;  // [0] edge-heuristic fix count, [1] disabled triangles, [2] work items, [8..23] work items per level
     unsigned long long* workloadDev = nullptr;
     uint64_t *triKey = nullptr, *tableKeys = nullptr;
     uint32_t *tableVals = nullptr, *triFirst = nullptr, *isItem = nullptr, *itemScan = nullptr, *triItem = nullptr, *triFinal = nullptr;
-    ItemRec* items = nullptr;
+    ItemRec *itemsW = nullptr, *items = nullptr;  // first-seen order (the SDK's vmWorkItems order) / output order (K3b)
+    uint32_t *posOfOrig = nullptr, *origOf = nullptr;
     unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr, *itemNodes = nullptr, *nodeStart = nullptr;
     ShardBound* boundsDev = nullptr;
     uint32_t* chunkFirstDev = nullptr;
@@ -2130,30 +2359,34 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     OwnedShards owned{};
     const unsigned long long hierChunkRegions = HierNominalChunkRegions(baker->device);
     uint32_t* stateWords = nullptr;
-    uint32_t* compactWords = nullptr;                // sharded bakes: blocks of the items without a special index, see the exchange
-    unsigned long long* compactStart = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;
     int32_t* special = nullptr;
     uint32_t *mergeRoot = nullptr, *survivor2 = nullptr;
-    uint32_t *survivor = nullptr, *hist = nullptr, *sortKeysIn = nullptr, *sortValsIn = nullptr, *sortKeysOut = nullptr, *sortValsOut = nullptr,
-             *descOfItem = nullptr;
-    unsigned long long *blockBytes = nullptr, *blockOffset = nullptr;
+    uint32_t *survivor = nullptr, *hist = nullptr, *sortKeysIn = nullptr, *sortValsIn = nullptr, *sortKeysOut = nullptr, *emit = nullptr, *descOfItem = nullptr;
+    unsigned long long *blockBytes = nullptr, *offsetOfItem = nullptr, *shardOffDev = nullptr;
     unsigned long long totalUnits = 0, totalWords = 0, microTris = 0, myMicroTris = 0;
+    unsigned long long shardOff[kMaxShards + 1];
     uint32_t W = 0;
     uint32_t countersHost[32];
     uint32_t histHost[52];
-    ShardBound bounds[65];
+    ShardBound bounds[kMaxShards + 1];
     uint32_t numDescs = 0;
     unsigned long long arrayBytes = 0;
     int indexBytes = 4;
+    bool resort = false;  // Compress changed item levels: the serialized items are sorted again (see ResortKeys)
+    SharedHostWindow* window = nullptr;  // sharded ommCpuBake: the root's host copy of arrayData, written by every rank
+    bool windowProtocol = false;         // this bake takes part in the window hand-shake (every rank decides alike)
+    unsigned long long sharedD2hBytes = 0;
     const uint32_t gridT = (T + TPB - 1) / TPB;
+    int sms = 1;
 
     BakeParams P{};
     SetupArgs sa{};
     memset(histHost, 0, sizeof(histHost));
     memset(countersHost, 0, sizeof(countersHost));
     memset(bounds, 0, sizeof(bounds));
+    memset(shardOff, 0, sizeof(shardOff));
 
     if (world > kMaxShards) return ommResult_INVALID_ARGUMENT;
     for (int v = 0; v < numShards; ++v)
@@ -2166,8 +2399,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         ownStream = true;
     }
     scratch.stream = stream;
+    NvtxRange nvtxBake("omm-b200 bake");
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
     CUDA_TRY(cudaEventRecord(ev[0], stream));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
     HostTrace::Mark("stream + events created");
 
     // ---- parameters ----
@@ -2186,7 +2421,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     P.disableFine = (flags & (1u << 9)) != 0;
     P.disableLevelLine = (flags & (1u << 8)) != 0;
     P.aabbTesting = (flags & (1u << 7)) != 0;
-    P.skipUniformFill = (flags & ommCpuBakeFlags_DisableSpecialIndices) == 0 && !HostPassesNeeded(d);
+    P.skipUniformFill = (flags & ommCpuBakeFlags_DisableSpecialIndices) == 0 && !hostPasses;
 
     sa.indices = in.devIndices;
     sa.texCoords = in.devTexCoords;
@@ -2206,6 +2441,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     // ---- K1: triangles ----
     if (T > 0) {
+        NvtxRange nvtxSetup("setup: triangles, UV pre-dedup, work items in output order");
         CUDA_TRY(scratch.alloc(&triUV, (size_t)3 * T));
         CUDA_TRY(scratch.alloc(&triLevel, T));
         CUDA_TRY(scratch.alloc(&triFormat, T));
@@ -2219,7 +2455,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&itemScan, T));
         CUDA_TRY(scratch.alloc(&triItem, T));
         CUDA_TRY(scratch.alloc(&triFinal, T));
-        CUDA_TRY(scratch.alloc(&boundsDev, 65));
+        CUDA_TRY(scratch.alloc(&boundsDev, kMaxShards + 1));
         CUDA_TRY(scratch.alloc(&chunkFirstDev, (size_t)kMaxShardsPerRank * (kHierMaxChunks + 1)));
         CUDA_TRY(cudaMemsetAsync(counters, 0, 32 * sizeof(uint32_t), stream));
         CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
@@ -2275,19 +2511,30 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, isItem, itemScan, (int)T, stream));
             launches += 2;
         }
+        CUDA_TRY(scratch.alloc(&itemsW, T));
         CUDA_TRY(scratch.alloc(&items, T));
+        CUDA_TRY(scratch.alloc(&posOfOrig, T));
+        CUDA_TRY(scratch.alloc(&origOf, T));
+        CUDA_TRY(scratch.alloc(&sortKeysIn, T));
+        CUDA_TRY(scratch.alloc(&sortValsIn, T));
+        CUDA_TRY(scratch.alloc(&sortKeysOut, T));
         CUDA_TRY(scratch.alloc(&itemUnits, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&itemWords, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&unitStart, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&wordStart, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&itemNodes, (size_t)T + 1));
         CUDA_TRY(scratch.alloc(&nodeStart, (size_t)T + 1));
-        CUDA_TRY(cudaMemsetAsync(itemNodes, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
-        CUDA_TRY(cudaMemsetAsync(itemUnits, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
-        CUDA_TRY(cudaMemsetAsync(itemWords, 0, sizeof(unsigned long long) * ((size_t)T + 1), stream));
-        BuildItems<<<gridT, TPB, 0, stream>>>(triUV, triLevel, triFormat, triDegenerate, isItem, itemScan, T, items, itemUnits, itemWords, itemNodes, counters + 8);
-        MapTrianglesToItems<<<gridT, TPB, 0, stream>>>(triFirst, itemScan, T, triItem);
-        launches += 2;
+        BuildItems<<<gridT, TPB, 0, stream>>>(triUV, triLevel, triFormat, triDegenerate, isItem, itemScan, T, itemsW, counters + 8, counters + 2);
+        // ---- K3b: output order first (see ItemSortKey) ----
+        ItemKeysAll<<<gridT, TPB, 0, stream>>>(itemsW, counters + 2, T, sortKeysIn, sortValsIn);
+        {
+            size_t tmp = cubTempBytes;
+            // bits [0, 31): the key is (level < 13) << 26 | 26 Morton bits, plus one
+            CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(cubTemp, tmp, sortKeysIn, sortKeysOut, sortValsIn, origOf, (int)T, 0, 31, stream));
+        }
+        PermuteItems<<<(T + 1 + TPB - 1) / TPB, TPB, 0, stream>>>(itemsW, origOf, counters + 2, T, items, posOfOrig, itemUnits, itemWords, itemNodes);
+        MapTrianglesToItems<<<gridT, TPB, 0, stream>>>(triFirst, itemScan, posOfOrig, T, triItem);
+        launches += 4 + 8;
         {
             // exclusive scans over T+1 entries: entry [W] (and everything after it) holds the grand total
             size_t tmp = cubTempBytes;
@@ -2337,6 +2584,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     // ---- K4: classification of this rank's shard of work items ----
     if (W > 0) {
+        NvtxRange nvtxClassify("classify + per-item post pass");
         uint32_t myItems = 0;
         for (int k = 0; k < owned.count; ++k) myItems += bounds[owned.shard[k] + 1].item - bounds[owned.shard[k]].item;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
@@ -2361,8 +2609,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
-            int sms = 0;
-            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
             const uint32_t listGrid = (uint32_t)std::max(sms, 1) * 16u;
             for (int k = 0; k < owned.count; ++k) {
                 const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
@@ -2415,6 +2661,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
         CUDA_TRY(cudaEventRecord(ev[5], stream));  // end of the per-item post pass
         if (world > 1) {
+            // ---- the exchange, part 1: 12 bytes per work item (digest + special index), one group of broadcasts rooted at the shard owners ----
             // exact share of micro-triangles classified on this rank
             CUDA_TRY(cudaMemsetAsync(workloadDev, 0, sizeof(unsigned long long), stream));
             for (int k = 0; k < owned.count; ++k) {
@@ -2431,13 +2678,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 goto cleanup;
             }
             const ncclComm_t comm = (ncclComm_t)baker->shard.ncclComm;
-            const bool fullBlocks = HostPassesNeeded(d);  // the host passes read and rewrite every block
             bool ncclOk = nccl.GroupStart() == ncclSuccess;
             for (int r = 0; r < numShards && ncclOk; ++r) {  // one broadcast per shard, rooted at its owner
                 const int root = ShardOwner(r, world);
+                // the optional host passes (a17 / a18) read and rewrite every block on every rank: then the state words travel as well
                 const size_t count = (size_t)(bounds[r + 1].word - bounds[r].word);
                 uint32_t* seg = stateWords + bounds[r].word;
-                if (fullBlocks && count) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint32, root, comm, stream) == ncclSuccess;
+                if (hostPasses && count) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint32, root, comm, stream) == ncclSuccess;
                 const size_t nItems = bounds[r + 1].item - bounds[r].item;
                 if (ncclOk && nItems) {
                     ncclOk = nccl.Broadcast(digest + bounds[r].item, digest + bounds[r].item, nItems, ncclUint64, root, comm, stream) == ncclSuccess;
@@ -2449,42 +2696,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&gatherEv[i]));
                 CUDA_TRY(cudaEventRecord(gatherEv[0], stream));
             }
-            if (ncclOk && !fullBlocks) {
-                // Only blocks of items WITHOUT a special index can reach the output array: every rank packs those of its own items
-                // into a compact buffer laid out by a prefix sum all ranks compute alike, and the all-gather moves just these
-                // (28 % of the state words at config 3).  The serializer then reads the compact buffer.
-                unsigned long long* compactSizes = nullptr;
-                unsigned long long* compactBoundsDev = nullptr;
-                unsigned long long compactBounds[65];
-                CUDA_TRY(scratch.alloc(&compactSizes, (size_t)W + 1));
-                CUDA_TRY(scratch.alloc(&compactStart, (size_t)W + 1));
-                CUDA_TRY(scratch.alloc(&compactBoundsDev, 65));
-                CUDA_TRY(scratch.alloc(&compactWords, (size_t)totalWords + 4));
-                CompactSizes<<<(W + 1 + TPB - 1) / TPB, TPB, 0, stream>>>(special, itemWords, W, compactSizes);
-                size_t tmp = cubTempBytes;
-                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, compactSizes, compactStart, (int)W + 1, stream));
-                CompactBoundsKernel<<<1, 96, 0, stream>>>(compactStart, boundsDev, numShards, compactBoundsDev);
-                for (int k = 0; k < owned.count; ++k) {
-                    const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
-                    if (itemEnd > itemBegin)
-                        CompactCopy<<<(itemEnd - itemBegin + 7) / 8, 256, 0, stream>>>(special, itemWords, wordStart, compactStart, stateWords, itemBegin, itemEnd, compactWords);
-                }
-                launches += 6;
-                if (gatherEv[1]) CUDA_TRY(cudaEventRecord(gatherEv[1], stream));
-                CUDA_TRY(cudaMemcpyAsync(compactBounds, compactBoundsDev, sizeof(unsigned long long) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
-                CUDA_TRY(cudaStreamSynchronize(stream));
-                HostTrace::Mark("    exchange: compact bounds read (host sync)");
-                ncclOk = nccl.GroupStart() == ncclSuccess;
-                for (int r = 0; r < numShards && ncclOk; ++r) {
-                    const size_t count = (size_t)(compactBounds[r + 1] - compactBounds[r]);
-                    if (count)
-                        ncclOk = nccl.Broadcast(compactWords + compactBounds[r], compactWords + compactBounds[r], count, ncclUint32, ShardOwner(r, world), comm, stream) == ncclSuccess;
-                }
-                ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
-                if (gatherEv[2]) CUDA_TRY(cudaEventRecord(gatherEv[2], stream));
-            }
             if (!ncclOk) {
-                log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL all-gather of the state blocks failed");
+                log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL all-gather of the per-item records failed");
                 rc = ommResult_FAILURE;
                 goto cleanup;
             }
@@ -2493,30 +2706,30 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     CUDA_TRY(cudaEventRecord(ev[2], stream));
     HostTrace::Mark("classify + post launched");
 
-    // ---- K5..K7: post ----
+    // ---- K6, K7: exact dedup, descriptor slots and byte offsets (replicated on every rank of a sharded bake) ----
     if (W > 0) {
-        const uint32_t gridW = (W + TPB - 1) / TPB;
+        NvtxRange nvtxMerge("dedup + offsets");
+        const uint32_t gridW = (W + TPB - 1) / TPB, gridW1 = (W + 1 + TPB - 1) / TPB;
         CUDA_TRY(scratch.alloc(&survivor, W));
         CUDA_TRY(scratch.alloc(&hist, 64));
-        CUDA_TRY(scratch.alloc(&sortKeysIn, W));
-        CUDA_TRY(scratch.alloc(&sortValsIn, W));
-        CUDA_TRY(scratch.alloc(&sortKeysOut, W));
-        CUDA_TRY(scratch.alloc(&sortValsOut, W));
-        CUDA_TRY(scratch.alloc(&descOfItem, W));
+        CUDA_TRY(scratch.alloc(&emit, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&descOfItem, (size_t)W + 1));
         CUDA_TRY(scratch.alloc(&blockBytes, (size_t)W + 1));
-        CUDA_TRY(scratch.alloc(&blockOffset, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&offsetOfItem, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&shardOffDev, kMaxShards + 1));
         CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
         const uint64_t cap = NextPow2((uint64_t)W * 2 + 16);
         if (!disableDup) {
             // the UV table (capacity >= 2T+16 >= 2W+16) is reused for the digests
             FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
-            DigestInsert<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1);
+            DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, 0, W, tableKeys, tableVals, cap - 1);
             launches += 2;
         }
-        DigestResolve<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
+        DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
         launches++;
-        if (HostPassesNeeded(d)) {
-            // ---- a17 / a18: near-duplicate merge and size-budget compression run on the host (omm_host_passes.cpp) ----
+        if (hostPasses) {
+            // ---- a17 / a18: near-duplicate merge and size-budget compression (omm_host_passes.cpp).  Both walk the work items in the
+            // SDK's first-seen order, so the host side sees them through posOfOrig. ----
             uint32_t* primCount = nullptr;
             uint8_t* levelsDev = nullptr;
             CUDA_TRY(scratch.alloc(&primCount, W));
@@ -2528,35 +2741,40 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches++;
             std::vector<ItemRec> hItems(W);
             std::vector<int32_t> hSpecial(W);
-            std::vector<uint32_t> hPrims(W), hRoot(W), hWords((size_t)totalWords);
-            std::vector<unsigned long long> hWordStart((size_t)W + 1);
+            std::vector<uint32_t> hPrims(W), hRoot(W), hPos(W), hWords((size_t)totalWords);
+            std::vector<unsigned long long> hWordStart((size_t)W + 1), hWordStartW(W);
             std::vector<uint8_t> hLevels(W);
             std::vector<HostPassItem> hp(W);
             CUDA_TRY(cudaMemcpyAsync(hItems.data(), items, sizeof(ItemRec) * W, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hSpecial.data(), special, sizeof(int32_t) * W, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hPrims.data(), primCount, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(hPos.data(), posOfOrig, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hWordStart.data(), wordStart, sizeof(unsigned long long) * ((size_t)W + 1), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hWords.data(), stateWords, sizeof(uint32_t) * (size_t)totalWords, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
             for (uint32_t w = 0; w < W; ++w) {
+                const uint32_t s = hPos[w];
                 HostPassItem& it = hp[w];
-                it.level = hItems[w].level;
-                it.format = hItems[w].format;
-                it.uv[0] = hItems[w].p0.x; it.uv[1] = hItems[w].p0.y; it.uv[2] = hItems[w].p1.x; it.uv[3] = hItems[w].p1.y;
-                it.uv[4] = hItems[w].p2.x; it.uv[5] = hItems[w].p2.y;
-                it.numPrims = hPrims[w];
-                it.special = hSpecial[w];
+                it.level = hItems[s].level;
+                it.format = hItems[s].format;
+                it.uv[0] = hItems[s].p0.x; it.uv[1] = hItems[s].p0.y; it.uv[2] = hItems[s].p1.x; it.uv[3] = hItems[s].p1.y;
+                it.uv[4] = hItems[s].p2.x; it.uv[5] = hItems[s].p2.y;
+                it.numPrims = hPrims[s];
+                it.special = hSpecial[s];
                 it.mergedInto = w;
                 it.statesChanged = false;
+                hWordStartW[w] = hWordStart[s];
             }
-            rc = RunHostPasses(d, hp.data(), W, hWords.data(), hWordStart.data());
+            rc = RunHostPasses(d, hp.data(), W, hWords.data(), hWordStartW.data());
             if (rc != ommResult_SUCCESS) goto cleanup;
             for (uint32_t w = 0; w < W; ++w) {
                 uint32_t r = w;
                 while (hp[r].mergedInto != r) r = hp[r].mergedInto;
-                hRoot[w] = r;
-                hSpecial[w] = hp[w].special;
-                hLevels[w] = (uint8_t)hp[w].level;
+                const uint32_t s = hPos[w];
+                hRoot[s] = hPos[r];
+                hSpecial[s] = hp[w].special;
+                hLevels[s] = (uint8_t)hp[w].level;
+                resort = resort || hp[w].level != hItems[s].level;
             }
             CUDA_TRY(cudaMemcpyAsync(stateWords, hWords.data(), sizeof(uint32_t) * (size_t)totalWords, cudaMemcpyHostToDevice, stream));
             CUDA_TRY(cudaMemcpyAsync(special, hSpecial.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, stream));
@@ -2571,24 +2789,28 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches += 2;
             if (!disableDup) {
                 FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
-                DigestInsert<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1);
+                DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, 0, W, tableKeys, tableVals, cap - 1);
                 launches += 2;
             }
-            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, W, tableKeys, tableVals, cap - 1, disableDup, survivor2, special);
+            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, survivor2, special);
             launches++;
             CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors above must outlive the copies
         }
-        ItemHistogramAndKeys<<<gridW, TPB, 0, stream>>>(items, special, W, hist, sortKeysIn, sortValsIn);
+        // serialized items, their descriptor slots and byte offsets: prefix sums in output order
+        EmitInfo<<<gridW1, TPB, 0, stream>>>(items, special, 0, W, 1, (int)d.format, hist, emit, blockBytes);
         TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, mergeRoot, survivor2, items, special, T, triFinal, hist);
-        launches += 2;
         {
             size_t tmp = cubTempBytes;
-            CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(cubTemp, tmp, sortKeysIn, sortKeysOut, sortValsIn, sortValsOut, (int)W, 0, 32, stream));
-            launches += 8;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, emit, descOfItem, (int)W + 1, stream));
+            tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, offsetOfItem, (int)W + 1, stream));
         }
+        ShardByteOffsets<<<1, 96, 0, stream>>>(offsetOfItem, boundsDev, numShards, shardOffDev);
+        launches += 7;
         CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(shardOff, shardOffDev, sizeof(unsigned long long) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-    HostTrace::Mark("    histograms read (host sync 2)");
+        HostTrace::Mark("    histograms read (host sync 2)");
     }
 
     // ---- sizes (ref: bake_cpu_impl.cpp:1763-1777) ----
@@ -2605,7 +2827,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         for (int i = 0; i < 26; ++i) numDescs += histHost[i];
         if (numDescs != globalFormatDescs) {
             // The SDK sizes its arrays from the global format only and then walks every item (undefined behaviour with mixed
-            // per-triangle formats, SURVEY 7 "reference quirks").  Refuse instead of overrunning.
+            // per-triangle formats, SURVEY 7 "reference quirks").  Refused at staging already; kept as a guard.
             log.Log(ommMessageSeverity_Fatal, "[omm-b200] per-triangle formats that differ from desc.format are not supported");
             rc = ommResult_FAILURE;
             goto cleanup;
@@ -2619,6 +2841,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     // ---- K8: serialize ----
     {
+        NvtxRange nvtxPack("pack + index buffer");
         const bool allow8 = (flags & ommCpuBakeFlags_Allow8BitIndices) != 0, force32 = (flags & ommCpuBakeFlags_Force32BitIndices) != 0;
         ommIndexFormat ifmt = ommIndexFormat_UINT_32;  // ref: :1873-1902
         if (allow8 && (int32_t)T <= 127 && !force32) { ifmt = ommIndexFormat_UINT_8; indexBytes = 1; }
@@ -2630,50 +2853,117 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         res->indexFormat = ifmt;
         CUDA_TRY(cudaMallocAsync(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4, stream));
         if (numDescs) {
+            const uint32_t packGridMax = (uint32_t)std::max(sms, 1) * 32u;
             CUDA_TRY(cudaMallocAsync(&res->devArrayData, (size_t)arrayBytes + 16, stream));
             CUDA_TRY(cudaMallocAsync(&res->devDescArray, (size_t)numDescs * sizeof(ommCpuOpacityMicromapDesc), stream));
-            SortedBlockSizes<<<(numDescs + TPB - 1) / TPB, TPB, 0, stream>>>(sortValsOut, items, numDescs, (int)d.format, blockBytes, descOfItem);
-            size_t tmp = cubTempBytes;
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, blockOffset, (int)numDescs, stream));
-            // after a sharded bake the blocks of serializable items live in the compact exchange buffer
-            // The caller wants the result in host memory (ommCpuBake): pack the array in slices of descriptors and send each slice
-            // over PCIe while the next one is packed; the 8-byte slice boundaries are read back first.  Page-locked destination only
-            // (a pageable one makes the copies synchronous).
-            constexpr uint32_t kPackSlices = 8;
-            unsigned long long sliceOffset[kPackSlices + 1];
-            uint32_t sliceDesc[kPackSlices + 1];
-            uint32_t slices = 1;
-            sliceDesc[0] = 0; sliceOffset[0] = 0;
-            if (earlyDownload && arrayBytes >= ((size_t)8 << 20) && numDescs >= 64 * kPackSlices && AllocHostArrayData(res) && res->arrayDataFromPinnedPool) {
-                slices = kPackSlices;
-                for (uint32_t i = 1; i < slices; ++i) {
-                    sliceDesc[i] = (uint32_t)((unsigned long long)numDescs * i / slices);
-                    CUDA_TRY(cudaMemcpyAsync(&sliceOffset[i], blockOffset + sliceDesc[i], 8, cudaMemcpyDeviceToHost, stream));
-                }
-                CUDA_TRY(cudaStreamSynchronize(stream));
-                CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
-                CUDA_TRY(cudaEventCreate(&copyEv[0]));
-                CUDA_TRY(cudaEventCreate(&copyEv[1]));
-                CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+            if (resort) {
+                // Compress lowered the level of some items and with it their sort keys: order the serialized items again
+                uint32_t* resortVals = nullptr;
+                unsigned long long* blockOffset = nullptr;
+                CUDA_TRY(scratch.alloc(&resortVals, W));
+                CUDA_TRY(scratch.alloc(&blockOffset, (size_t)numDescs + 1));
+                ResortKeys<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, special, origOf, W, sortKeysIn, sortValsIn);
+                size_t tmp = cubTempBytes;
+                CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(cubTemp, tmp, sortKeysIn, sortKeysOut, sortValsIn, resortVals, (int)W, 0, 31, stream));
+                ResortBlockSizes<<<(numDescs + 1 + TPB - 1) / TPB, TPB, 0, stream>>>(resortVals, items, numDescs, (int)d.format, blockBytes);
+                tmp = cubTempBytes;
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, blockOffset, (int)numDescs + 1, stream));
+                ResortScatter<<<(numDescs + TPB - 1) / TPB, TPB, 0, stream>>>(resortVals, blockOffset, numDescs, descOfItem, offsetOfItem);
+                launches += 13;
             }
-            sliceDesc[slices] = numDescs; sliceOffset[slices] = arrayBytes;
-            for (uint32_t i = 0; i < slices; ++i) {
-                const uint32_t k0 = sliceDesc[i], k1 = sliceDesc[i + 1];
-                if (k1 <= k0) continue;
-                WriteDescsAndPack<<<(k1 - k0 + 7) / 8, 256, 0, stream>>>(sortValsOut, items, compactWords ? compactStart : wordStart,
-                                                                         compactWords ? compactWords : stateWords, blockOffset, k0, k1, arrayBytes,
-                                                                         (ommCpuOpacityMicromapDesc*)res->devDescArray, (uint8_t*)res->devArrayData);
-                launches++;
-                if (copyStream) {
-                    CUDA_TRY(cudaEventRecord(sliceEv, stream));
-                    CUDA_TRY(cudaStreamWaitEvent(copyStream, sliceEv, 0));
-                    if (i == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
-                    CUDA_TRY(cudaMemcpyAsync((uint8_t*)res->hostArrayData + sliceOffset[i], (const uint8_t*)res->devArrayData + sliceOffset[i],
-                                             (size_t)(sliceOffset[i + 1] - sliceOffset[i]), cudaMemcpyDeviceToHost, copyStream));
+            WriteDescs<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, special, descOfItem, offsetOfItem, 0, W, (ommCpuOpacityMicromapDesc*)res->devDescArray);
+            launches++;
+            if (world > 1 && !hostPasses) {
+                // ---- the exchange, part 2.  The survivors of a shard (a contiguous run of positions of the output order) occupy ONE
+                // contiguous byte range of arrayData: every rank packs its own shards straight to their final place, and one group of
+                // in-place broadcasts rooted at the shard owners completes the array on every rank.  No staging buffer, no host
+                // synchronisation between packing and sending (the byte ranges came with the histograms above). ----
+                NcclApi& nccl = Nccl();
+                const ncclComm_t comm = (ncclComm_t)baker->shard.ncclComm;
+                // ommCpuBake: the host copy of the array is assembled in a page-locked window shared by the ranks -- every rank sends
+                // the blocks of its own shards there with its own copy engine over its own PCIe link, while NVLink completes the
+                // device copies.  (One GPU pulling the whole array through one link was 5.3 of the 10.6 ms of an 8-GPU call.)
+                if (earlyDownload && baker->shard.ctl && arrayBytes >= ((size_t)1 << 20)) {
+                    windowProtocol = true;
+                    baker->shard.bakeSeq++;
+                    window = AcquireSharedWindow(baker->shard, (size_t)arrayBytes, log);
+                    if (!window && baker->shard.ctl->winId >= 0) baker->shard.ctl->failSeq.store(baker->shard.bakeSeq, std::memory_order_release);
+                    if (baker->shard.ctl->winId < 0) windowProtocol = false;  // the root has no window: every rank sees that
+                    if (window) {
+                        CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+                        CUDA_TRY(cudaEventCreate(&copyEv[0]));
+                        CUDA_TRY(cudaEventCreate(&copyEv[1]));
+                        CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+                    }
                 }
+                for (int k = 0; k < owned.count; ++k) {
+                    const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
+                    const unsigned long long b0 = shardOff[owned.shard[k]], b1 = shardOff[owned.shard[k] + 1];
+                    if (itemEnd <= itemBegin || b1 == b0) continue;
+                    PackItems<<<std::min(packGridMax, (itemEnd - itemBegin + 7) / 8), 256, 0, stream>>>(items, special, wordStart, stateWords, descOfItem, offsetOfItem, nullptr, nullptr,
+                                                                                                 itemBegin, itemEnd, arrayBytes, (uint8_t*)res->devArrayData, nullptr);
+                    launches++;
+                    if (window) {
+                        CUDA_TRY(cudaEventRecord(sliceEv, stream));
+                        CUDA_TRY(cudaStreamWaitEvent(copyStream, sliceEv, 0));
+                        if (k == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
+                        CUDA_TRY(cudaMemcpyAsync((uint8_t*)window->ptr + b0, (const uint8_t*)res->devArrayData + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, copyStream));
+                        sharedD2hBytes += b1 - b0;
+                    }
+                }
+                if (window) CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
+                if (gatherEv[1]) CUDA_TRY(cudaEventRecord(gatherEv[1], stream));
+                bool ncclOk = nccl.GroupStart() == ncclSuccess;
+                for (int r = 0; r < numShards && ncclOk; ++r) {
+                    const size_t count = (size_t)(shardOff[r + 1] - shardOff[r]);
+                    uint8_t* seg = (uint8_t*)res->devArrayData + shardOff[r];
+                    if (count) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint8, ShardOwner(r, world), comm, stream) == ncclSuccess;
+                }
+                ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
+                if (gatherEv[2]) CUDA_TRY(cudaEventRecord(gatherEv[2], stream));
+                if (!ncclOk) {
+                    log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL all-gather of the packed blocks failed");
+                    rc = ommResult_FAILURE;
+                    goto cleanup;
+                }
+            } else {
+                // The caller wants the result in host memory (ommCpuBake): pack the array in slices of work items and send each slice
+                // over PCIe while the next one is packed; the slice boundaries (8 bytes each) are read back first.  Page-locked
+                // destination only (a pageable one makes the copies synchronous).
+                constexpr uint32_t kPackSlices = 8;
+                unsigned long long sliceOffset[kPackSlices + 1];
+                uint32_t sliceItem[kPackSlices + 1];
+                uint32_t slices = 1;
+                sliceItem[0] = 0; sliceOffset[0] = 0;
+                if (earlyDownload && world == 1 && arrayBytes >= ((size_t)8 << 20) && W >= 64 * kPackSlices && AllocHostArrayData(res) && res->arrayDataFromPinnedPool) {
+                    slices = kPackSlices;
+                    for (uint32_t i = 1; i < slices; ++i) {
+                        sliceItem[i] = (uint32_t)((unsigned long long)W * i / slices);
+                        CUDA_TRY(cudaMemcpyAsync(&sliceOffset[i], offsetOfItem + sliceItem[i], 8, cudaMemcpyDeviceToHost, stream));
+                    }
+                    CUDA_TRY(cudaStreamSynchronize(stream));
+                    CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+                    CUDA_TRY(cudaEventCreate(&copyEv[0]));
+                    CUDA_TRY(cudaEventCreate(&copyEv[1]));
+                    CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+                }
+                sliceItem[slices] = W; sliceOffset[slices] = arrayBytes;
+                for (uint32_t i = 0; i < slices; ++i) {
+                    const uint32_t i0 = sliceItem[i], i1 = sliceItem[i + 1];
+                    if (i1 <= i0) continue;
+                    PackItems<<<std::min(packGridMax, (i1 - i0 + 7) / 8), 256, 0, stream>>>(items, special, wordStart, stateWords, descOfItem, offsetOfItem, nullptr, nullptr, i0, i1,
+                                                                                     arrayBytes, (uint8_t*)res->devArrayData, nullptr);
+                    launches++;
+                    if (copyStream && sliceOffset[i + 1] > sliceOffset[i]) {
+                        CUDA_TRY(cudaEventRecord(sliceEv, stream));
+                        CUDA_TRY(cudaStreamWaitEvent(copyStream, sliceEv, 0));
+                        if (i == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
+                        CUDA_TRY(cudaMemcpyAsync((uint8_t*)res->hostArrayData + sliceOffset[i], (const uint8_t*)res->devArrayData + sliceOffset[i],
+                                                 (size_t)(sliceOffset[i + 1] - sliceOffset[i]), cudaMemcpyDeviceToHost, copyStream));
+                    }
+                }
+                if (copyStream) CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
             }
-            if (copyStream) CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
-            launches += 3;
         }
         if (T > 0) {
             // no work item at all (every triangle invalid): the per-triangle item table was never written -> all unresolved
@@ -2708,15 +2998,36 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         cudaEventElapsedTime(&a, ev[5], gatherEv[0]);
         cudaEventElapsedTime(&b, gatherEv[0], gatherEv[1]);
         cudaEventElapsedTime(&c, gatherEv[1], gatherEv[2]);
-        fprintf(stderr, "[omm-b200 trace] rank %d exchange: digests + special indices %.3f ms, compaction %.3f ms, bounds read-back + blocks %.3f ms\n", rank, a, b, c);
+        fprintf(stderr, "[omm-b200 trace] rank %d exchange: digests + special indices %.3f ms, merge + pack of own shards %.3f ms, blocks %.3f ms\n", rank, a, b, c);
     }
     if (copyStream) {
         CUDA_TRY(cudaStreamSynchronize(copyStream));
         HostTrace::Mark("array data on the host");
         float ms = 0.f;
         cudaEventElapsedTime(&ms, copyEv[0], copyEv[1]);
-        res->arrayDataDownloaded = true;
         res->earlyD2hMs = ms;
+        if (!windowProtocol) res->arrayDataDownloaded = true;
+    }
+    if (windowProtocol) {
+        // every rank's part of the window is written once all ranks have passed this point
+        const bool all = HostBarrier(baker->shard);
+        const bool failed = !all || baker->shard.ctl->failSeq.load(std::memory_order_acquire) == baker->shard.bakeSeq;
+        HostTrace::Mark("shared window complete (host barrier)");
+        if (rank == 0 && window) {
+            if (!window->unlinked) {  // every rank has mapped it by now
+                char name[96];
+                ShmName(name, sizeof(name), baker->shard.idHash, "w", window->id);
+                shm_unlink(name);
+                window->unlinked = true;
+            }
+            if (failed) window->inUse = false;  // some rank could not write its part: the result is downloaded the ordinary way on request
+            else {
+                res->hostArrayData = window->ptr;
+                res->sharedWindowId = window->id;
+                res->arrayDataDownloaded = true;
+            }
+        }
+        tm->d2hBytes = sharedD2hBytes;
     }
     {
         float ms = 0.f;
@@ -2847,9 +3158,41 @@ ommResult InitSharding(BakerObject* baker, int rank, int world, const void* idBy
     baker->shard.rank = rank;
     baker->shard.world = world;
     baker->shard.ncclComm = comm;
+    // control block in shared memory (one box: the ranks are processes of one node).  Its absence only disables the parallel host
+    // download of sharded ommCpuBake results.
+    {
+        unsigned long long h = 1469598103934665603ull;  // FNV-1a of the unique id
+        for (size_t i = 0; i < sizeof(id); ++i) h = (h ^ (unsigned char)id.internal[i]) * 1099511628211ull;
+        baker->shard.idHash = h;
+        char name[96];
+        ShmName(name, sizeof(name), h, "ctl", 0);
+        baker->shard.ctl = (ShmControl*)MapShm(name, sizeof(ShmControl), true);  // every rank creates-or-opens; fresh objects are zero-filled
+        baker->shard.bakeSeq = 0;
+        if (baker->shard.ctl) {
+            if (!HostBarrier(baker->shard, 60.0)) {  // everybody has mapped it: the name can go
+                munmap(baker->shard.ctl, sizeof(ShmControl));
+                baker->shard.ctl = nullptr;
+            }
+            if (rank == 0) shm_unlink(name);
+        }
+    }
     return ommResult_SUCCESS;
 }
 void DestroySharding(BakerObject* baker) {
+    for (SharedHostWindow& w : baker->shard.windows) {
+        if (!w.ptr) continue;
+        cudaHostUnregister(w.ptr);
+        munmap(w.ptr, w.capacity);
+        if (baker->shard.rank == 0 && !w.unlinked) {
+            char name[96];
+            ShmName(name, sizeof(name), baker->shard.idHash, "w", w.id);
+            shm_unlink(name);
+        }
+    }
+    cudaGetLastError();
+    baker->shard.windows.clear();
+    if (baker->shard.ctl) munmap(baker->shard.ctl, sizeof(ShmControl));
+    baker->shard.ctl = nullptr;
     if (baker->shard.ncclComm) {
         Nccl().CommDestroy((ncclComm_t)baker->shard.ncclComm);
         baker->shard.ncclComm = nullptr;

@@ -161,6 +161,7 @@ struct BakeResultObject {
     bool arrayDataDownloaded = false;  // hostArrayData was filled slice by slice while the array was packed (ommCpuBake on one GPU)
     float earlyD2hMs = 0.f;
     bool arrayDataFromPinnedPool = false;  // hostArrayData came from the library's page-locked pool (default allocator only)
+    int sharedWindowId = -1;               // hostArrayData is a SharedHostWindow of the baker's sharding (root rank of a sharded ommCpuBake)
     bool usesDefaultAllocator = false;
     struct BakerObject* baker = nullptr;
 };
@@ -181,9 +182,24 @@ struct StagedInputs {
     float h2dMs = 0.f;
 };
 
+// Sharded bakes on one box: a page-locked host buffer that EVERY rank can write with its own copy engine over its own PCIe link
+// (POSIX shared memory, registered with CUDA in each process), so that the host copy of a result is assembled in parallel instead of
+// being pulled through one GPU's link.  Created by the root rank on demand, cached for the life of the sharding.
+struct SharedHostWindow {
+    int id = -1;
+    void* ptr = nullptr;
+    size_t capacity = 0;
+    bool inUse = false;     // root only: a live result owns it
+    bool unlinked = false;  // root only: the name is gone from /dev/shm (every rank has mapped it)
+};
+struct ShmControl;  // lives in shared memory (omm_bake.cu)
 struct ShardState {
     int rank = 0, world = 1;
     void* ncclComm = nullptr;  // ncclComm_t
+    ShmControl* ctl = nullptr;
+    unsigned long long idHash = 0;  // names of the shared-memory objects derive from the ncclUniqueId
+    unsigned long long bakeSeq = 0; // sharded ommCpuBake calls so far (the same number on every rank: the call is collective)
+    std::vector<SharedHostWindow> windows;
 };
 
 struct BakerObject {
@@ -233,6 +249,7 @@ int DeviceCount();
 ommResult InitSharding(BakerObject* baker, int rank, int world, const void* id, size_t idSize);
 ommResult GetNcclUniqueId(void* out, size_t size);
 void DestroySharding(BakerObject* baker);
+void ReleaseSharedWindow(BakerObject* baker, int windowId);
 ommResult ComputeShardBounds(const unsigned long long* unitStart, uint32_t entries, int world, uint32_t* outFirstItem);
 int ShardsPerRankOf(int world);
 int ShardOwnerOf(int shard, int world);
