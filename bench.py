@@ -277,7 +277,7 @@ def run_b200(a):
     assert lib.dll.ommB200GetDeviceCount() > 0, "no CUDA device visible"
     assert lib.dll.ommB200SetDevice(local) == capi.SUCCESS
 
-    baker = Baker(lib)
+    baker = Baker(lib, on_message=lambda sev, msg: print(f"[omm-b200 message, rank {rank}, severity {sev}] {msg}", file=sys.stderr, flush=True))
     if world > 1:
         idbuf = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
@@ -313,9 +313,11 @@ def run_b200(a):
         for it in range(warmup + steps):
             flush.fill_(it & 0xFF)  # evict L2 between steps (outside the timed events)
             barrier()
-            if sampler is not None and rank == 0 and it == max(warmup - 1, 0):
+            if sampler is not None and rank == 0 and it == 0:
+                # started with the FIRST warm-up step: nvidia-smi's start-up (NVML enumerates every GPU of the box) stalls CUDA calls for tens of
+                # milliseconds and was seen to leak into the first timed step when it was started during the last warm-up step
                 sampler.start()
-                sampler.wait_first()
+                sampler.wait_first(5.0)
             if sampler is not None and it == warmup:
                 sampler.mark()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

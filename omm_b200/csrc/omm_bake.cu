@@ -1315,6 +1315,54 @@ __global__ void DigestInsert(const uint64_t* __restrict__ digest, const ItemRec*
     const uint32_t peers = __match_any_sync(active, d);
     if (__reduce_min_sync(peers, tri) == tri) TableInsertMin(keys, vals, mask, d, tri);  // first triangles are unique per item: one lane per group
 }
+// The same for one classifier chunk of a STREAMED bake (the chunk's survivors are packed and sent to the host while later chunks are still
+// being classified, see BakeOnDevice).  A chunk is resolved against the table as it stands after its own insertions, so a survivor of
+// an earlier chunk is final only if no later item with its digest has a lower first triangle: when an insertion lowers an entry that
+// belonged to a serialized item of an earlier chunk, `conflict` is raised and the bake falls back to the non-streamed merge (rare: equal blocks under
+// different UV triangles, the later-sorted one seen first by the SDK).
+__global__ void DigestInsertChunk(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, const uint32_t* __restrict__ triItem,
+                                  const int32_t* __restrict__ special, uint32_t itemBegin, uint32_t itemEnd, uint64_t* keys, uint32_t* vals, uint64_t mask,
+                                  uint32_t* __restrict__ conflict) {
+    const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < itemEnd;
+    const uint64_t d = valid ? digest[s] : 0ull;
+    const uint32_t tri = valid ? items[s].tri : 0xFFFFFFFFu;
+    const uint32_t active = __ballot_sync(0xFFFFFFFFu, valid);
+    if (!valid) return;
+    const uint32_t peers = __match_any_sync(active, d);
+    if (__reduce_min_sync(peers, tri) != tri) return;
+    uint64_t key = d == kEmptyKey ? 0x7FFFFFFFFFFFFFFFull : d;
+    uint64_t slot = TableSlot(key, mask);
+    while (true) {
+        const uint64_t prev = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)key);
+        if (prev == kEmptyKey || prev == key) {
+            const uint32_t old = atomicMin(&vals[slot], tri);
+            // (only a SERIALIZED earlier item matters: one with a special index was never emitted, and whichever item of its digest
+            // its triangles resolve to carries the same special index)
+            if (old != 0xFFFFFFFFu && old > tri) {
+                const uint32_t prev = triItem[old];
+                if (prev < itemBegin && special[prev] == 0 && atomicOr(conflict, 1u) == 0u) {
+                    conflict[1] = prev;  // diagnostics (OMM_B200_TRACE): the first pair that forced the fallback
+                    conflict[2] = s;
+                }
+            }
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+// running totals of a streamed bake: descriptors / bytes emitted by the chunks so far (the initial values of the next chunk's scans)
+__global__ void AdvanceRunningTotals(const uint32_t* __restrict__ emit, const unsigned long long* __restrict__ blockBytes, const uint32_t* __restrict__ descOfItem,
+                                     const unsigned long long* __restrict__ offsetOfItem, uint32_t lastItem, uint32_t* __restrict__ runDesc,
+                                     unsigned long long* __restrict__ runBytes, unsigned long long* __restrict__ hostSlot) {
+    *runDesc = descOfItem[lastItem] + emit[lastItem];
+    const unsigned long long bytes = offsetOfItem[lastItem] + blockBytes[lastItem];
+    *runBytes = bytes;
+    // the host learns the chunk's end through page-locked memory written from here: a cudaMemcpyAsync on this stream would queue behind
+    // the previous chunk's 36 MB transfer on the device-to-host copy engine and stall the classification by that long (measured)
+    *hostSlot = bytes;
+    __threadfence_system();
+}
 __global__ void DigestResolve(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, const uint32_t* __restrict__ triItem, uint32_t itemBegin,
                               uint32_t itemEnd, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask, int disableDup,
                               uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
@@ -1739,14 +1787,34 @@ size_t PinnedPoolTrim(size_t keepBytes) {
 }
 
 // Host memory of arrayData: the library's page-locked pool under the default allocator (full PCIe speed), the user's allocator otherwise.
-static bool AllocHostArrayData(BakeResultObject* res) {
+static bool AllocHostArrayData(BakeResultObject* res, size_t bytes = 0) {
     if (res->hostArrayData) return true;
-    if (res->usesDefaultAllocator && res->arrayDataSize >= (1u << 20)) {
-        res->hostArrayData = PinnedPoolAcquire(res->arrayDataSize);
+    if (bytes == 0) bytes = res->arrayDataSize;
+    if (res->usesDefaultAllocator && bytes >= (1u << 20)) {
+        res->hostArrayData = PinnedPoolAcquire(bytes);
         res->arrayDataFromPinnedPool = res->hostArrayData != nullptr;
     }
-    if (!res->hostArrayData) res->hostArrayData = res->alloc.alloc(res->arrayDataSize, 64);
+    if (!res->hostArrayData) res->hostArrayData = res->alloc.alloc(bytes, 64);
     return res->hostArrayData != nullptr;
+}
+// Streamed ommCpuBake (one GPU): classifier chunks per bake = the nominal number times this (more chunks: a shorter tail after the last
+// kernel, ~50 us of kernel boundaries each).  OMM_B200_STREAM_DIV overrides (1 = the chunks of a resident bake).
+static unsigned StreamChunkDivisor() {
+    static const unsigned v = [] {
+        const char* e = getenv("OMM_B200_STREAM_DIV");
+        const long n = e ? atol(e) : 4;
+        return (unsigned)(n < 1 ? 1 : (n > 16 ? 16 : n));
+    }();
+    return v;
+}
+// OFF by default (OMM_B200_STREAMED_DOWNLOAD=1 enables it; read per bake so that tests can toggle it).  Measured at config 3: one in 27
+// serialized blocks is shared by several UV triangles (almost-uniform blocks whose few odd micro-triangles coincide), half of those pairs
+// have their SDK survivor in a later chunk than the copy that was sent first, and every such case shifts all later offsets -- so the
+// optimistic merge always falls back there and the call gets 1.7 ms slower (22.0 vs 20.3 ms) instead of 4 ms faster.  It pays for
+// inputs whose blocks do not repeat across triangles.
+static bool StreamedDownloadEnabled() {
+    const char* e = getenv("OMM_B200_STREAMED_DOWNLOAD");
+    return e != nullptr && e[0] != '0';
 }
 
 static ommResult RequireDevice(const Logger& log, int device) {
@@ -2182,6 +2250,16 @@ static const char* SpecialIndexText(int s) {  // ref: log.h:20-31
     }
 }
 
+}  // namespace ommb200
+#include "omm_post_passes.cuh"
+namespace ommb200 {
+
+bool HostPassesNeeded(const ommCpuBakeInputDesc& desc) {
+    const uint32_t flags = (uint32_t)desc.bakeFlags;
+    if (flags & ommCpuBakeFlags_DisableDuplicateDetection) return desc.maxArrayDataSize != 0xFFFFFFFFu;  // the merge is off with the dedup (ref: bake_cpu_impl.cpp:1136)
+    return (flags & ommCpuBakeFlags_EnableNearDuplicateDetection) != 0 || desc.maxArrayDataSize != 0xFFFFFFFFu;
+}
+
 // ---- host side of a sharding on one box: a control block and result windows in POSIX shared memory -------------------------------
 struct ShmControl {
     std::atomic<uint32_t> barCount, barGen;  // sense-reversing barrier of the ranks' host threads
@@ -2329,6 +2407,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     const bool hostPasses = HostPassesNeeded(d);
     const int TPB = 256;
     uint32_t launches = 0;
+    // ref: bake_cpu_impl.cpp:1873-1902 -- width of the index buffer
+    const bool allow8 = (flags & ommCpuBakeFlags_Allow8BitIndices) != 0, force32 = (flags & ommCpuBakeFlags_Force32BitIndices) != 0;
+    const ommIndexFormat ifmt = (allow8 && (int32_t)T <= 127 && !force32) ? ommIndexFormat_UINT_8 : (((int32_t)T <= 32767 && !force32) ? ommIndexFormat_UINT_16 : ommIndexFormat_UINT_32);
+    const int indexBytes = ifmt == ommIndexFormat_UINT_8 ? 1 : (ifmt == ommIndexFormat_UINT_16 ? 2 : 4);
 
     cudaStream_t stream = (cudaStream_t)userStream;
     bool ownStream = false;
@@ -2357,7 +2439,25 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     uint32_t chunkFirst[kMaxShardsPerRank][kHierMaxChunks + 1];
     const int numShards = world * ShardsPerRank(world);  // see ShardOwner
     OwnedShards owned{};
-    const unsigned long long hierChunkRegions = HierNominalChunkRegions(baker->device);
+    // ommCpuBake on one GPU: the array is packed and written to the caller-visible host memory chunk by chunk WHILE later chunks are
+    // classified (possible because the items are in output order, K3b); see "streamed" below
+    const bool streamCandidate = earlyDownload && world == 1 && !hostPasses && res->usesDefaultAllocator && StreamedDownloadEnabled() &&
+                                 (flags & ommCpuBakeFlags_DisableSpecialIndices) == 0 && T >= 4096;
+    unsigned long long hierChunkRegions = HierNominalChunkRegions(baker->device);
+    if (streamCandidate) {
+        hierChunkRegions = std::max(kHierChunkRegionsMin, hierChunkRegions / StreamChunkDivisor());
+        if (const char* e = getenv("OMM_B200_STREAM_CHUNK_REGIONS")) {  // tests: many chunks at small sizes (read per bake)
+            const unsigned long long v = strtoull(e, nullptr, 10);
+            if (v >= 4096) hierChunkRegions = v;
+        }
+    }
+    bool streaming = false, streamFallback = false;
+    std::vector<cudaEvent_t> chunkEvs;           // streamed: "chunk c is packed into the device array"
+    unsigned long long* chunkEndHost = nullptr;  // streamed: arrayData bytes emitted up to and including chunk c (page-locked, read by the host as chunks complete)
+    uint32_t *runDesc = nullptr, *conflictDev = nullptr;
+    unsigned long long* runBytes = nullptr;
+    unsigned long long worstBytes = 0;
+    uint32_t streamHost[4] = {0, 0, 0, 0};  // [0] descriptors emitted by the chunks, [1] conflict flag of the optimistic dedup
     uint32_t* stateWords = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;
@@ -2373,7 +2473,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     ShardBound bounds[kMaxShards + 1];
     uint32_t numDescs = 0;
     unsigned long long arrayBytes = 0;
-    int indexBytes = 4;
     bool resort = false;  // Compress changed item levels: the serialized items are sorted again (see ResortKeys)
     SharedHostWindow* window = nullptr;  // sharded ommCpuBake: the root's host copy of arrayData, written by every rank
     bool windowProtocol = false;         // this bake takes part in the window hand-shake (every rank decides alike)
@@ -2505,6 +2604,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                                                 (int)T, 0, 32, stream));
             need = std::max(need, tmp);
+            CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, cub::Sum(),
+                                                     cub::FutureValue<unsigned long long>((unsigned long long*)nullptr), (int)T + 1, stream));
+            need = std::max(need, tmp);
             cubTempBytes = need;
             CUDA_TRY(scratch.alloc((uint8_t**)&cubTemp, cubTempBytes));
             tmp = cubTempBytes;
@@ -2588,8 +2690,46 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         uint32_t myItems = 0;
         for (int k = 0; k < owned.count; ++k) myItems += bounds[owned.shard[k] + 1].item - bounds[owned.shard[k]].item;
         CUDA_TRY(scratch.alloc(&stateWords, (size_t)totalWords + 4));
+        CUDA_TRY(scratch.alloc(&digest, W));
+        CUDA_TRY(scratch.alloc(&special, W));
+        CUDA_TRY(scratch.alloc(&survivor, W));
+        CUDA_TRY(scratch.alloc(&hist, 64));
+        CUDA_TRY(scratch.alloc(&emit, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&descOfItem, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&blockBytes, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&offsetOfItem, (size_t)W + 1));
+        CUDA_TRY(scratch.alloc(&shardOffDev, kMaxShards + 1));
+        CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
+        const uint64_t tableCap = NextPow2((uint64_t)W * 2 + 16);
+        if (streamCandidate && useHier && myItems > 0 && chunkFirst[0][2] < bounds[1].item) {  // at least three chunks
+            // ---- streamed: sizes are not known before the last chunk, so the array is laid out in buffers of the worst-case size
+            // (every work item serialized); the host one comes from the page-locked pool and is written by PackItems directly ----
+            for (int l = 0; l <= kMaxLevel; ++l) {
+                const unsigned long long bytes = ((1ull << (2 * l)) * (unsigned long long)d.format) >> 3;
+                worstBytes += (unsigned long long)countersHost[8 + l] * (bytes > 1 ? bytes : 1);
+            }
+            if (worstBytes >= ((unsigned long long)8 << 20) && worstBytes <= ((unsigned long long)3 << 30) && AllocHostArrayData(res, (size_t)worstBytes) &&
+                res->arrayDataFromPinnedPool) {
+                chunkEndHost = (unsigned long long*)PinnedPoolAcquire(sizeof(unsigned long long) * (kHierMaxChunks + 1));
+                if (!chunkEndHost) {
+                    rc = ommResult_FAILURE;
+                    goto cleanup;
+                }
+                CUDA_TRY(scratch.alloc(&runDesc, 4));
+                CUDA_TRY(scratch.alloc(&runBytes, 2));
+                conflictDev = runDesc + 1;
+                CUDA_TRY(cudaMemsetAsync(runDesc, 0, 4 * sizeof(uint32_t), stream));
+                CUDA_TRY(cudaMemsetAsync(runBytes, 0, 2 * sizeof(unsigned long long), stream));
+                CUDA_TRY(cudaMallocAsync(&res->devArrayData, (size_t)worstBytes + 16, stream));
+                if (!disableDup) {
+                    FillTable<<<(uint32_t)((tableCap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, tableCap);
+                    launches++;
+                }
+                streaming = true;
+            }
+        }
         if (myItems > 0 && useHier) {
             if (P.tex.mipCount == 1) cellTables = AcquireCellTables(tex, P, stream, &launches);  // (H), (I): built on first use per texture and cutoff
             // worst case of a chunk: the nominal number of initial regions plus the rest of its last item (at most 4^9 regions at level 12)
@@ -2627,6 +2767,32 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
                     hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
                     launches += 6;
+                    if (streaming) {
+                        // the chunk's items are final: special indices + digests, dedup against the chunks so far, descriptor slots and
+                        // byte offsets continuing the running totals, then the blocks go to the device array; the host thread forwards each
+                        // chunk's byte range to a copy engine as soon as it is packed (below), so the array crosses PCIe while later chunks
+                        // are classified.  (PackItems writing the page-locked host array directly was measured first: 52 GB/s, as fast as
+                        // the copy engine -- but the SMs it ran on stalled behind the PCIe writes and the whole bake took 5 ms longer.)
+                        const uint32_t n = i1 - i0, gridC = (n + TPB - 1) / TPB;
+                        ItemPostKernel<<<(n + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(
+                            items, wordStart, stateWords, i0, i1, d.rejectionThreshold, 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE, GetUniformDigests(), digest, special);
+                        if (!disableDup) DigestInsertChunk<<<gridC, TPB, 0, stream>>>(digest, items, triItem, special, i0, i1, tableKeys, tableVals, tableCap - 1, conflictDev);
+                        DigestResolve<<<gridC, TPB, 0, stream>>>(digest, items, triItem, i0, i1, tableKeys, tableVals, tableCap - 1, disableDup, survivor, special);
+                        EmitInfo<<<gridC, TPB, 0, stream>>>(items, special, i0, i1, 0, (int)d.format, hist, emit, blockBytes);
+                        size_t tmp = cubTempBytes;
+                        CUDA_TRY(cub::DeviceScan::ExclusiveScan(cubTemp, tmp, emit + i0, descOfItem + i0, cub::Sum(), cub::FutureValue<uint32_t>(runDesc), (int)n, stream));
+                        tmp = cubTempBytes;
+                        CUDA_TRY(cub::DeviceScan::ExclusiveScan(cubTemp, tmp, blockBytes + i0, offsetOfItem + i0, cub::Sum(), cub::FutureValue<unsigned long long>(runBytes), (int)n,
+                                                                 stream));
+                        AdvanceRunningTotals<<<1, 1, 0, stream>>>(emit, blockBytes, descOfItem, offsetOfItem, i1 - 1, runDesc, runBytes, chunkEndHost + chunkEvs.size());
+                        PackItems<<<std::min((uint32_t)std::max(sms, 1) * 32u, (n + 7) / 8), 256, 0, stream>>>(items, special, wordStart, stateWords, descOfItem, offsetOfItem, nullptr,
+                                                                                                      nullptr, i0, i1, worstBytes, (uint8_t*)res->devArrayData, nullptr);
+                        cudaEvent_t e = nullptr;
+                        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        chunkEvs.push_back(e);
+                        CUDA_TRY(cudaEventRecord(e, stream));
+                        launches += 10;
+                    }
                 }
             }
         } else if (myItems > 0) {
@@ -2648,9 +2814,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
         myMicroTris = microTris;
         CUDA_TRY(cudaEventRecord(ev[4], stream));  // end of the classification kernels proper
-        CUDA_TRY(scratch.alloc(&digest, W));
-        CUDA_TRY(scratch.alloc(&special, W));
-        for (int k = 0; k < owned.count; ++k) {
+        for (int k = 0; k < owned.count && !streaming; ++k) {
             const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
             if (itemEnd <= itemBegin) continue;
             // special-index scan + XXH64 of this rank's items (their state words are local already)
@@ -2710,26 +2874,68 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     if (W > 0) {
         NvtxRange nvtxMerge("dedup + offsets");
         const uint32_t gridW = (W + TPB - 1) / TPB, gridW1 = (W + 1 + TPB - 1) / TPB;
-        CUDA_TRY(scratch.alloc(&survivor, W));
-        CUDA_TRY(scratch.alloc(&hist, 64));
-        CUDA_TRY(scratch.alloc(&emit, (size_t)W + 1));
-        CUDA_TRY(scratch.alloc(&descOfItem, (size_t)W + 1));
-        CUDA_TRY(scratch.alloc(&blockBytes, (size_t)W + 1));
-        CUDA_TRY(scratch.alloc(&offsetOfItem, (size_t)W + 1));
-        CUDA_TRY(scratch.alloc(&shardOffDev, kMaxShards + 1));
-        CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
         const uint64_t cap = NextPow2((uint64_t)W * 2 + 16);
-        if (!disableDup) {
+        if (streaming) {
+            // Every chunk has been merged already.  Left to do on the device: index histogram, descriptors, index buffer -- launched now
+            // so that the GPU never waits for the host; then the host forwards the chunks to the copy engine as they complete.
+            TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, mergeRoot, survivor2, items, special, T, triFinal, hist);
+            CUDA_TRY(cudaMallocAsync(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4, stream));
+            CUDA_TRY(cudaMallocAsync(&res->devDescArray, (size_t)W * sizeof(ommCpuOpacityMicromapDesc), stream));
+            WriteDescs<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, special, descOfItem, offsetOfItem, 0, W, (ommCpuOpacityMicromapDesc*)res->devDescArray);
+            WriteIndexBuffer<<<gridT, TPB, 0, stream>>>(triFinal, special, descOfItem, T, (int)d.unresolvedTriState, indexBytes, res->devIndexBuffer);
+            launches += 3;
+            CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreate(&copyEv[0]));
+            CUDA_TRY(cudaEventCreate(&copyEv[1]));
+            {
+                unsigned long long sent = 0;
+                for (size_t c = 0; c < chunkEvs.size(); ++c) {
+                    CUDA_TRY(cudaEventSynchronize(chunkEvs[c]));
+                    if (c == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
+                    const unsigned long long end = chunkEndHost[c];
+                    if (end > sent)
+                        CUDA_TRY(cudaMemcpyAsync((uint8_t*)res->hostArrayData + sent, (const uint8_t*)res->devArrayData + sent, (size_t)(end - sent), cudaMemcpyDeviceToHost, copyStream));
+                    sent = end;
+                }
+                CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
+            }
+            HostTrace::Mark("    streamed: last chunk handed to the copy engine");
+            CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(streamHost, runDesc, sizeof(streamHost), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            HostTrace::Mark("    histograms read (host sync 2, streamed)");
+            if (streamHost[1] != 0 && HostTrace::Enabled())
+                fprintf(stderr, "[omm-b200 trace] streamed bake falls back: the block of item %u (already sent) equals that of item %u in a later chunk, which the SDK keeps\n",
+                        streamHost[2], streamHost[3]);
+            if (streamHost[1] != 0) {
+                // a later chunk held the true survivor of a digest an earlier chunk had already emitted: merge and pack again, the ordinary way
+                streamFallback = true;
+                CUDA_TRY(cudaStreamSynchronize(copyStream));
+                CUDA_TRY(cudaStreamDestroy(copyStream));
+                copyStream = nullptr;
+                for (int i = 0; i < 2; ++i) {
+                    cudaEventDestroy(copyEv[i]);
+                    copyEv[i] = nullptr;
+                }
+                CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
+                memset(histHost, 0, sizeof(histHost));
+            }
+        }
+        if (!streaming && !disableDup) {
             // the UV table (capacity >= 2T+16 >= 2W+16) is reused for the digests
             FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
             DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, 0, W, tableKeys, tableVals, cap - 1);
             launches += 2;
         }
-        DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
-        launches++;
+        if (!streaming || streamFallback) {
+            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
+            launches++;
+        }
         if (hostPasses) {
-            // ---- a17 / a18: near-duplicate merge and size-budget compression (omm_host_passes.cpp).  Both walk the work items in the
-            // SDK's first-seen order, so the host side sees them through posOfOrig. ----
+            // ---- a17 / a18: near-duplicate merge and size-budget compression (omm_post_passes.cuh).  The states stay on the device; the
+            // host drives the passes from per-item records (32 B each), hashes, distances and counts.  Both passes walk the work items in
+            // the SDK's first-seen order, so the host sees them through posOfOrig. ----
+            const bool nearDup = !disableDup && (flags & ommCpuBakeFlags_EnableNearDuplicateDetection) != 0, bruteForce = (flags & (1u << 10)) != 0;
             uint32_t* primCount = nullptr;
             uint8_t* levelsDev = nullptr;
             CUDA_TRY(scratch.alloc(&primCount, W));
@@ -2741,43 +2947,58 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches++;
             std::vector<ItemRec> hItems(W);
             std::vector<int32_t> hSpecial(W);
-            std::vector<uint32_t> hPrims(W), hRoot(W), hPos(W), hWords((size_t)totalWords);
-            std::vector<unsigned long long> hWordStart((size_t)W + 1), hWordStartW(W);
+            std::vector<uint32_t> hPrims(W), hRoot(W), hPos(W);
             std::vector<uint8_t> hLevels(W);
-            std::vector<HostPassItem> hp(W);
+            std::vector<PassItem> pass(W);
             CUDA_TRY(cudaMemcpyAsync(hItems.data(), items, sizeof(ItemRec) * W, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hSpecial.data(), special, sizeof(int32_t) * W, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hPrims.data(), primCount, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(hPos.data(), posOfOrig, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaMemcpyAsync(hWordStart.data(), wordStart, sizeof(unsigned long long) * ((size_t)W + 1), cudaMemcpyDeviceToHost, stream));
-            CUDA_TRY(cudaMemcpyAsync(hWords.data(), stateWords, sizeof(uint32_t) * (size_t)totalWords, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
             for (uint32_t w = 0; w < W; ++w) {
-                const uint32_t s = hPos[w];
-                HostPassItem& it = hp[w];
-                it.level = hItems[s].level;
-                it.format = hItems[s].format;
-                it.uv[0] = hItems[s].p0.x; it.uv[1] = hItems[s].p0.y; it.uv[2] = hItems[s].p1.x; it.uv[3] = hItems[s].p1.y;
-                it.uv[4] = hItems[s].p2.x; it.uv[5] = hItems[s].p2.y;
-                it.numPrims = hPrims[s];
-                it.special = hSpecial[s];
-                it.mergedInto = w;
-                it.statesChanged = false;
-                hWordStartW[w] = hWordStart[s];
+                const ItemRec& it = hItems[hPos[w]];
+                PassItem& p = pass[w];
+                p.pos = hPos[w];
+                p.prims = hPrims[p.pos];
+                p.special = hSpecial[p.pos];
+                p.root = w;
+                p.level = p.levelAtStart = it.level;
+                p.format = it.format;
+                // ref: bake_cpu_impl.cpp:464-468 (area of the UV triangle: half the length of the cross product)
+                const float v0x = it.p2.x - it.p0.x, v0y = it.p2.y - it.p0.y, v1x = it.p1.x - it.p0.x, v1y = it.p1.y - it.p0.y;
+                const float cz = v0x * v1y - v1x * v0y;
+                p.area = 0.5f * std::sqrt(cz * cz);
             }
-            rc = RunHostPasses(d, hp.data(), W, hWords.data(), hWordStartW.data());
-            if (rc != ommResult_SUCCESS) goto cleanup;
+            PostPasses passes(stream, pass, stateWords, wordStart, totalWords);
+            if (nearDup && !(bruteForce ? passes.nearDuplicatesWindowed() : passes.nearDuplicatesLsh(d.nearDuplicateDeduplicationFactor, 3))) {
+                log.Log(ommMessageSeverity_Fatal, "[omm-b200] near-duplicate pass failed (CUDA error or out of memory)");
+                rc = ommResult_FAILURE;
+                goto cleanup;
+            }
+            // ref: bake_cpu_impl.cpp:1965 -- promotion between the merge and the budget pass: blocks the merge made uniform get their special
+            // index now (and are then no candidates for downsampling)
+            for (uint32_t w = 0; w < W; ++w) hSpecial[pass[w].pos] = pass[w].special;
+            CUDA_TRY(cudaMemcpyAsync(special, hSpecial.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, stream));
+            ItemPostKernel<<<(W + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
+                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
+                                                            GetUniformDigests(), digest, special);
+            launches++;
+            if (d.maxArrayDataSize != 0xFFFFFFFFu) {
+                CUDA_TRY(cudaMemcpyAsync(hSpecial.data(), special, sizeof(int32_t) * W, cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                for (uint32_t w = 0; w < W; ++w) pass[w].special = hSpecial[pass[w].pos];
+                rc = passes.compress(d.maxArrayDataSize);
+                if (rc != ommResult_SUCCESS) goto cleanup;
+            }
+            launches += passes.launches;
             for (uint32_t w = 0; w < W; ++w) {
                 uint32_t r = w;
-                while (hp[r].mergedInto != r) r = hp[r].mergedInto;
-                const uint32_t s = hPos[w];
-                hRoot[s] = hPos[r];
-                hSpecial[s] = hp[w].special;
-                hLevels[s] = (uint8_t)hp[w].level;
-                resort = resort || hp[w].level != hItems[s].level;
+                while (pass[r].root != r) r = pass[r].root;
+                const uint32_t s = pass[w].pos;
+                hRoot[s] = pass[r].pos;
+                hLevels[s] = pass[w].level;
+                resort = resort || pass[w].level != pass[w].levelAtStart;
             }
-            CUDA_TRY(cudaMemcpyAsync(stateWords, hWords.data(), sizeof(uint32_t) * (size_t)totalWords, cudaMemcpyHostToDevice, stream));
-            CUDA_TRY(cudaMemcpyAsync(special, hSpecial.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, stream));
             CUDA_TRY(cudaMemcpyAsync(mergeRoot, hRoot.data(), sizeof(uint32_t) * W, cudaMemcpyHostToDevice, stream));
             CUDA_TRY(cudaMemcpyAsync(levelsDev, hLevels.data(), W, cudaMemcpyHostToDevice, stream));
             UpdateItemLevels<<<gridW, TPB, 0, stream>>>(items, levelsDev, W);
@@ -2796,21 +3017,23 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches++;
             CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors above must outlive the copies
         }
-        // serialized items, their descriptor slots and byte offsets: prefix sums in output order
-        EmitInfo<<<gridW1, TPB, 0, stream>>>(items, special, 0, W, 1, (int)d.format, hist, emit, blockBytes);
-        TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, mergeRoot, survivor2, items, special, T, triFinal, hist);
-        {
-            size_t tmp = cubTempBytes;
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, emit, descOfItem, (int)W + 1, stream));
-            tmp = cubTempBytes;
-            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, offsetOfItem, (int)W + 1, stream));
+        if (!streaming || streamFallback) {
+            // serialized items, their descriptor slots and byte offsets: prefix sums in output order
+            EmitInfo<<<gridW1, TPB, 0, stream>>>(items, special, 0, W, 1, (int)d.format, hist, emit, blockBytes);
+            TriangleFinalItems<<<gridT, TPB, 0, stream>>>(triItem, survivor, mergeRoot, survivor2, items, special, T, triFinal, hist);
+            {
+                size_t tmp = cubTempBytes;
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, emit, descOfItem, (int)W + 1, stream));
+                tmp = cubTempBytes;
+                CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, blockBytes, offsetOfItem, (int)W + 1, stream));
+            }
+            ShardByteOffsets<<<1, 96, 0, stream>>>(offsetOfItem, boundsDev, numShards, shardOffDev);
+            launches += 7;
+            CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaMemcpyAsync(shardOff, shardOffDev, sizeof(unsigned long long) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            HostTrace::Mark("    histograms read (host sync 2)");
         }
-        ShardByteOffsets<<<1, 96, 0, stream>>>(offsetOfItem, boundsDev, numShards, shardOffDev);
-        launches += 7;
-        CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync(shardOff, shardOffDev, sizeof(unsigned long long) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        HostTrace::Mark("    histograms read (host sync 2)");
     }
 
     // ---- sizes (ref: bake_cpu_impl.cpp:1763-1777) ----
@@ -2842,20 +3065,16 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     // ---- K8: serialize ----
     {
         NvtxRange nvtxPack("pack + index buffer");
-        const bool allow8 = (flags & ommCpuBakeFlags_Allow8BitIndices) != 0, force32 = (flags & ommCpuBakeFlags_Force32BitIndices) != 0;
-        ommIndexFormat ifmt = ommIndexFormat_UINT_32;  // ref: :1873-1902
-        if (allow8 && (int32_t)T <= 127 && !force32) { ifmt = ommIndexFormat_UINT_8; indexBytes = 1; }
-        else if ((int32_t)T <= 32767 && !force32) { ifmt = ommIndexFormat_UINT_16; indexBytes = 2; }
         res->device = baker->device;
         res->arrayDataSize = (uint32_t)arrayBytes;
         res->descCount = numDescs;
         res->indexCount = T;
         res->indexFormat = ifmt;
-        CUDA_TRY(cudaMallocAsync(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4, stream));
+        if (!res->devIndexBuffer) CUDA_TRY(cudaMallocAsync(&res->devIndexBuffer, (size_t)(T ? T : 1) * 4, stream));
         if (numDescs) {
             const uint32_t packGridMax = (uint32_t)std::max(sms, 1) * 32u;
-            CUDA_TRY(cudaMallocAsync(&res->devArrayData, (size_t)arrayBytes + 16, stream));
-            CUDA_TRY(cudaMallocAsync(&res->devDescArray, (size_t)numDescs * sizeof(ommCpuOpacityMicromapDesc), stream));
+            if (!res->devArrayData) CUDA_TRY(cudaMallocAsync(&res->devArrayData, (size_t)arrayBytes + 16, stream));  // (a streamed bake has its worst-case buffer)
+            if (!res->devDescArray) CUDA_TRY(cudaMallocAsync(&res->devDescArray, (size_t)numDescs * sizeof(ommCpuOpacityMicromapDesc), stream));
             if (resort) {
                 // Compress lowered the level of some items and with it their sort keys: order the serialized items again
                 uint32_t* resortVals = nullptr;
@@ -2871,9 +3090,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 ResortScatter<<<(numDescs + TPB - 1) / TPB, TPB, 0, stream>>>(resortVals, blockOffset, numDescs, descOfItem, offsetOfItem);
                 launches += 13;
             }
-            WriteDescs<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, special, descOfItem, offsetOfItem, 0, W, (ommCpuOpacityMicromapDesc*)res->devDescArray);
-            launches++;
-            if (world > 1 && !hostPasses) {
+            if (!(streaming && !streamFallback)) {
+                WriteDescs<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, special, descOfItem, offsetOfItem, 0, W, (ommCpuOpacityMicromapDesc*)res->devDescArray);
+                launches++;
+            }
+            if (streaming && !streamFallback) {
+                // nothing left to pack or send: the last chunk's blocks are with the copy engine
+            } else if (world > 1 && !hostPasses) {
                 // ---- the exchange, part 2.  The survivors of a shard (a contiguous run of positions of the output order) occupy ONE
                 // contiguous byte range of arrayData: every rank packs its own shards straight to their final place, and one group of
                 // in-place broadcasts rooted at the shard owners completes the array on every rank.  No staging buffer, no host
@@ -2894,6 +3117,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                         CUDA_TRY(cudaEventCreate(&copyEv[0]));
                         CUDA_TRY(cudaEventCreate(&copyEv[1]));
                         CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+                        CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
                     }
                 }
                 for (int k = 0; k < owned.count; ++k) {
@@ -2906,7 +3130,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     if (window) {
                         CUDA_TRY(cudaEventRecord(sliceEv, stream));
                         CUDA_TRY(cudaStreamWaitEvent(copyStream, sliceEv, 0));
-                        if (k == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
                         CUDA_TRY(cudaMemcpyAsync((uint8_t*)window->ptr + b0, (const uint8_t*)res->devArrayData + b0, (size_t)(b1 - b0), cudaMemcpyDeviceToHost, copyStream));
                         sharedD2hBytes += b1 - b0;
                     }
@@ -2946,6 +3169,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     CUDA_TRY(cudaEventCreate(&copyEv[0]));
                     CUDA_TRY(cudaEventCreate(&copyEv[1]));
                     CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+                    CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
                 }
                 sliceItem[slices] = W; sliceOffset[slices] = arrayBytes;
                 for (uint32_t i = 0; i < slices; ++i) {
@@ -2957,7 +3181,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     if (copyStream && sliceOffset[i + 1] > sliceOffset[i]) {
                         CUDA_TRY(cudaEventRecord(sliceEv, stream));
                         CUDA_TRY(cudaStreamWaitEvent(copyStream, sliceEv, 0));
-                        if (i == 0) CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
                         CUDA_TRY(cudaMemcpyAsync((uint8_t*)res->hostArrayData + sliceOffset[i], (const uint8_t*)res->devArrayData + sliceOffset[i],
                                                  (size_t)(sliceOffset[i + 1] - sliceOffset[i]), cudaMemcpyDeviceToHost, copyStream));
                     }
@@ -2965,7 +3188,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 if (copyStream) CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
             }
         }
-        if (T > 0) {
+        if (T > 0 && !(streaming && !streamFallback)) {
             // no work item at all (every triangle invalid): the per-triangle item table was never written -> all unresolved
             // (found by the SDK's own LogTest.Validation_InvalidTriangles run against this library)
             if (W == 0) CUDA_TRY(cudaMemsetAsync(triFinal, 0xFF, sizeof(uint32_t) * (size_t)T, stream));
@@ -3004,7 +3227,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(cudaStreamSynchronize(copyStream));
         HostTrace::Mark("array data on the host");
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, copyEv[0], copyEv[1]);
+        if (cudaEventElapsedTime(&ms, copyEv[0], copyEv[1]) != cudaSuccess) cudaGetLastError();
         res->earlyD2hMs = ms;
         if (!windowProtocol) res->arrayDataDownloaded = true;
     }
@@ -3066,6 +3289,8 @@ cleanup:
         cudaStreamSynchronize(copyStream);
         cudaStreamDestroy(copyStream);
     }
+    for (cudaEvent_t e : chunkEvs) cudaEventDestroy(e);
+    if (chunkEndHost) PinnedPoolRelease(chunkEndHost);
     for (cudaEvent_t e : {copyEv[0], copyEv[1], sliceEv, gatherEv[0], gatherEv[1], gatherEv[2]})
         if (e) cudaEventDestroy(e);
     if (rc != ommResult_SUCCESS) {

@@ -213,18 +213,8 @@ struct BakerObject {
     bool haveTimings = false;
 };
 
-// one work item as the host passes (omm_host_passes.cpp) see it
-struct HostPassItem {
-    uint32_t level;
-    uint32_t format;
-    float uv[6];          // p0, p1, p2
-    uint32_t numPrims;    // primitives referencing the item after the first exact dedup
-    int32_t special;      // 0 = none, -1..-4 special index / merged away
-    uint32_t mergedInto;  // item that received this item's primitives in a near-duplicate merge (self if none)
-    bool statesChanged;
-};
+// a17 / a18 (near-duplicate merge, size-budget compression) are requested by this desc (omm_post_passes.cuh)
 bool HostPassesNeeded(const ommCpuBakeInputDesc& desc);
-ommResult RunHostPasses(const ommCpuBakeInputDesc& desc, HostPassItem* items, uint32_t count, uint32_t* words, const unsigned long long* wordStart);
 
 // implemented in omm_serialize.cpp
 struct SerializedResultObject;

@@ -27,10 +27,10 @@
 #include <vector>
 
 #include "omm_internal.h"
+#include "omm_xxh64.h"
 
 namespace ommb200 {
 
-uint64_t HostXxh64(const void* data, size_t len, uint64_t seed);  // omm_host_passes.cpp
 
 namespace {
 
