@@ -819,6 +819,7 @@ constexpr uint32_t kHierTaskRegions = 64;
 #ifndef OMM_LEAF_MIN_BLOCKS
 #define OMM_LEAF_MIN_BLOCKS 8
 #endif
+
 template <class Cfg>
 __global__ void __launch_bounds__(kHierInitWarps * 32, 6) HierTestInitial(const BakeParams P, const HierItem* __restrict__ hierItems,
                                                                        const unsigned long long* __restrict__ regionStart,
@@ -1015,7 +1016,10 @@ __global__ void __launch_bounds__(128, OMM_LEAF_MIN_BLOCKS) HierLeaves(const Bak
             uint32_t st = 0;
             if (index < (1u << (2 * hi.level))) {  // a level-0 item has one micro-triangle in its only "4-region"
                 if (hi.ok) {
-                    // (a single-micro-triangle TestRegion first was measured slower: the leaf's own edge filter (D) does the same work)
+                    // (a single-micro-triangle TestRegion first was measured slower: the leaf's own edge filter (D) does the same work.  So was, in
+                    // round 2, a warp-synchronous walk that deals the three edge tests of every lane needing them out over all 32 lanes each cell
+                    // iteration: parity-green, but 14.9 vs 12.5 ms classify on the same box -- an iteration has ~12 requesting lanes, i.e. two dense
+                    // rounds against the ~2.3 the short-circuiting per-lane calls take, and the shuffles and spills cost more than that saves.)
                     if (M == 1) st = (uint32_t)LeafClassify<Cfg>(P, P.tex.mips[0], hi, index);
                     else st = (uint32_t)LeafClassifyMips<Cfg>(P, [&](int k) { return k == 0 ? hi : LoadHierItem(its + k); }, index);
                 }
@@ -1189,11 +1193,12 @@ static const UniformDigests& GetUniformDigests() {
 // Four lanes per work item: lane j carries XXH64 accumulator j and consumes bytes [8j, 8j+8) of every 32-byte stripe (= 8 two-bit
 // states = half a state word), so the four accumulators of an item advance in parallel and a warp hashes eight items at once.
 constexpr int kItemPostItemsPerBlock = 64;
+constexpr uint32_t kBigHashLevel = 9;  // 4^9 bytes = 8192 stripes
 __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
                                                       const uint32_t* __restrict__ stateWords, uint32_t itemBegin, uint32_t itemEnd, float rejectionThreshold,
                                                       int disableSpecial, int keepExistingSpecial, const uint32_t* __restrict__ uniformVotes,
                                                       uint32_t stateGT, uint32_t stateLE, const UniformDigests table, uint64_t* __restrict__ digest,
-                                                      int32_t* special) {
+                                                      int32_t* special, uint32_t* __restrict__ bigList, uint32_t* __restrict__ bigCount) {
     // Phase 1, one thread per item of the block's range: items the hierarchical classifier proved uniform (all initial regions on
     // one side, HierTestInitial) get their constant digest without reading anything; the others are compacted into a list.
     __shared__ uint32_t sList[kItemPostItemsPerBlock * 4];
@@ -1215,7 +1220,12 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
                     done = true;
                 }
             }
-            if (!done) sList[atomicAdd(&sCount, 1u)] = wi;
+            if (!done) {
+                // blocks of 256 KiB and more: a warp of their own (ItemPostBigKernel) -- here their one sequential XXH64 chain would
+                // hold up the seven items sharing the warp, and runs at half the speed
+                if (bigList && items[wi].hashLevel >= kBigHashLevel) bigList[atomicAdd(bigCount, 1u)] = wi;
+                else sList[atomicAdd(&sCount, 1u)] = wi;
+            }
         }
     }
     __syncthreads();
@@ -1296,6 +1306,96 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
         if (!(keepExistingSpecial && special[w] != 0)) special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
     }
     }
+}
+
+// The same for ONE big block per warp.  XXH64 is four sequential chains  acc <- rotl(acc + in * P2, 31) * P1  over the 32-byte stripes, and a
+// level-12 block has 524 288 stripes: the digest of such a block is a latency chain nothing can shorten (the rotation does not commute with
+// the carries of the addition, so there is no parallel-prefix form).  What CAN be removed is everything else from the chain's issue slots: the
+// 32 lanes load, expand and pre-multiply eight stripes at a time (lane = stripe * 4 + accumulator), and the chain itself -- kept
+// redundantly in every lane for accumulator lane & 3, so there is no divergence -- is a shuffle, a fused multiply-add and two funnel shifts
+// per stripe.  Config 5 (one level-12 item): 13.7 ms -> see DESIGN.md section 6.
+__global__ void __launch_bounds__(32) ItemPostBigKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
+                                                        const uint32_t* __restrict__ stateWords, const uint32_t* __restrict__ bigList,
+                                                        const uint32_t* __restrict__ bigCount, float rejectionThreshold, int disableSpecial, int keepExistingSpecial,
+                                                        uint64_t* __restrict__ digest, int32_t* special) {
+    if (blockIdx.x >= *bigCount) return;
+    const uint32_t w = bigList[blockIdx.x], lane = threadIdx.x;
+    const uint32_t level = items[w].level;
+    const uint32_t n = 1u << (2 * level);                   // micro-triangles of the item now (uniformity / rejection test)
+    const uint32_t nHash = 1u << (2 * items[w].hashLevel);  // bytes the SDK's digest covers (>= n, differs only after Compress)
+    const uint32_t* words = stateWords + wordStart[w];
+    const uint32_t fullWords = n >> 4, numBatches = nHash >> 8;  // a batch = 8 stripes = 256 bytes = 16 state words
+    const uint32_t j = lane & 3u, t = lane >> 2, half = j & 1u, wordInBatch = 2u * t + (j >> 1);
+    const uint32_t s0 = __ldg(words) & 3u, pattern = s0 * 0x55555555u;
+    uint32_t diff = 0, known = 0;
+    auto fetch = [&](uint32_t b) -> uint64_t {
+        const uint32_t wi = 16u * b + wordInBatch;
+        const uint32_t v = __ldg(words + wi);
+        if (half == 0 && wi < fullWords) {  // statistics once per word
+            diff |= v ^ pattern;
+            known += __popc(~(v >> 1) & 0x55555555u);
+        }
+        return Expand3State(half ? (v >> 16) : (v & 0xFFFFu)) * XP2;
+    };
+    uint64_t acc = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
+    uint64_t x = fetch(0);
+    for (uint32_t b = 0; b < numBatches; ++b) {
+        const uint64_t xNext = b + 1 < numBatches ? fetch(b + 1) : 0ull;
+        uint64_t xs[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) xs[q] = __shfl_sync(0xFFFFFFFFu, x, 4 * q + (int)j);
+        // s = acc + in * P2 of the pending round; every step is rotl(s, 31) * P1 + (next in * P2): one fused multiply-add on the chain
+        uint64_t s = acc + xs[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) s = Rotl64(s, 31) * XP1 + xs[q];
+        acc = Rotl64(s, 31) * XP1;
+        x = xNext;
+    }
+    diff = __reduce_or_sync(0xFFFFFFFFu, diff);
+    known = __reduce_add_sync(0xFFFFFFFFu, known);
+    const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2), v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+    if (lane != 0) return;
+    uint64_t h = Rotl64(v1, 1) + Rotl64(v2, 7) + Rotl64(v3, 12) + Rotl64(v4, 18);
+    h = XxhMerge(h, v1); h = XxhMerge(h, v2); h = XxhMerge(h, v3); h = XxhMerge(h, v4);
+    h += (uint64_t)nHash;
+    h = XxhAvalanche(h);
+    bool allEqual = diff == 0;
+    int common = (int)s0;
+    if (!allEqual && rejectionThreshold > 0.f) {
+        const float frac = (float)known / (float)n;
+        if (frac < rejectionThreshold) {
+            allEqual = true;
+            common = ommOpacityState_UnknownTransparent;
+        }
+    }
+    digest[w] = h;
+    if (!(keepExistingSpecial && special[w] != 0)) special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
+}
+
+// ItemPostKernel over [itemBegin, itemEnd) and, when the bake has blocks of level >= kBigHashLevel, ItemPostBigKernel over those of them
+struct BigItemList {
+    uint32_t* list = nullptr;   // device, capacity entries
+    uint32_t* count = nullptr;  // device
+    uint32_t capacity = 0;      // work items of level >= kBigHashLevel in the whole bake (0: no big kernel)
+};
+static cudaError_t LaunchItemPost(cudaStream_t stream, const ItemRec* items, const unsigned long long* wordStart, const uint32_t* stateWords, uint32_t itemBegin,
+                                  uint32_t itemEnd, float rejectionThreshold, int disableSpecial, int keepExistingSpecial, const uint32_t* uniformVotes, uint32_t stateGT,
+                                  uint32_t stateLE, uint64_t* digest, int32_t* special, const BigItemList& big, uint32_t* launches) {
+    if (itemEnd <= itemBegin) return cudaSuccess;
+    if (big.capacity) {
+        const cudaError_t e = cudaMemsetAsync(big.count, 0, sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return e;
+    }
+    const uint32_t n = itemEnd - itemBegin;
+    ItemPostKernel<<<(n + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(
+        items, wordStart, stateWords, itemBegin, itemEnd, rejectionThreshold, disableSpecial, keepExistingSpecial, uniformVotes, stateGT, stateLE, GetUniformDigests(), digest, special,
+        big.capacity ? big.list : nullptr, big.count);
+    (*launches)++;
+    if (big.capacity) {
+        ItemPostBigKernel<<<big.capacity, 32, 0, stream>>>(items, wordStart, stateWords, big.list, big.count, rejectionThreshold, disableSpecial, keepExistingSpecial, digest, special);
+        (*launches)++;
+    }
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -2458,6 +2558,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     unsigned long long* runBytes = nullptr;
     unsigned long long worstBytes = 0;
     uint32_t streamHost[4] = {0, 0, 0, 0};  // [0] descriptors emitted by the chunks, [1] conflict flag of the optimistic dedup
+    BigItemList bigItems;  // work items whose blocks get a warp of their own in the post pass
     uint32_t* stateWords = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
     uint64_t* digest = nullptr;
@@ -2700,6 +2801,11 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         CUDA_TRY(scratch.alloc(&offsetOfItem, (size_t)W + 1));
         CUDA_TRY(scratch.alloc(&shardOffDev, kMaxShards + 1));
         CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
+        for (uint32_t l = kBigHashLevel; l <= (uint32_t)kMaxLevel; ++l) bigItems.capacity += countersHost[8 + l];
+        if (bigItems.capacity) {
+            CUDA_TRY(scratch.alloc(&bigItems.list, bigItems.capacity));
+            CUDA_TRY(scratch.alloc(&bigItems.count, 1));
+        }
         HierKernels hier{};
         const bool useHier = SelectHierKernels(P, &hier);
         const uint64_t tableCap = NextPow2((uint64_t)W * 2 + 16);
@@ -2774,8 +2880,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                         // are classified.  (PackItems writing the page-locked host array directly was measured first: 52 GB/s, as fast as
                         // the copy engine -- but the SMs it ran on stalled behind the PCIe writes and the whole bake took 5 ms longer.)
                         const uint32_t n = i1 - i0, gridC = (n + TPB - 1) / TPB;
-                        ItemPostKernel<<<(n + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(
-                            items, wordStart, stateWords, i0, i1, d.rejectionThreshold, 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE, GetUniformDigests(), digest, special);
+                        CUDA_TRY(LaunchItemPost(stream, items, wordStart, stateWords, i0, i1, d.rejectionThreshold, 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE, digest,
+                                                special, bigItems, &launches));
                         if (!disableDup) DigestInsertChunk<<<gridC, TPB, 0, stream>>>(digest, items, triItem, special, i0, i1, tableKeys, tableVals, tableCap - 1, conflictDev);
                         DigestResolve<<<gridC, TPB, 0, stream>>>(digest, items, triItem, i0, i1, tableKeys, tableVals, tableCap - 1, disableDup, survivor, special);
                         EmitInfo<<<gridC, TPB, 0, stream>>>(items, special, i0, i1, 0, (int)d.format, hist, emit, blockBytes);
@@ -2818,10 +2924,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
             if (itemEnd <= itemBegin) continue;
             // special-index scan + XXH64 of this rank's items (their state words are local already)
-            ItemPostKernel<<<(itemEnd - itemBegin + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold,
-                                                                              (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
-                                                                              GetUniformDigests(), digest, special);
-            launches++;
+            CUDA_TRY(LaunchItemPost(stream, items, wordStart, stateWords, itemBegin, itemEnd, d.rejectionThreshold, (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes,
+                                    (uint32_t)P.stateGT, (uint32_t)P.stateLE, digest, special, bigItems, &launches));
         }
         CUDA_TRY(cudaEventRecord(ev[5], stream));  // end of the per-item post pass
         if (world > 1) {
@@ -2979,10 +3083,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             // index now (and are then no candidates for downsampling)
             for (uint32_t w = 0; w < W; ++w) hSpecial[pass[w].pos] = pass[w].special;
             CUDA_TRY(cudaMemcpyAsync(special, hSpecial.data(), sizeof(int32_t) * W, cudaMemcpyHostToDevice, stream));
-            ItemPostKernel<<<(W + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
-                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
-                                                            GetUniformDigests(), digest, special);
-            launches++;
+            CUDA_TRY(LaunchItemPost(stream, items, wordStart, stateWords, 0, W, d.rejectionThreshold, (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, (uint32_t)P.stateGT,
+                                    (uint32_t)P.stateLE, digest, special, bigItems, &launches));
             if (d.maxArrayDataSize != 0xFFFFFFFFu) {
                 CUDA_TRY(cudaMemcpyAsync(hSpecial.data(), special, sizeof(int32_t) * W, cudaMemcpyDeviceToHost, stream));
                 CUDA_TRY(cudaStreamSynchronize(stream));
@@ -3004,10 +3106,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             UpdateItemLevels<<<gridW, TPB, 0, stream>>>(items, levelsDev, W);
             // ref: bake_cpu_impl.cpp:1969-1971 -- second exact dedup over ALL items with the current states, then the last promotion
             // (computed first here; the dedup overwrites duplicates with -1 exactly as the serial order does)
-            ItemPostKernel<<<(W + kItemPostItemsPerBlock * 4 - 1) / (kItemPostItemsPerBlock * 4), kItemPostItemsPerBlock * 4, 0, stream>>>(items, wordStart, stateWords, 0, W, d.rejectionThreshold,
-                                                            (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, (uint32_t)P.stateGT, (uint32_t)P.stateLE,
-                                                            GetUniformDigests(), digest, special);
-            launches += 2;
+            CUDA_TRY(LaunchItemPost(stream, items, wordStart, stateWords, 0, W, d.rejectionThreshold, (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 1, nullptr, (uint32_t)P.stateGT,
+                                    (uint32_t)P.stateLE, digest, special, bigItems, &launches));
+            launches++;
             if (!disableDup) {
                 FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
                 DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, 0, W, tableKeys, tableVals, cap - 1);
