@@ -65,6 +65,8 @@ def parse_args():
                     help="the full-config SDK bake of the cpu_baseline leg is replaced by a slice when a probe predicts it would take longer than this")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: target duration of all K + W steps together")
     ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs 2 and 5")
+    ap.add_argument("--result-mode", default="rank0", choices=["rank0", "replicated"],
+                    help="N > 1: where the complete arrayData ends up (ommB200SetShardedResultMode); rank0 = in one GPU's HBM / one host buffer, like at N = 1")
     return ap.parse_args()
 
 
@@ -288,6 +290,8 @@ def run_b200(a):
         dist.broadcast(idbuf, 0)
         raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
         assert lib.dll.ommB200InitSharding(baker.handle, rank, world, raw, 128) == capi.SUCCESS
+        assert lib.dll.ommB200SetShardedResultMode(baker.handle, capi.SHARDED_RESULT_ON_RANK0 if a.result_mode == "rank0" else capi.SHARDED_RESULT_REPLICATED) == capi.SUCCESS
+    everywhere = world == 1 or a.result_mode == "replicated"   # the complete result exists on every rank
     stream = torch.cuda.current_stream()
     stream_ptr = C.c_void_p(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -349,7 +353,8 @@ def run_b200(a):
             rc = lib.dll.ommCpuBake(baker.handle, C.byref(desc), C.byref(h))
             pdesc = C.POINTER(capi.CpuBakeResultDesc)()
             # the host copy of the result is materialised where it is consumed: on rank 0
-            rc2 = lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc)) if (rank == 0 or every_rank_downloads) else capi.SUCCESS
+            wants = rank == 0 or (every_rank_downloads and everywhere)
+            rc2 = lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc)) if wants else capi.SUCCESS
             dt = time.perf_counter() - t0
             assert rc == capi.SUCCESS and rc2 == capi.SUCCESS, (rc, rc2)
             dt = max_over_ranks(dt)
@@ -360,7 +365,7 @@ def run_b200(a):
             if it >= warmup:
                 secs.append(dt)
                 launches += tm.kernelLaunches
-            if keep_last and it == warmup + steps - 1 and (rank == 0 or every_rank_downloads):
+            if keep_last and it == warmup + steps - 1 and wants:
                 kept = _copy_result(pdesc.contents)
             lib.dll.ommCpuDestroyBakeResult(h)
         return secs, launches, info, kept
@@ -392,14 +397,15 @@ def run_b200(a):
     pg_s, _, _, _ = e2e_steps(desc_pg, 1, max(2, min(3, a.steps)))
     # ---- verification bake (outside every timed region): every rank downloads its copy of the result; digests must agree ----
     _, _, _, mine = e2e_steps(desc_pg, 0, 1, keep_last=True, every_rank_downloads=True)
-    my_sha = result_sha256(mine)
+    my_sha = result_sha256(mine) if mine is not None else None
     shas = [my_sha]
     if dist is not None:
         shas = [None] * world
         dist.all_gather_object(shas, my_sha)
+        shas = [x for x in shas if x is not None]
     golden = golden_digests()
     parity = {"config": "C3 full" if is_full_c3(a) else f"C3 variant ({a.tris} triangles, {a.tex}^2, level {a.level})", "result_sha256": shas[0],
-              "ranks_identical": len(set(shas)) == 1, "ranks": world}
+              "ranks_identical": len(set(shas)) == 1, "ranks": world, "ranks_holding_the_result": len(shas)}
     if is_full_c3(a) and "C3" in golden:
         parity["golden_sha256"] = golden["C3"]["sha256"]
         parity["matches_golden"] = shas[0] == golden["C3"]["sha256"] and len(set(shas)) == 1
@@ -416,11 +422,12 @@ def run_b200(a):
             sms, scl, sl, slast = resident_steps(sdesc, 2, 3)
             ss, sl2, _, sres = e2e_steps(sdesc, 1, 3, keep_last=True, every_rank_downloads=True)
             launches += sl + sl2
-            sha = result_sha256(sres)
+            sha = result_sha256(sres) if sres is not None else None
             sshas = [sha]
             if dist is not None:
                 sshas = [None] * world
                 dist.all_gather_object(sshas, sha)
+                sshas = [x for x in sshas if x is not None]
             sutris = int(slast["my_utris"]) if world == 1 else None
             entry = {"workload": swl.name, "ms_per_step": statistics.median(sms), "classify_ms": statistics.median(scl), "item_post_ms": slast["item_post_ms"],
                      "post_ms": slast["post_ms"], "setup_ms": slast["setup_ms"], "gather_ms": slast["gather_ms"], "e2e_ms_per_step": 1e3 * statistics.median(ss),
@@ -474,7 +481,9 @@ def run_b200(a):
                        "work_items": last["work_items"], "array_data_bytes": last["array_bytes"], "desc_count": last["desc_count"],
                        "step_ms": [round(x, 3) for x in step_ms], "setup_ms": last["setup_ms"], "classify_ms": cls_ms, "post_ms": last["post_ms"],
                        "item_post_ms": last["item_post_ms"], "gather_ms": last["gather_ms"],
-                       "sharding": "none" if world == 1 else f"work items split over {world} ranks; one NCCL all-gather of 12-byte per-item records, blocks written to their final place over NVLink",
+                       "sharding": "none" if world == 1 else f"work items split over {world} ranks; one NCCL all-gather of 12-byte per-item records; every rank packs its shards to their final byte range; "
+                                   + ("ranges gathered into rank 0's HBM (resident) / written by every rank into one page-locked host window (ommCpuBake)" if a.result_mode == "rank0"
+                                      else "ranges broadcast in place to every rank"),
                        "secondary": secondary},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_info["h2d"], "d2h_bytes_per_step": e2e_info["d2h"],

@@ -426,16 +426,25 @@ OMM_API ommResult ommB200GetDeviceResultDesc(ommCpuBakeResult bakeResult, ommB20
 OMM_API ommResult ommB200DownloadResult(ommCpuBakeResult bakeResult);
 
 /*
- * Multi-GPU: one process per GPU.  Every rank calls the same bake with the same desc; work items are
- * sharded across ranks (contiguous unit-balanced runs, dealt in boustrophedon order when there are
- * several per rank); one all-gather of per-item records and of the state blocks that can still be
- * serialized precedes the (replicated) dedup / sort / offset merge.  Every rank then holds the complete
- * result in HBM; ommCpuGetBakeResultDesc / ommB200DownloadResult make the host copy on the ranks that
- * call them.  ncclUniqueIdBytes is the 128-byte ncclUniqueId created by rank 0 and
- * distributed by the launcher (bench.py uses torch.distributed for that).
+ * Multi-GPU: one process per GPU of one box.  Every rank calls the same bake with the same desc and the same input arrays (rank 0
+ * uploads them, the others receive them over NVLink); the work items, already in output order, are cut into contiguous unit-balanced
+ * runs ("shards", dealt in boustrophedon order when there are several per rank) which the ranks classify; ONE all-gather of 12 bytes
+ * per work item (block digest + special index) precedes the replicated dedup / offset merge; every rank then packs its own shards
+ * straight to their final byte range of arrayData, and the ranges are exchanged as ommB200SetShardedResultMode says.
+ * ncclUniqueIdBytes is the 128-byte ncclUniqueId created by rank 0 and distributed by the launcher (bench.py uses torch.distributed).
  */
 OMM_API ommResult ommB200InitSharding(ommBaker baker, int rank, int worldSize, const void* ncclUniqueIdBytes, size_t idSize);
 OMM_API ommResult ommB200GetNcclUniqueId(void* outBytes, size_t idSize);
+/* Where the complete arrayData of a sharded bake ends up (descriptors, index buffer and histograms are complete on every rank either way;
+ * set it alike on every rank before baking):
+ *   Replicated (default)  every rank: ommB200BakeResident leaves it in every GPU's HBM (one group of in-place NCCL broadcasts of the shards'
+ *                         byte ranges); after ommCpuBake any rank may ask for the host copy.
+ *   OnRank0               rank 0 only: ommB200BakeResident gathers the other ranks' byte ranges into rank 0's HBM (ncclSend / ncclRecv);
+ *                         ommCpuBake assembles the host copy in a page-locked window every rank writes over its own PCIe link, with no
+ *                         device-to-device traffic at all.  On the other ranks ommCpuGetBakeResultDesc, ommB200DownloadResult and
+ *                         ommB200GetDeviceResultDesc report INVALID_ARGUMENT. */
+typedef enum ommB200ShardedResultMode { ommB200ShardedResultMode_Replicated = 0, ommB200ShardedResultMode_OnRank0 = 1 } ommB200ShardedResultMode;
+OMM_API ommResult ommB200SetShardedResultMode(ommBaker baker, ommB200ShardedResultMode mode);
 /* The partition used by sharded bakes, exposed for tests: unitPrefix is the exclusive prefix sum (entries = items + 1,
  * last entry = total) of per-item warp units (max(4^level / 32, 1)); outFirstItem receives worldSize + 1 item indices. */
 OMM_API ommResult ommB200ComputeShardBounds(const uint64_t* unitPrefix, uint32_t entries, int worldSize, uint32_t* outFirstItem);

@@ -233,8 +233,9 @@ B200_SYMBOLS = [
     "ommDebugGetStats", "ommB200SetDevice", "ommB200GetDeviceCount", "ommB200GetLastBakeTimings", "ommB200StageInputs",
     "ommB200DestroyStagedInputs", "ommB200BakeResident", "ommB200GetDeviceResultDesc", "ommB200DownloadResult",
     "ommB200InitSharding", "ommB200GetNcclUniqueId", "ommB200ComputeShardBounds", "ommB200ShardsPerRank", "ommB200ShardOwner",
-    "ommB200TrimHostPool",
+    "ommB200TrimHostPool", "ommB200SetShardedResultMode",
 ]
+SHARDED_RESULT_REPLICATED, SHARDED_RESULT_ON_RANK0 = 0, 1
 
 
 class OmmLib:
@@ -318,6 +319,8 @@ class OmmLib:
             d.ommB200ShardsPerRank.argtypes = [C.c_int]
             d.ommB200ShardOwner.restype = C.c_int
             d.ommB200ShardOwner.argtypes = [C.c_int, C.c_int]
+            d.ommB200SetShardedResultMode.restype = C.c_int
+            d.ommB200SetShardedResultMode.argtypes = [C.c_void_p, C.c_int]
             d.ommB200TrimHostPool.restype = C.c_size_t
             d.ommB200TrimHostPool.argtypes = [C.c_size_t]
 

@@ -449,6 +449,7 @@ OMM_API ommResult ommCpuGetBakeResultDesc(ommCpuBakeResult bakeResult, const omm
     if (bakeResult == 0) return ommResult_INVALID_ARGUMENT;
     BakeResultObject* r = (BakeResultObject*)bakeResult;
     if (desc == nullptr) return r->log.InvalidArg("[Invalid Arg] - No BakeResultDesc provided");  // ref: bake_cpu_impl.h:113-120
+    if (!r->arrayOnThisRank) return r->log.InvalidArg("[omm-b200] the complete result of this sharded bake lives on rank 0 (ommB200ShardedResultMode_OnRank0)");
     if (!r->downloaded) {
         float d2hMs = 0.f;
         uint64_t d2hBytes = 0;
@@ -556,6 +557,9 @@ OMM_API ommResult ommB200BakeResident(ommBaker baker, ommB200StagedInputs staged
 OMM_API ommResult ommB200GetDeviceResultDesc(ommCpuBakeResult bakeResult, ommB200DeviceResultDesc* out) {
     if (bakeResult == 0 || out == nullptr) return ommResult_INVALID_ARGUMENT;
     const BakeResultObject* r = (const BakeResultObject*)bakeResult;
+    if (!r->arrayOnThisRank || !r->deviceArrayComplete)
+        return r->log.InvalidArg(r->arrayOnThisRank ? "[omm-b200] this result was assembled in host memory (sharded ommCpuBake, rank-0 mode); use ommB200BakeResident for a device-resident array"
+                                                    : "[omm-b200] the complete result of this sharded bake lives on rank 0 (ommB200ShardedResultMode_OnRank0)");
     out->arrayData = r->devArrayData;
     out->descArray = r->devDescArray;
     out->indexBuffer = r->devIndexBuffer;
@@ -568,6 +572,7 @@ OMM_API ommResult ommB200GetDeviceResultDesc(ommCpuBakeResult bakeResult, ommB20
 OMM_API ommResult ommB200DownloadResult(ommCpuBakeResult bakeResult) {
     if (bakeResult == 0) return ommResult_INVALID_ARGUMENT;
     BakeResultObject* r = (BakeResultObject*)bakeResult;
+    if (!r->arrayOnThisRank) return r->log.InvalidArg("[omm-b200] the complete result of this sharded bake lives on rank 0 (ommB200ShardedResultMode_OnRank0)");
     float ms = 0.f;
     uint64_t bytes = 0;
     const bool was = r->downloaded;
@@ -580,6 +585,12 @@ OMM_API ommResult ommB200InitSharding(ommBaker baker, int rank, int worldSize, c
     return InitSharding(HandlePtr<BakerObject>(baker), rank, worldSize, ncclUniqueIdBytes, idSize);
 }
 OMM_API ommResult ommB200GetNcclUniqueId(void* outBytes, size_t idSize) { return GetNcclUniqueId(outBytes, idSize); }
+OMM_API ommResult ommB200SetShardedResultMode(ommBaker baker, ommB200ShardedResultMode mode) {
+    if (baker == 0 || HandleTagOf(baker) != HandleTag::CpuBaker) return ommResult_INVALID_ARGUMENT;
+    if (mode != ommB200ShardedResultMode_Replicated && mode != ommB200ShardedResultMode_OnRank0) return ommResult_INVALID_ARGUMENT;
+    HandlePtr<BakerObject>(baker)->shard.resultMode = (int)mode;
+    return ommResult_SUCCESS;
+}
 OMM_API int ommB200ShardsPerRank(int worldSize) { return ShardsPerRankOf(worldSize); }
 OMM_API int ommB200ShardOwner(int shard, int worldSize) { return ShardOwnerOf(shard, worldSize); }
 OMM_API ommResult ommB200ComputeShardBounds(const uint64_t* unitPrefix, uint32_t entries, int worldSize, uint32_t* outFirstItem) {

@@ -2052,6 +2052,45 @@ static void ReleaseCellTables(TextureObject* tex, CellTables* set) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time.  The only collective of the path: an all-gather (with per-rank counts, issued as one group of
+// broadcasts) of the per-item state blocks, after which dedup / sort / offsets are computed redundantly on every rank.
+// ---------------------------------------------------------------------------------------------------------------------
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+static NcclApi& Nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+        api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
+        api.Send = (decltype(api.Send))dlsym(api.lib, "ncclSend");
+        api.Recv = (decltype(api.Recv))dlsym(api.lib, "ncclRecv");
+        api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+    });
+    return api;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // staging of the per-bake inputs
 // ---------------------------------------------------------------------------------------------------------------------
 // Largest vertex index the triangles use: it sizes the upload of the caller's UV buffer (nothing beyond the last referenced vertex may
@@ -2090,8 +2129,23 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
         CUDA_TRY(cudaEventCreate(&e0));
         CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, 0));
+        // Sharded baker: every rank is handed the same inputs (the call is collective), so only rank 0 sends them over PCIe and the
+        // others receive them over NVLink -- eight simultaneous uploads of the same 36 MB through one host ran at half speed.
+        const int world = baker->shard.world, rank = baker->shard.rank;
+        NcclApi& nccl = Nccl();
+        const ncclComm_t comm = (ncclComm_t)baker->shard.ncclComm;
+        const bool viaRoot = world > 1 && nccl.ok && comm != nullptr;
+        auto put = [&](void* dst, const void* src, size_t bytes) -> bool {
+            if (bytes == 0) return true;
+            if (!viaRoot || rank == 0) {
+                if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, 0) != cudaSuccess) return false;
+                out->h2dBytes += bytes;
+            }
+            return !viaRoot || nccl.Broadcast(dst, dst, bytes, ncclUint8, 0, comm, 0) == ncclSuccess;
+        };
+        out->h2dBytes = 0;
         CUDA_TRY(cudaMallocAsync(&out->devIndices, (indexBytes ? indexBytes : 4) + 8, 0));  // + the (aligned) max-index word
-        CUDA_TRY(cudaMemcpyAsync(out->devIndices, desc.indexBuffer, indexBytes, cudaMemcpyHostToDevice, 0));
+        if (!put(out->devIndices, desc.indexBuffer, indexBytes)) { rc = ommResult_FAILURE; goto cleanup; }
         if (usedIndices) {
             uint32_t* devMax = (uint32_t*)((uint8_t*)out->devIndices + ((indexBytes + 3) & ~(size_t)3));
             CUDA_TRY(cudaMemsetAsync(devMax, 0, 4, 0));
@@ -2104,12 +2158,10 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
         }
         out->texCoordBytes = (size_t)maxIndex * out->texCoordStride + TexCoordSize(desc.texCoordFormat);
         CUDA_TRY(cudaMallocAsync(&out->devTexCoords, out->texCoordBytes + 8, 0));
-        CUDA_TRY(cudaMemcpyAsync(out->devTexCoords, desc.texCoords, out->texCoordBytes, cudaMemcpyHostToDevice, 0));
-        out->h2dBytes = indexBytes + out->texCoordBytes;
+        if (!put(out->devTexCoords, desc.texCoords, out->texCoordBytes)) { rc = ommResult_FAILURE; goto cleanup; }
         if (desc.subdivisionLevels) {
             CUDA_TRY(cudaMallocAsync((void**)&out->devLevels, out->triangleCount ? out->triangleCount : 1, 0));
-            CUDA_TRY(cudaMemcpyAsync(out->devLevels, desc.subdivisionLevels, out->triangleCount, cudaMemcpyHostToDevice, 0));
-            out->h2dBytes += out->triangleCount;
+            if (!put(out->devLevels, desc.subdivisionLevels, out->triangleCount)) { rc = ommResult_FAILURE; goto cleanup; }
         }
         if (desc.formats) {
             // The SDK sizes its arrays from desc.format alone and then serializes every item (bake_cpu_impl.cpp:1763-1771): a per-triangle
@@ -2123,8 +2175,7 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
                 }
             }
             CUDA_TRY(cudaMallocAsync((void**)&out->devFormats, (size_t)(out->triangleCount ? out->triangleCount : 1) * 4, 0));
-            CUDA_TRY(cudaMemcpyAsync(out->devFormats, desc.formats, (size_t)out->triangleCount * 4, cudaMemcpyHostToDevice, 0));
-            out->h2dBytes += (uint64_t)out->triangleCount * 4;
+            if (!put(out->devFormats, desc.formats, (size_t)out->triangleCount * 4)) { rc = ommResult_FAILURE; goto cleanup; }
         }
         CUDA_TRY(cudaEventRecord(e1, 0));
         CUDA_TRY(cudaEventSynchronize(e1));
@@ -2177,41 +2228,6 @@ struct Scratch {
         ptrs.clear();
     }
 };
-
-// ---------------------------------------------------------------------------------------------------------------------
-// NCCL, bound at run time.  The only collective of the path: an all-gather (with per-rank counts, issued as one group of
-// broadcasts) of the per-item state blocks, after which dedup / sort / offsets are computed redundantly on every rank.
-// ---------------------------------------------------------------------------------------------------------------------
-struct NcclApi {
-    void* lib = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
-    bool ok = false;
-};
-static NcclApi& Nccl() {
-    static NcclApi api;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        const char* names[] = {"libnccl.so.2", "libnccl.so"};
-        for (const char* n : names) {
-            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
-            if (api.lib) break;
-        }
-        if (!api.lib) return;
-        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
-        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
-        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
-        api.Broadcast = (decltype(api.Broadcast))dlsym(api.lib, "ncclBroadcast");
-        api.GroupStart = (decltype(api.GroupStart))dlsym(api.lib, "ncclGroupStart");
-        api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.lib, "ncclGroupEnd");
-        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Broadcast && api.GroupStart && api.GroupEnd;
-    });
-    return api;
-}
 
 struct ShardBound {
     unsigned long long unit, word, node;
@@ -3237,16 +3253,28 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 }
                 if (window) CUDA_TRY(cudaEventRecord(copyEv[1], copyStream));
                 if (gatherEv[1]) CUDA_TRY(cudaEventRecord(gatherEv[1], stream));
-                bool ncclOk = nccl.GroupStart() == ncclSuccess;
-                for (int r = 0; r < numShards && ncclOk; ++r) {
-                    const size_t count = (size_t)(shardOff[r + 1] - shardOff[r]);
-                    uint8_t* seg = (uint8_t*)res->devArrayData + shardOff[r];
-                    if (count) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint8, ShardOwner(r, world), comm, stream) == ncclSuccess;
+                const bool onRank0 = baker->shard.resultMode == 1;
+                bool ncclOk = true;
+                if (onRank0 && windowProtocol) {
+                    // the array is being assembled in host memory by all ranks: nothing crosses NVLink
+                    if (rank == 0) res->deviceArrayComplete = false;
+                } else {
+                    ncclOk = nccl.GroupStart() == ncclSuccess;
+                    for (int r = 0; r < numShards && ncclOk; ++r) {
+                        const size_t count = (size_t)(shardOff[r + 1] - shardOff[r]);
+                        uint8_t* seg = (uint8_t*)res->devArrayData + shardOff[r];
+                        const int owner = ShardOwner(r, world);
+                        if (!count) continue;
+                        if (!onRank0) ncclOk = nccl.Broadcast(seg, seg, count, ncclUint8, owner, comm, stream) == ncclSuccess;
+                        else if (owner != 0 && rank == owner) ncclOk = nccl.Send(seg, count, ncclUint8, 0, comm, stream) == ncclSuccess;
+                        else if (owner != 0 && rank == 0) ncclOk = nccl.Recv(seg, count, ncclUint8, owner, comm, stream) == ncclSuccess;
+                    }
+                    ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
                 }
-                ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
+                if (onRank0 && rank != 0) res->arrayOnThisRank = false;
                 if (gatherEv[2]) CUDA_TRY(cudaEventRecord(gatherEv[2], stream));
                 if (!ncclOk) {
-                    log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL all-gather of the packed blocks failed");
+                    log.Log(ommMessageSeverity_Fatal, "[omm-b200] NCCL exchange of the packed blocks failed");
                     rc = ommResult_FAILURE;
                     goto cleanup;
                 }
@@ -3344,8 +3372,14 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 shm_unlink(name);
                 window->unlinked = true;
             }
-            if (failed) window->inUse = false;  // some rank could not write its part: the result is downloaded the ordinary way on request
-            else {
+            if (failed) {
+                window->inUse = false;  // some rank could not write its part: the result is downloaded the ordinary way on request ...
+                if (baker->shard.resultMode == 1) {  // ... which only works when this GPU holds the whole array
+                    log.Log(ommMessageSeverity_Fatal, "[omm-b200] a rank could not write its shards to the shared host window");
+                    rc = ommResult_FAILURE;
+                    goto cleanup;
+                }
+            } else {
                 res->hostArrayData = window->ptr;
                 res->sharedWindowId = window->id;
                 res->arrayDataDownloaded = true;

@@ -162,6 +162,8 @@ struct BakeResultObject {
     float earlyD2hMs = 0.f;
     bool arrayDataFromPinnedPool = false;  // hostArrayData came from the library's page-locked pool (default allocator only)
     int sharedWindowId = -1;               // hostArrayData is a SharedHostWindow of the baker's sharding (root rank of a sharded ommCpuBake)
+    bool arrayOnThisRank = true;           // false: sharded bake in rank-0 mode, seen from another rank (descriptors and index buffer only)
+    bool deviceArrayComplete = true;       // false: rank 0 of a sharded ommCpuBake in rank-0 mode -- the array was assembled in host memory only
     bool usesDefaultAllocator = false;
     struct BakerObject* baker = nullptr;
 };
@@ -199,6 +201,7 @@ struct ShardState {
     ShmControl* ctl = nullptr;
     unsigned long long idHash = 0;  // names of the shared-memory objects derive from the ncclUniqueId
     unsigned long long bakeSeq = 0; // sharded ommCpuBake calls so far (the same number on every rank: the call is collective)
+    int resultMode = 0;             // ommB200ShardedResultMode: 0 = every rank gets the complete array, 1 = rank 0 only
     std::vector<SharedHostWindow> windows;
 };
 

@@ -42,12 +42,15 @@ def main():
         "c3_nearest": (W.config3(num_tris=1500, tex_size=256, level=5), dict(filter=capi.FILTER_NEAREST)),
         "c3_near_duplicates": (W.config3(num_tris=600, tex_size=128, level=4), dict(bake_flags=capi.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION)),
         "three_items": W.config3(num_tris=3, tex_size=64, level=3),  # fewer work items than shards
+        # the complete array on rank 0 only: gathered over NVLink (resident) / assembled in the shared page-locked window (ommCpuBake, > 1 MiB)
+        "c3_on_rank0": (W.config3(num_tris=9000, tex_size=1024, level=6), dict(), "rank0"),
     }
     out = {}
     for name, wl in cases.items():
-        over = {}
+        over, mode = {}, "replicated"
         if isinstance(wl, tuple):
-            wl, over = wl
+            mode = wl[2] if len(wl) > 2 else "replicated"
+            wl, over = wl[0], wl[1]
         # single-GPU result on this rank
         with Baker(lib) as b:
             inp, tex = W.make_input(b, wl, **over)
@@ -64,8 +67,42 @@ def main():
         raw = (C.c_uint8 * 128)(*idbuf.cpu().tolist())
         assert lib.dll.ommB200InitSharding(b.handle, rank, world, raw, 128) == capi.SUCCESS
         inp, tex = W.make_input(b, wl, **over)
-        sharded = b.bake(inp)
-        mine = sharded.timings.microTriangles
+        if mode == "rank0":
+            assert lib.dll.ommB200SetShardedResultMode(b.handle, capi.SHARDED_RESULT_ON_RANK0) == capi.SUCCESS
+            desc = inp.to_desc()
+            # ommCpuBake: host copy assembled by all ranks; complete on rank 0, refused elsewhere
+            rc, h = b.bake_raw(desc)
+            assert rc == capi.SUCCESS
+            pdesc = C.POINTER(capi.CpuBakeResultDesc)()
+            rc = lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc))
+            if rank == 0:
+                assert rc == capi.SUCCESS
+                from omm_b200.baker import _copy_result
+                assert _copy_result(pdesc.contents).diff(single) == [], f"{name}: host copy on rank 0 differs from the single-GPU result"
+            else:
+                assert rc == capi.INVALID_ARGUMENT
+            lib.dll.ommCpuDestroyBakeResult(h)
+            # ommB200BakeResident: gathered into rank 0's HBM
+            staged = C.c_void_p()
+            assert lib.dll.ommB200StageInputs(b.handle, C.byref(desc), C.byref(staged)) == capi.SUCCESS
+            h = C.c_void_p()
+            assert lib.dll.ommB200BakeResident(b.handle, staged, None, C.byref(h)) == capi.SUCCESS
+            rc = lib.dll.ommB200DownloadResult(h)
+            assert rc == (capi.SUCCESS if rank == 0 else capi.INVALID_ARGUMENT)
+            if rank == 0:
+                assert lib.dll.ommCpuGetBakeResultDesc(h, C.byref(pdesc)) == capi.SUCCESS
+                sharded = _copy_result(pdesc.contents)
+                assert sharded.diff(single) == [], f"{name}: resident result gathered on rank 0 differs from the single-GPU result"
+            else:
+                sharded = single
+            t2 = capi.B200BakeTimings()
+            lib.dll.ommB200GetLastBakeTimings(b.handle, C.byref(t2))
+            mine = t2.microTriangles
+            lib.dll.ommCpuDestroyBakeResult(h)
+            lib.dll.ommB200DestroyStagedInputs(staged)
+        else:
+            sharded = b.bake(inp)
+            mine = sharded.timings.microTriangles
         tex.destroy()
         b.destroy()
         assert sharded.diff(single) == [], f"rank {rank} {name}: sharded result differs from the single-GPU result"
