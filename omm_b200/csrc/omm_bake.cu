@@ -76,6 +76,65 @@ struct NvtxRange {
         if (on) Nvtx().pop();
     }
 };
+// Events and non-blocking streams are recycled across bakes (per process and device): creating and destroying the dozen a bake uses cost
+// ~0.35 ms of host time per call -- 2 % of a config-3 bake on one GPU, 10 % of its eighth on eight.
+struct CudaObjectPool {
+    std::mutex mu;
+    std::vector<cudaEvent_t> timing[64], plain[64];
+    std::vector<cudaStream_t> streams[64];
+};
+static CudaObjectPool& ObjectPool() {
+    static CudaObjectPool* pool = new CudaObjectPool();  // never destroyed: CUDA may be gone by the time static destructors run
+    return *pool;
+}
+static int PoolDevice() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) cudaGetLastError();
+    return d >= 0 && d < 64 ? d : 0;
+}
+static cudaError_t PoolEventCreate(cudaEvent_t* e, bool timing = true) {
+    CudaObjectPool& p = ObjectPool();
+    const int d = PoolDevice();
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        std::vector<cudaEvent_t>& v = timing ? p.timing[d] : p.plain[d];
+        if (!v.empty()) {
+            *e = v.back();
+            v.pop_back();
+            return cudaSuccess;
+        }
+    }
+    return timing ? cudaEventCreate(e) : cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+}
+static void PoolEventRelease(cudaEvent_t e, bool timing = true) {
+    if (!e) return;
+    CudaObjectPool& p = ObjectPool();
+    const int d = PoolDevice();
+    std::lock_guard<std::mutex> g(p.mu);
+    (timing ? p.timing[d] : p.plain[d]).push_back(e);
+}
+static cudaError_t PoolStreamCreate(cudaStream_t* s) {
+    CudaObjectPool& p = ObjectPool();
+    const int d = PoolDevice();
+    {
+        std::lock_guard<std::mutex> g(p.mu);
+        if (!p.streams[d].empty()) {
+            *s = p.streams[d].back();
+            p.streams[d].pop_back();
+            return cudaSuccess;
+        }
+    }
+    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+}
+// (the caller has synchronised the stream: nothing of the finished bake is pending on it)
+static void PoolStreamRelease(cudaStream_t s) {
+    if (!s) return;
+    CudaObjectPool& p = ObjectPool();
+    const int d = PoolDevice();
+    std::lock_guard<std::mutex> g(p.mu);
+    p.streams[d].push_back(s);
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Work item record (one per unique UV triangle).
@@ -680,13 +739,29 @@ __global__ void HierPrepare(const BakeParams P, const ItemRec* __restrict__ item
 }
 
 __device__ __forceinline__ HierItem LoadHierItem(const HierItem* __restrict__ p) {
-    HierItem hi;
+    // five 16-byte loads, unpacked field by field: copying through a uint4 view of the struct made ptxas keep it on the stack
+    // (72-byte frame, 33 LDL in HierLeaves, profiles/r2_sass_*)
     const uint4* src = reinterpret_cast<const uint4*>(p);
-    uint4* dst = reinterpret_cast<uint4*>(&hi);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) dst[i] = __ldg(src + i);
+    const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3), e = __ldg(src + 4);
+    HierItem hi;
+    hi.p0 = make_float2(__uint_as_float(a.x), __uint_as_float(a.y));
+    hi.p1 = make_float2(__uint_as_float(a.z), __uint_as_float(a.w));
+    hi.p2 = make_float2(__uint_as_float(b.x), __uint_as_float(b.y));
+    hi.level = b.z;
+    hi.epsRegion = __uint_as_float(b.w);
+    hi.epsSingle = __uint_as_float(c.x);
+    hi.deltaEdge = __uint_as_float(c.y);
+    hi.kmin[0] = __uint_as_float(c.z); hi.kmin[1] = __uint_as_float(c.w); hi.kmin[2] = __uint_as_float(d.x);
+    hi.kmax[0] = __uint_as_float(d.y); hi.kmax[1] = __uint_as_float(d.z); hi.kmax[2] = __uint_as_float(d.w);
+    hi.pitX = __uint_as_float(e.x);
+    hi.pitY = __uint_as_float(e.y);
+    hi.ok = (int)e.z;
+    hi.pad = 0;
     return hi;
 }
+static_assert(offsetof(HierItem, level) == 24 && offsetof(HierItem, epsSingle) == 32 && offsetof(HierItem, kmin) == 40 && offsetof(HierItem, kmax) == 52 &&
+                  offsetof(HierItem, pitX) == 64 && offsetof(HierItem, ok) == 72,
+              "LoadHierItem unpacks this layout");
 
 // warp-aggregated append of (item, idx) for the lanes with `push`
 __device__ __forceinline__ void HierAppend(unsigned long long* __restrict__ list, unsigned long long* __restrict__ count, bool push, uint32_t item, uint32_t idx) {
@@ -2126,8 +2201,8 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
         const size_t usedIndices = (size_t)out->triangleCount * 3;
         const size_t indexBytes = usedIndices * IndexSize(desc.indexFormat);
         uint32_t maxIndex = 0;
-        CUDA_TRY(cudaEventCreate(&e0));
-        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(PoolEventCreate(&e0));
+        CUDA_TRY(PoolEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, 0));
         // Sharded baker: every rank is handed the same inputs (the call is collective), so only rank 0 sends them over PCIe and the
         // others receive them over NVLink -- eight simultaneous uploads of the same 36 MB through one host ran at half speed.
@@ -2182,8 +2257,8 @@ ommResult StageInputs(BakerObject* baker, const ommCpuBakeInputDesc& desc, Stage
         CUDA_TRY(cudaEventElapsedTime(&out->h2dMs, e0, e1));
     }
 cleanup:
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
+    PoolEventRelease(e0);
+    PoolEventRelease(e1);
     if (rc != ommResult_SUCCESS) DestroyStagedDevice(out);
     return rc;
 }
@@ -2608,7 +2683,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     for (int v = 0; v < numShards; ++v)
         if (ShardOwner(v, world) == rank) owned.shard[owned.count++] = v;
     if (!stream) {
-        if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
+        if (PoolStreamCreate(&stream) != cudaSuccess) {
             cudaGetLastError();
             return ommResult_FAILURE;
         }
@@ -2616,7 +2691,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     }
     scratch.stream = stream;
     NvtxRange nvtxBake("omm-b200 bake");
-    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
+    for (int i = 0; i < 6; ++i) CUDA_TRY(PoolEventCreate(&ev[i]));
     CUDA_TRY(cudaEventRecord(ev[0], stream));
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, baker->device));
     HostTrace::Mark("stream + events created");
@@ -2910,7 +2985,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                         PackItems<<<std::min((uint32_t)std::max(sms, 1) * 32u, (n + 7) / 8), 256, 0, stream>>>(items, special, wordStart, stateWords, descOfItem, offsetOfItem, nullptr,
                                                                                                       nullptr, i0, i1, worstBytes, (uint8_t*)res->devArrayData, nullptr);
                         cudaEvent_t e = nullptr;
-                        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        CUDA_TRY(PoolEventCreate(&e, false));
                         chunkEvs.push_back(e);
                         CUDA_TRY(cudaEventRecord(e, stream));
                         launches += 10;
@@ -2954,7 +3029,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 SumMicroTriangles<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(items, itemBegin, itemEnd, workloadDev);
                 launches++;
             }
-            CUDA_TRY(cudaMemcpyAsync(&myMicroTris, workloadDev, 8, cudaMemcpyDeviceToHost, stream));
+            // (read back with the histograms: a copy into pageable memory here would hold the host until the classification has finished, and
+            // the exchange below would be enqueued -- and start -- that much later)
             NcclApi& nccl = Nccl();
             if (!nccl.ok || !baker->shard.ncclComm) {
                 log.Log(ommMessageSeverity_Fatal, "[omm-b200] sharded bake requested but NCCL is not initialised");
@@ -2977,7 +3053,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             }
             ncclOk = (nccl.GroupEnd() == ncclSuccess) && ncclOk;
             if (HostTrace::Enabled()) {
-                for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&gatherEv[i]));
+                for (int i = 0; i < 3; ++i) CUDA_TRY(PoolEventCreate(&gatherEv[i]));
                 CUDA_TRY(cudaEventRecord(gatherEv[0], stream));
             }
             if (!ncclOk) {
@@ -3004,9 +3080,9 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             WriteDescs<<<(W + TPB - 1) / TPB, TPB, 0, stream>>>(items, special, descOfItem, offsetOfItem, 0, W, (ommCpuOpacityMicromapDesc*)res->devDescArray);
             WriteIndexBuffer<<<gridT, TPB, 0, stream>>>(triFinal, special, descOfItem, T, (int)d.unresolvedTriState, indexBytes, res->devIndexBuffer);
             launches += 3;
-            CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreate(&copyEv[0]));
-            CUDA_TRY(cudaEventCreate(&copyEv[1]));
+            CUDA_TRY(PoolStreamCreate(&copyStream));
+            CUDA_TRY(PoolEventCreate(&copyEv[0]));
+            CUDA_TRY(PoolEventCreate(&copyEv[1]));
             {
                 unsigned long long sent = 0;
                 for (size_t c = 0; c < chunkEvs.size(); ++c) {
@@ -3031,10 +3107,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 // a later chunk held the true survivor of a digest an earlier chunk had already emitted: merge and pack again, the ordinary way
                 streamFallback = true;
                 CUDA_TRY(cudaStreamSynchronize(copyStream));
-                CUDA_TRY(cudaStreamDestroy(copyStream));
+                PoolStreamRelease(copyStream);
                 copyStream = nullptr;
                 for (int i = 0; i < 2; ++i) {
-                    cudaEventDestroy(copyEv[i]);
+                    PoolEventRelease(copyEv[i]);
                     copyEv[i] = nullptr;
                 }
                 CUDA_TRY(cudaMemsetAsync(hist, 0, 64 * sizeof(uint32_t), stream));
@@ -3148,6 +3224,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches += 7;
             CUDA_TRY(cudaMemcpyAsync(histHost, hist, sizeof(histHost), cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaMemcpyAsync(shardOff, shardOffDev, sizeof(unsigned long long) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
+            if (world > 1) CUDA_TRY(cudaMemcpyAsync(&myMicroTris, workloadDev, 8, cudaMemcpyDeviceToHost, stream));
             CUDA_TRY(cudaStreamSynchronize(stream));
             HostTrace::Mark("    histograms read (host sync 2)");
         }
@@ -3230,10 +3307,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     if (!window && baker->shard.ctl->winId >= 0) baker->shard.ctl->failSeq.store(baker->shard.bakeSeq, std::memory_order_release);
                     if (baker->shard.ctl->winId < 0) windowProtocol = false;  // the root has no window: every rank sees that
                     if (window) {
-                        CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
-                        CUDA_TRY(cudaEventCreate(&copyEv[0]));
-                        CUDA_TRY(cudaEventCreate(&copyEv[1]));
-                        CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+                        CUDA_TRY(PoolStreamCreate(&copyStream));
+                        CUDA_TRY(PoolEventCreate(&copyEv[0]));
+                        CUDA_TRY(PoolEventCreate(&copyEv[1]));
+                        CUDA_TRY(PoolEventCreate(&sliceEv, false));
                         CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
                     }
                 }
@@ -3294,10 +3371,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                         CUDA_TRY(cudaMemcpyAsync(&sliceOffset[i], offsetOfItem + sliceItem[i], 8, cudaMemcpyDeviceToHost, stream));
                     }
                     CUDA_TRY(cudaStreamSynchronize(stream));
-                    CUDA_TRY(cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking));
-                    CUDA_TRY(cudaEventCreate(&copyEv[0]));
-                    CUDA_TRY(cudaEventCreate(&copyEv[1]));
-                    CUDA_TRY(cudaEventCreateWithFlags(&sliceEv, cudaEventDisableTiming));
+                    CUDA_TRY(PoolStreamCreate(&copyStream));
+                    CUDA_TRY(PoolEventCreate(&copyEv[0]));
+                    CUDA_TRY(PoolEventCreate(&copyEv[1]));
+                    CUDA_TRY(PoolEventCreate(&sliceEv, false));
                     CUDA_TRY(cudaEventRecord(copyEv[0], copyStream));
                 }
                 sliceItem[slices] = W; sliceOffset[slices] = arrayBytes;
@@ -3411,23 +3488,23 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 cleanup:
     scratch.freeAll();
     for (int i = 0; i < 6; ++i)
-        if (ev[i]) cudaEventDestroy(ev[i]);
+        PoolEventRelease(ev[i]);
     if (cellTables) {
         if (rc != ommResult_SUCCESS) cudaStreamSynchronize(stream);  // kernels of a failed bake may still be reading the tables
         ReleaseCellTables(tex, cellTables);
     }
     if (ownStream) {
         cudaStreamSynchronize(stream);
-        cudaStreamDestroy(stream);
+        PoolStreamRelease(stream);
     }
     if (copyStream) {
         cudaStreamSynchronize(copyStream);
-        cudaStreamDestroy(copyStream);
+        PoolStreamRelease(copyStream);
     }
-    for (cudaEvent_t e : chunkEvs) cudaEventDestroy(e);
+    for (cudaEvent_t e : chunkEvs) PoolEventRelease(e, false);
     if (chunkEndHost) PinnedPoolRelease(chunkEndHost);
-    for (cudaEvent_t e : {copyEv[0], copyEv[1], sliceEv, gatherEv[0], gatherEv[1], gatherEv[2]})
-        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {copyEv[0], copyEv[1], gatherEv[0], gatherEv[1], gatherEv[2]}) PoolEventRelease(e);
+    PoolEventRelease(sliceEv, false);
     if (rc != ommResult_SUCCESS) {
         cudaGetLastError();
         DestroyResultDevice(res);
@@ -3442,8 +3519,8 @@ ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes
     if (res->downloaded) return ommResult_SUCCESS;
     const size_t idxBytes = (size_t)res->indexCount * (res->indexFormat == ommIndexFormat_UINT_32 ? 4 : (res->indexFormat == ommIndexFormat_UINT_16 ? 2 : 1));
     CUDA_TRY(cudaSetDevice(res->device));
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(PoolEventCreate(&e0));
+    CUDA_TRY(PoolEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, 0));
     if (res->descCount) {
         res->hostDescArray = res->alloc.alloc((size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), 64);
@@ -3475,8 +3552,8 @@ ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes
     res->desc.indexHistogram = res->hostIndexHist;
     res->downloaded = true;
 cleanup:
-    if (e0) cudaEventDestroy(e0);
-    if (e1) cudaEventDestroy(e1);
+    PoolEventRelease(e0);
+    PoolEventRelease(e1);
     return rc;
 }
 
