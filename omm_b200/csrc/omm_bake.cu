@@ -20,6 +20,7 @@
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -2509,7 +2510,10 @@ static SharedHostWindow* AcquireSharedWindow(ShardState& sh, size_t bytes, const
             w.capacity = (bytes + (bytes >> 3) + ((size_t)2 << 20)) & ~(((size_t)2 << 20) - 1);
             ShmName(name, sizeof(name), sh.idHash, "w", w.id);
             shm_unlink(name);
-            w.ptr = MapShm(name, w.capacity, true);
+            // a tmpfs that cannot back the window would only fail when its pages are touched (SIGBUS): ask first
+            struct statvfs vfs;
+            const bool roomy = statvfs("/dev/shm", &vfs) != 0 || (unsigned long long)vfs.f_bavail * vfs.f_frsize > (unsigned long long)w.capacity + ((unsigned long long)64 << 20);
+            w.ptr = roomy ? MapShm(name, w.capacity, true) : nullptr;
             if (w.ptr && cudaHostRegister(w.ptr, w.capacity, cudaHostRegisterPortable) != cudaSuccess) {
                 cudaGetLastError();
                 munmap(w.ptr, w.capacity);
