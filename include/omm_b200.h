@@ -446,7 +446,8 @@ OMM_API ommResult ommB200GetNcclUniqueId(void* outBytes, size_t idSize);
 typedef enum ommB200ShardedResultMode { ommB200ShardedResultMode_Replicated = 0, ommB200ShardedResultMode_OnRank0 = 1 } ommB200ShardedResultMode;
 OMM_API ommResult ommB200SetShardedResultMode(ommBaker baker, ommB200ShardedResultMode mode);
 /* The partition used by sharded bakes, exposed for tests: unitPrefix is the exclusive prefix sum (entries = items + 1,
- * last entry = total) of per-item warp units (max(4^level / 32, 1)); outFirstItem receives worldSize + 1 item indices. */
+ * last entry = total) of the per-item balancing weights -- warp units (max(4^level / 32, 1)), times a level-line density
+ * factor estimated from the texture when the baker is sharded; outFirstItem receives worldSize + 1 item indices. */
 OMM_API ommResult ommB200ComputeShardBounds(const uint64_t* unitPrefix, uint32_t entries, int worldSize, uint32_t* outFirstItem);
 /* How the runs are dealt (exposed for tests): a sharded bake cuts the work items into worldSize x ommB200ShardsPerRank(worldSize)
  * runs with the partition above (called with that product as its worldSize); run s is classified by rank ommB200ShardOwner(s). */

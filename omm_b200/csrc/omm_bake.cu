@@ -21,6 +21,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/statvfs.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -2305,6 +2306,47 @@ struct Scratch {
     }
 };
 
+// Sharded bakes: what a work item will cost to classify, for the cut of the shards.  The time of the hierarchical classifier follows the
+// level line -- regions it does not touch are proved in bulk, micro-triangles it crosses run the exact edge tests -- so contiguous shards of
+// equal micro-triangle count differ by 8-12 % in time.  (Opt-in, see CostBalanceDisabled: folded shards already average that out.)  Proxy: a 5 x 5 lattice of texels over the item's
+// bounding box; the share of neighbouring lattice pairs on different sides of the cutoff estimates the density of the level line
+// (Cauchy-Crofton), and   cost = units * (8 + 128 * share)   weighs an item the line fills 17 times an untouched one (the ratio of the leaf
+// path to the bulk path per micro-triangle at config 3).  Only the balance depends on it, never a result.
+template <bool kFp32>
+__global__ void ItemCostKernel(const BakeParams P, const ItemRec* __restrict__ items, const uint32_t* __restrict__ numItemsPtr, uint32_t slots,
+                               const unsigned long long* __restrict__ itemUnits, unsigned long long* __restrict__ itemCost) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > slots) return;
+    if (s >= *numItemsPtr) {
+        itemCost[s] = 0ull;
+        return;
+    }
+    const ItemRec it = items[s];
+    const DevMip& m = P.tex.mips[0];
+    const float W = (float)m.w, H = (float)m.h;
+    const float x0 = fminf(fminf(it.p0.x, it.p1.x), it.p2.x) * W, x1 = fmaxf(fmaxf(it.p0.x, it.p1.x), it.p2.x) * W;
+    const float y0 = fminf(fminf(it.p0.y, it.p1.y), it.p2.y) * H, y1 = fmaxf(fmaxf(it.p0.y, it.p1.y), it.p2.y) * H;
+    uint32_t changes = 0;
+    if (x0 > -1e6f && x1 < 1e6f && y0 > -1e6f && y1 < 1e6f) {  // (also false for NaN)
+        uint32_t rows[5];
+        for (int j = 0; j < 5; ++j) {
+            const int ty = (int)floorf(y0 + (y1 - y0) * (0.25f * (float)j));
+            const int ay = Addr1Generic(P.addrMode, m.isPow2, ty, m.h, m.log2h);
+            uint32_t bits = 0;
+            for (int i = 0; i < 5; ++i) {
+                const int tx = (int)floorf(x0 + (x1 - x0) * (0.25f * (float)i));
+                const int ax = Addr1Generic(P.addrMode, m.isPow2, tx, m.w, m.log2w);
+                const float a = TexFetch<KernelCfg<kAddrGeneric, kFp32>>(P, m, ax, ay);
+                bits |= (P.cutoff < a ? 1u : 0u) << i;
+            }
+            rows[j] = bits;
+            changes += __popc((bits ^ (bits >> 1)) & 0xFu);
+            if (j) changes += __popc(bits ^ rows[j - 1]);
+        }
+    }
+    itemCost[s] = itemUnits[s] * (unsigned long long)(8u + (128u * changes) / 40u);
+}
+
 struct ShardBound {
     unsigned long long unit, word, node;
     uint32_t item, pad;
@@ -2339,6 +2381,15 @@ __host__ __device__ inline int ShardOwner(int shard, int world) {
     const int pass = shard / world, pos = shard % world;
     return (pass & 1) ? world - 1 - pos : pos;
 }
+// OMM_B200_COST_BALANCE=1 cuts the shards by the cost estimate of ItemCostKernel instead of by micro-triangle count.  OFF by default: measured
+// on two B200s at config 3 it does balance one shard per rank (rank 0 waits 0.09 instead of 0.65 ms in the record exchange) -- but two
+// count-balanced shards per rank dealt in boustrophedon order already end within the same total (7.87 ms against 7.94-7.96 with the
+// estimate, whose kernel and scan cost 0.07 ms on every rank): what a sharded classification loses is the fixed cost per shard
+// (2 x 6.45 ms of classification against 12.3 on one GPU), not the balance.
+static bool CostBalanceDisabled() {
+    static const bool on = getenv("OMM_B200_COST_BALANCE") != nullptr;
+    return !on;
+}
 static int ShardsPerRank(int world) {
     if (world <= 1) return 1;
     // Measured at config 3: two shards per rank win 2.3 % on two GPUs (8.22 -> 8.03 ms: no more waiting, +0.1 ms for the second chunk
@@ -2356,13 +2407,14 @@ struct OwnedShards {
     int count;
     int shard[kMaxShardsPerRank];
 };
-__global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart,
+__global__ void ShardBounds(const unsigned long long* __restrict__ weightStart /* prefix sums the shards are balanced by */,
+                            const unsigned long long* __restrict__ unitStart, const unsigned long long* __restrict__ wordStart,
                             const unsigned long long* __restrict__ nodeStart, uint32_t entries, int world /* number of shards */, OwnedShards owned,
                             unsigned long long chunkRegions, ShardBound* __restrict__ bounds, uint32_t* __restrict__ chunkFirstItem) {
     const int r = threadIdx.x;
     for (int k = 0; k < owned.count; ++k) {
         // chunks of the hierarchical classifier: runs of whole work items of an owned shard holding about `chunkRegions` initial regions each
-        const uint32_t ib = ShardFirstItem(unitStart, entries, world, owned.shard[k]), ie = ShardFirstItem(unitStart, entries, world, owned.shard[k] + 1);
+        const uint32_t ib = ShardFirstItem(weightStart, entries, world, owned.shard[k]), ie = ShardFirstItem(weightStart, entries, world, owned.shard[k] + 1);
         if (r <= kHierMaxChunks) {
             const unsigned long long cr = HierChunkRegions(nodeStart[ie] - nodeStart[ib], chunkRegions);
             const unsigned long long target = nodeStart[ib] + (unsigned long long)r * cr;
@@ -2376,7 +2428,7 @@ __global__ void ShardBounds(const unsigned long long* __restrict__ unitStart, co
         }
     }
     if (r > world) return;
-    const uint32_t lo = ShardFirstItem(unitStart, entries, world, r);
+    const uint32_t lo = ShardFirstItem(weightStart, entries, world, r);
     bounds[r].item = lo;
     bounds[r].unit = unitStart[lo];
     bounds[r].word = wordStart[lo];
@@ -2495,6 +2547,38 @@ static void* MapShm(const char* name, size_t bytes, bool create) {
     close(fd);
     return p == MAP_FAILED ? nullptr : p;
 }
+// Spread the pages of a fresh window over the NUMA nodes of the box (before they are touched): the GPUs of an 8-GPU box hang off two
+// sockets, and eight copy engines writing memory of ONE node reached 87 GB/s in total.  Best effort: containers may forbid mbind.
+static void InterleaveOverNumaNodes(void* ptr, size_t bytes) {
+    if (getenv("OMM_B200_NO_NUMA_INTERLEAVE")) return;
+    unsigned long mask = 0;
+    if (FILE* f = fopen("/sys/devices/system/node/online", "r")) {  // e.g. "0-1" or "0,2-3"
+        char buf[128] = {0};
+        if (fgets(buf, sizeof(buf), f)) {
+            for (char* p = buf; *p;) {
+                char* end = nullptr;
+                const long a = strtol(p, &end, 10);
+                if (end == p) break;
+                long b = a;
+                p = end;
+                if (*p == '-') {
+                    b = strtol(p + 1, &end, 10);
+                    p = end;
+                }
+                for (long n = a; n <= b && n < 64; ++n) mask |= 1ul << n;
+                if (*p == ',') ++p;
+                else break;
+            }
+        }
+        fclose(f);
+    }
+    if (__builtin_popcountl(mask) < 2) return;
+#if defined(SYS_mbind)
+    constexpr int kMpolInterleave = 3;
+    if (syscall(SYS_mbind, ptr, bytes, kMpolInterleave, &mask, (unsigned long)(8 * sizeof(mask) + 1), 0) != 0 && HostTrace::Enabled())
+        fprintf(stderr, "[omm-b200 trace] mbind(MPOL_INTERLEAVE) on the shared window was refused; pages stay on the creating rank's node\n");
+#endif
+}
 // The window the root's host copy of this bake's arrayData lives in (every rank returns its own mapping of the same memory).
 static SharedHostWindow* AcquireSharedWindow(ShardState& sh, size_t bytes, const Logger& log) {
     ShmControl* c = sh.ctl;
@@ -2514,6 +2598,7 @@ static SharedHostWindow* AcquireSharedWindow(ShardState& sh, size_t bytes, const
             struct statvfs vfs;
             const bool roomy = statvfs("/dev/shm", &vfs) != 0 || (unsigned long long)vfs.f_bavail * vfs.f_frsize > (unsigned long long)w.capacity + ((unsigned long long)64 << 20);
             w.ptr = roomy ? MapShm(name, w.capacity, true) : nullptr;
+            if (w.ptr) InterleaveOverNumaNodes(w.ptr, w.capacity);
             if (w.ptr && cudaHostRegister(w.ptr, w.capacity, cudaHostRegisterPortable) != cudaSuccess) {
                 cudaGetLastError();
                 munmap(w.ptr, w.capacity);
@@ -2843,7 +2928,19 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemNodes, nodeStart, (int)T + 1, stream));
             launches += 6;
         }
-        ShardBounds<<<1, 128, 0, stream>>>(unitStart, wordStart, nodeStart, T + 1, numShards, owned, hierChunkRegions, boundsDev, chunkFirstDev);
+        const unsigned long long* weightStart = unitStart;
+        if (world > 1 && !CostBalanceDisabled()) {
+            unsigned long long *itemCost = nullptr, *costStart = nullptr;
+            CUDA_TRY(scratch.alloc(&itemCost, (size_t)T + 1));
+            CUDA_TRY(scratch.alloc(&costStart, (size_t)T + 1));
+            if (P.tex.isFp32) ItemCostKernel<true><<<(T + 1 + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, counters + 2, T, itemUnits, itemCost);
+            else ItemCostKernel<false><<<(T + 1 + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, counters + 2, T, itemUnits, itemCost);
+            size_t tmp = cubTempBytes;
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(cubTemp, tmp, itemCost, costStart, (int)T + 1, stream));
+            weightStart = costStart;
+            launches += 3;
+        }
+        ShardBounds<<<1, 128, 0, stream>>>(weightStart, unitStart, wordStart, nodeStart, T + 1, numShards, owned, hierChunkRegions, boundsDev, chunkFirstDev);
         launches++;
         CUDA_TRY(cudaMemcpyAsync(countersHost, counters, sizeof(countersHost), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(bounds, boundsDev, sizeof(ShardBound) * (numShards + 1), cudaMemcpyDeviceToHost, stream));
