@@ -2288,14 +2288,46 @@ static uint64_t NextPow2(uint64_t v) {
     return p;
 }
 
-// Simple bump list of device allocations made during one bake (stream-ordered, freed at the end).
+// Device scratch of one bake (stream-ordered, freed at the end).  Requests below a quarter of a block are carved out of shared 128 MiB blocks: a
+// bake makes about fifty allocations, and fifty cudaMallocAsync / cudaFreeAsync pairs are 0.2 ms of host time -- in the launch-bound set-up
+// phase, and after each host read-back while the GPU waits for the next kernels, that time is on the critical path.
 struct Scratch {
     cudaStream_t stream;
     std::vector<void*> ptrs;
+    uint8_t* block = nullptr;
+    size_t blockSize = 0, blockUsed = 0;
+    static constexpr size_t kBlock = (size_t)128 << 20, kAlign = 256;
+    // OMM_B200_SCRATCH_BLOCKS=0: every request is an allocation of its own, so that compute-sanitizer sees the bounds of every array
+    // (scripts/sanitize_cases.py runs that way)
+    static bool Shared() {
+        static const bool on = [] {
+            const char* e = getenv("OMM_B200_SCRATCH_BLOCKS");
+            return !(e && e[0] == '0');
+        }();
+        return on;
+    }
     template <class T>
     cudaError_t alloc(T** p, size_t count) {
+        const size_t bytes = (((count ? count : 1) * sizeof(T)) + kAlign - 1) & ~(kAlign - 1);
+        if (Shared() && bytes <= kBlock / 4) {
+            if (blockUsed + bytes > blockSize) {
+                void* q = nullptr;
+                const cudaError_t e = cudaMallocAsync(&q, kBlock, stream);
+                if (e != cudaSuccess) {
+                    *p = nullptr;
+                    return e;
+                }
+                ptrs.push_back(q);
+                block = (uint8_t*)q;
+                blockSize = kBlock;
+                blockUsed = 0;
+            }
+            *p = (T*)(block + blockUsed);
+            blockUsed += bytes;
+            return cudaSuccess;
+        }
         void* q = nullptr;
-        cudaError_t e = cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), stream);
+        const cudaError_t e = cudaMallocAsync(&q, bytes, stream);
         if (e == cudaSuccess) ptrs.push_back(q);
         *p = (T*)q;
         return e;
@@ -2303,6 +2335,8 @@ struct Scratch {
     void freeAll() {
         for (void* p : ptrs) cudaFreeAsync(p, stream);
         ptrs.clear();
+        block = nullptr;
+        blockSize = blockUsed = 0;
     }
 };
 
@@ -2670,6 +2704,16 @@ __global__ void ShardByteOffsets(const unsigned long long* __restrict__ offsetOf
     if (r <= shards) out[r] = offsetOfItem[bounds[r].item];
 }
 
+struct HostReadback {
+    uint32_t counters[32];
+    uint32_t hist[52];
+    uint32_t stream[4];
+    ShardBound bounds[kMaxShards + 1];
+    uint32_t chunkFirst[kMaxShardsPerRank][kHierMaxChunks + 1];
+    unsigned long long shardOff[kMaxShards + 1];
+    unsigned long long totalUnits, totalWords, myMicroTris;
+};
+
 ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStream, BakeResultObject* res, ommB200BakeTimings* tm, bool earlyDownload) {
     const Logger& log = baker->log;
     ommResult rc = RequireDevice(log, baker->device);
@@ -2692,6 +2736,12 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     const ommIndexFormat ifmt = (allow8 && (int32_t)T <= 127 && !force32) ? ommIndexFormat_UINT_8 : (((int32_t)T <= 32767 && !force32) ? ommIndexFormat_UINT_16 : ommIndexFormat_UINT_32);
     const int indexBytes = ifmt == ommIndexFormat_UINT_8 ? 1 : (ifmt == ommIndexFormat_UINT_16 ? 2 : 4);
 
+    // Everything the host reads back from the device during a bake lives in one page-locked block: the copies are then really asynchronous
+    // (a copy into pageable memory holds the host until it has completed), so each of the two read-back points costs one round trip, not
+    // one per array.
+    HostReadback stackReadback;
+    HostReadback* pinnedReadback = (HostReadback*)PinnedPoolAcquire(sizeof(HostReadback));
+    HostReadback& hb = pinnedReadback ? *pinnedReadback : stackReadback;
     cudaStream_t stream = (cudaStream_t)userStream;
     bool ownStream = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -2716,7 +2766,6 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     unsigned long long *itemUnits = nullptr, *itemWords = nullptr, *unitStart = nullptr, *wordStart = nullptr, *itemNodes = nullptr, *nodeStart = nullptr;
     ShardBound* boundsDev = nullptr;
     uint32_t* chunkFirstDev = nullptr;
-    uint32_t chunkFirst[kMaxShardsPerRank][kHierMaxChunks + 1];
     const int numShards = world * ShardsPerRank(world);  // see ShardOwner
     OwnedShards owned{};
     // ommCpuBake on one GPU: the array is packed and written to the caller-visible host memory chunk by chunk WHILE later chunks are
@@ -2737,7 +2786,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     uint32_t *runDesc = nullptr, *conflictDev = nullptr;
     unsigned long long* runBytes = nullptr;
     unsigned long long worstBytes = 0;
-    uint32_t streamHost[4] = {0, 0, 0, 0};  // [0] descriptors emitted by the chunks, [1] conflict flag of the optimistic dedup
+    auto& streamHost = hb.stream;  // [0] descriptors emitted by the chunks, [1] conflict flag of the optimistic dedup, [2], [3] the pair that raised it
+    auto& chunkFirst = hb.chunkFirst;
     BigItemList bigItems;  // work items whose blocks get a warp of their own in the post pass
     uint32_t* stateWords = nullptr;
     uint32_t* uniformVotes = nullptr;  // per work item: initial regions proved above / below the cutoff (hierarchical classifier only)
@@ -2746,12 +2796,13 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     uint32_t *mergeRoot = nullptr, *survivor2 = nullptr;
     uint32_t *survivor = nullptr, *hist = nullptr, *sortKeysIn = nullptr, *sortValsIn = nullptr, *sortKeysOut = nullptr, *emit = nullptr, *descOfItem = nullptr;
     unsigned long long *blockBytes = nullptr, *offsetOfItem = nullptr, *shardOffDev = nullptr;
-    unsigned long long totalUnits = 0, totalWords = 0, microTris = 0, myMicroTris = 0;
-    unsigned long long shardOff[kMaxShards + 1];
+    unsigned long long microTris = 0;
+    unsigned long long &totalUnits = hb.totalUnits, &totalWords = hb.totalWords, &myMicroTris = hb.myMicroTris;
+    auto& shardOff = hb.shardOff;
     uint32_t W = 0;
-    uint32_t countersHost[32];
-    uint32_t histHost[52];
-    ShardBound bounds[kMaxShards + 1];
+    auto& countersHost = hb.counters;
+    auto& histHost = hb.hist;
+    auto& bounds = hb.bounds;
     uint32_t numDescs = 0;
     unsigned long long arrayBytes = 0;
     bool resort = false;  // Compress changed item levels: the serialized items are sorted again (see ResortKeys)
@@ -2763,10 +2814,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
 
     BakeParams P{};
     SetupArgs sa{};
-    memset(histHost, 0, sizeof(histHost));
-    memset(countersHost, 0, sizeof(countersHost));
-    memset(bounds, 0, sizeof(bounds));
-    memset(shardOff, 0, sizeof(shardOff));
+    memset(&hb, 0, sizeof(hb));
 
     if (world > kMaxShards) return ommResult_INVALID_ARGUMENT;
     for (int v = 0; v < numShards; ++v)
@@ -3602,6 +3650,7 @@ cleanup:
         cudaStreamSynchronize(copyStream);
         PoolStreamRelease(copyStream);
     }
+    if (pinnedReadback) PinnedPoolRelease(pinnedReadback);
     for (cudaEvent_t e : chunkEvs) PoolEventRelease(e, false);
     if (chunkEndHost) PinnedPoolRelease(chunkEndHost);
     for (cudaEvent_t e : {copyEv[0], copyEv[1], gatherEv[0], gatherEv[1], gatherEv[2]}) PoolEventRelease(e);

@@ -6,6 +6,8 @@ usage: compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck python sc
 import os
 import sys
 
+os.environ.setdefault("OMM_B200_SCRATCH_BLOCKS", "0")   # one allocation per array: the sanitizer sees every bound
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
