@@ -1479,16 +1479,16 @@ static cudaError_t LaunchItemPost(cudaStream_t stream, const ItemRec* items, con
 // K6: exact dedup on digests: the lowest item index with a digest survives (ref: bake_cpu_impl.cpp:1043-1063).
 // ---------------------------------------------------------------------------------------------------------------------
 // Table value = the item's first triangle: monotone in the SDK's work-item index, which the output order of the items (K3b) is not.
-// `skipSpecial`: items that carry a special index take no part (their survivor is themselves).  Such an item is never serialized, and every
-// item of its digest has the same content and therefore the same special index, so the index its triangles receive is the same whether
-// they are resolved through the digest's first-seen item (as the SDK does, bake_cpu_impl.cpp:1043-1063) or not -- but three quarters of the
-// work items of a typical bake are uniform and would otherwise queue on a handful of table entries.  Not used around the optional passes,
-// whose walk looks at the primitive counts of the survivors.
-__global__ void DigestInsert(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, const int32_t* __restrict__ skipSpecial, uint32_t itemBegin,
-                             uint32_t itemEnd, uint64_t* keys, uint32_t* vals, uint64_t mask) {
-    // lanes with equal digests elect the lowest first triangle among themselves first, so the table sees one atomic per distinct digest per warp
+// EVERY item takes part, also those with a special index: the digest is over the 3-state bytes (UnknownTransparent folded into UnknownOpaque),
+// so a fully UnknownOpaque item (special index) and an item mixing the two unknown states (none) share a digest, and the SDK lets whichever
+// came first absorb the other.  Leaving the special ones out -- tried in round 2 to spare the table the three quarters of the items that are
+// uniform -- changed index buffers; the randomized GPU campaign caught it on its 28th bake.
+__global__ void DigestInsert(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, uint32_t itemBegin, uint32_t itemEnd, uint64_t* keys,
+                             uint32_t* vals, uint64_t mask) {
+    // Most items of a typical bake are uniform and share a handful of digests: lanes with equal digests elect the lowest
+    // first triangle among themselves first, so the table sees one atomic per distinct digest per warp.
     const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = s < itemEnd && !(skipSpecial && skipSpecial[s] != 0);
+    const bool valid = s < itemEnd;
     const uint64_t d = valid ? digest[s] : 0ull;
     uint32_t tri = valid ? items[s].tri : 0xFFFFFFFFu;
     const uint32_t active = __ballot_sync(0xFFFFFFFFu, valid);
@@ -1505,7 +1505,7 @@ __global__ void DigestInsertChunk(const uint64_t* __restrict__ digest, const Ite
                                   const int32_t* __restrict__ special, uint32_t itemBegin, uint32_t itemEnd, uint64_t* keys, uint32_t* vals, uint64_t mask,
                                   uint32_t* __restrict__ conflict) {
     const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = s < itemEnd && special[s] == 0;  // (see DigestInsert: items with a special index take no part)
+    const bool valid = s < itemEnd;
     const uint64_t d = valid ? digest[s] : 0ull;
     const uint32_t tri = valid ? items[s].tri : 0xFFFFFFFFu;
     const uint32_t active = __ballot_sync(0xFFFFFFFFu, valid);
@@ -1546,10 +1546,10 @@ __global__ void AdvanceRunningTotals(const uint32_t* __restrict__ emit, const un
 }
 __global__ void DigestResolve(const uint64_t* __restrict__ digest, const ItemRec* __restrict__ items, const uint32_t* __restrict__ triItem, uint32_t itemBegin,
                               uint32_t itemEnd, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask, int disableDup,
-                              int skipSpecial, uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
+                              uint32_t* __restrict__ survivor, int32_t* __restrict__ special) {
     const uint32_t s = itemBegin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= itemEnd) return;
-    const uint32_t v = (disableDup || (skipSpecial && special[s] != 0)) ? s : triItem[TableFind(keys, vals, mask, digest[s])];
+    const uint32_t v = disableDup ? s : triItem[TableFind(keys, vals, mask, digest[s])];
     survivor[s] = v;
     if (v != s) special[s] = -1;  // donated its primitives; never serialized (ref: :1059-1060)
 }
@@ -3127,7 +3127,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                         CUDA_TRY(LaunchItemPost(stream, items, wordStart, stateWords, i0, i1, d.rejectionThreshold, 0, 0, uniformVotes, (uint32_t)P.stateGT, (uint32_t)P.stateLE, digest,
                                                 special, bigItems, &launches));
                         if (!disableDup) DigestInsertChunk<<<gridC, TPB, 0, stream>>>(digest, items, triItem, special, i0, i1, tableKeys, tableVals, tableCap - 1, conflictDev);
-                        DigestResolve<<<gridC, TPB, 0, stream>>>(digest, items, triItem, i0, i1, tableKeys, tableVals, tableCap - 1, disableDup, 1, survivor, special);
+                        DigestResolve<<<gridC, TPB, 0, stream>>>(digest, items, triItem, i0, i1, tableKeys, tableVals, tableCap - 1, disableDup, survivor, special);
                         EmitInfo<<<gridC, TPB, 0, stream>>>(items, special, i0, i1, 0, (int)d.format, hist, emit, blockBytes);
                         size_t tmp = cubTempBytes;
                         CUDA_TRY(cub::DeviceScan::ExclusiveScan(cubTemp, tmp, emit + i0, descOfItem + i0, cub::Sum(), cub::FutureValue<uint32_t>(runDesc), (int)n, stream));
@@ -3273,11 +3273,11 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         if (!streaming && !disableDup) {
             // the UV table (capacity >= 2T+16 >= 2W+16) is reused for the digests
             FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
-            DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, hostPasses ? nullptr : special, 0, W, tableKeys, tableVals, cap - 1);
+            DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, 0, W, tableKeys, tableVals, cap - 1);
             launches += 2;
         }
         if (!streaming || streamFallback) {
-            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, hostPasses ? 0 : 1, survivor, special);
+            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, survivor, special);
             launches++;
         }
         if (hostPasses) {
@@ -3356,10 +3356,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             launches++;
             if (!disableDup) {
                 FillTable<<<(uint32_t)((cap + TPB - 1) / TPB), TPB, 0, stream>>>(tableKeys, tableVals, cap);
-                DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, nullptr, 0, W, tableKeys, tableVals, cap - 1);
+                DigestInsert<<<gridW, TPB, 0, stream>>>(digest, items, 0, W, tableKeys, tableVals, cap - 1);
                 launches += 2;
             }
-            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, 0, survivor2, special);
+            DigestResolve<<<gridW, TPB, 0, stream>>>(digest, items, triItem, 0, W, tableKeys, tableVals, cap - 1, disableDup, survivor2, special);
             launches++;
             CUDA_TRY(cudaStreamSynchronize(stream));  // the host vectors above must outlive the copies
         }
