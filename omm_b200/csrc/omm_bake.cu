@@ -1518,11 +1518,11 @@ __global__ void DigestInsertChunk(const uint64_t* __restrict__ digest, const Ite
         const uint64_t prev = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)key);
         if (prev == kEmptyKey || prev == key) {
             const uint32_t old = atomicMin(&vals[slot], tri);
-            // (only a SERIALIZED earlier item matters: one with a special index was never emitted, and whichever item of its digest
-            // its triangles resolve to carries the same special index)
+            // (an earlier item with a special index was never emitted; it only matters when this item does not carry the SAME special index --
+            // the digest folds the two unknown states, so a fully-unknown item and one mixing them meet here and the SDK merges them)
             if (old != 0xFFFFFFFFu && old > tri) {
                 const uint32_t prev = triItem[old];
-                if (prev < itemBegin && special[prev] == 0 && atomicOr(conflict, 1u) == 0u) {
+                if (prev < itemBegin && !(special[prev] != 0 && special[prev] == special[s]) && atomicOr(conflict, 1u) == 0u) {
                     conflict[1] = prev;  // diagnostics (OMM_B200_TRACE): the first pair that forced the fallback
                     conflict[2] = s;
                 }
