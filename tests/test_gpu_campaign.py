@@ -5,7 +5,7 @@ randomization.  The reference's analogous pin is running itself on every bake (s
 
 Configuration space (tests/campaign.py::random_bake): 5 address modes x pow2 / npot / tiny textures x FP32 / UNORM8 x 1-4 mips x SAT on / off / other
 cutoff x Linear / Nearest x 3 promotions x 2 formats x state mappings x per-triangle levels 0-8 (13 = global) x dynamic levels x degenerate / NaN /
-reused triangles x 8/16/32-bit indices x bake flags; a second leg adds work items of level 9-12.  OMM_CAMPAIGN_BAKES scales the first leg (default 260)."""
+reused triangles x 8/16/32-bit indices x bake flags; a second leg (10 bakes) adds work items of level 9-12.  OMM_CAMPAIGN_BAKES scales the first leg (default 260)."""
 import os
 
 import numpy as np
@@ -56,7 +56,7 @@ def test_random_bakes_with_big_levels_match_the_checker(product_lib, checker_lib
     megabyte blocks, special-index promotion of huge uniform blocks."""
     rng = np.random.default_rng(99)
     slow_checker = not checker_lib.path.endswith("libomm-lib.so")   # the scalar port: keep it short
-    for run in range(4 if slow_checker else 14):
+    for run in range(4 if slow_checker else 10):
         wl, kw = campaign.random_bake(rng, big_levels=True)
         if slow_checker:
             wl.subdivision_levels = np.minimum(wl.subdivision_levels, 9)

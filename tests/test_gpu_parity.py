@@ -51,12 +51,15 @@ def test_streamed_download_matches_checker(product_lib, checker_lib):
     the work items are in output order).  Both outcomes are covered: a bake whose blocks do not repeat across chunks (streamed to the end) and
     one where a later chunk holds the SDK's survivor of an already-sent block (detected, merged again the ordinary way)."""
     import os
+    from omm_b200 import capi
     from omm_b200 import workloads as W
     os.environ["OMM_B200_STREAMED_DOWNLOAD"] = "1"
-    os.environ["OMM_B200_STREAM_CHUNK_REGIONS"] = "65536"   # many chunks at test size
+    os.environ["OMM_B200_STREAM_CHUNK_REGIONS"] = "8192"   # many chunks at test size
     try:
-        for wl in (W.config3(num_tris=20000, tex_size=1024, level=6), W.config3(num_tris=6000, tex_size=512, level=7, cells=(64, 32)),
-                   W.config5(num_tris=9000, tex_size=512, distinct=2500, flat_tris=1500, max_level=8)):
+        for wl in (W.config3(num_tris=8000, tex_size=1024, level=6), W.config3(num_tris=4096, tex_size=512, level=6, cells=(64, 32)),
+                   W.config5(num_tris=9000, tex_size=512, distinct=2500, flat_tris=1500, max_level=7),
+                   # both unknown states in play (Nearest promotion): a fully-unknown special item and an item mixing them share a digest
+                   W.config3(num_tris=6000, tex_size=256, level=4, promotion=capi.PROMOTE_NEAREST)):
             want = PC.run_bake(checker_lib, wl)
             got = PC.run_bake(product_lib, wl)
             assert got.diff(want) == [], wl.name
