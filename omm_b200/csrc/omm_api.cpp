@@ -133,8 +133,10 @@ static void DestroyResult(BakeResultObject* r) {
         if (std::find(g_liveBakers.begin(), g_liveBakers.end(), r->baker) != g_liveBakers.end()) ReleaseSharedWindow(r->baker, r->sharedWindowId);
     } else if (r->arrayDataFromPinnedPool) PinnedPoolRelease(r->hostArrayData);
     else alloc.release(r->hostArrayData);
-    alloc.release(r->hostDescArray);
-    alloc.release(r->hostIndexBuffer);
+    if (r->descFromPinnedPool) PinnedPoolRelease(r->hostDescArray);
+    else alloc.release(r->hostDescArray);
+    if (r->indexFromPinnedPool) PinnedPoolRelease(r->hostIndexBuffer);
+    else alloc.release(r->hostIndexBuffer);
     FreeObject(alloc, r);
 }
 

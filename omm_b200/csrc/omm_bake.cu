@@ -3666,6 +3666,18 @@ cleanup:
     return rc;
 }
 
+// descriptors / index buffer of a result: page-locked like arrayData when they are big and the allocator is ours (a copy into pageable memory
+// is staged by the driver at a fifth of the PCIe speed: 0.3 ms of a config-3 call)
+static void* AllocHostSmallArray(BakeResultObject* res, size_t bytes, bool* fromPool) {
+    *fromPool = false;
+    if (res->usesDefaultAllocator && bytes >= ((size_t)1 << 20))
+        if (void* p = PinnedPoolAcquire(bytes)) {
+            *fromPool = true;
+            return p;
+        }
+    return res->alloc.alloc(bytes, 64);
+}
+
 ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes) {
     const Logger& log = res->log;
     ommResult rc = ommResult_SUCCESS;
@@ -3677,14 +3689,14 @@ ommResult DownloadResult(BakeResultObject* res, float* d2hMs, uint64_t* d2hBytes
     CUDA_TRY(PoolEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, 0));
     if (res->descCount) {
-        res->hostDescArray = res->alloc.alloc((size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), 64);
+        res->hostDescArray = AllocHostSmallArray(res, (size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), &res->descFromPinnedPool);
         if (!AllocHostArrayData(res) || !res->hostDescArray) { rc = ommResult_FAILURE; goto cleanup; }
         HostTrace::Mark("host result allocated");
         if (!res->arrayDataDownloaded)  // else: sent slice by slice while it was packed (BakeOnDevice, K8)
             CUDA_TRY(cudaMemcpyAsync(res->hostArrayData, res->devArrayData, res->arrayDataSize, cudaMemcpyDeviceToHost, 0));
         CUDA_TRY(cudaMemcpyAsync(res->hostDescArray, res->devDescArray, (size_t)res->descCount * sizeof(ommCpuOpacityMicromapDesc), cudaMemcpyDeviceToHost, 0));
     }
-    res->hostIndexBuffer = res->alloc.alloc((size_t)res->indexCount * 4, 64);
+    res->hostIndexBuffer = AllocHostSmallArray(res, (size_t)res->indexCount * 4, &res->indexFromPinnedPool);
     if (!res->hostIndexBuffer) { rc = ommResult_FAILURE; goto cleanup; }
     CUDA_TRY(cudaMemcpyAsync(res->hostIndexBuffer, res->devIndexBuffer, idxBytes, cudaMemcpyDeviceToHost, 0));
     CUDA_TRY(cudaEventRecord(e1, 0));

@@ -161,6 +161,7 @@ struct BakeResultObject {
     bool arrayDataDownloaded = false;  // hostArrayData was filled slice by slice while the array was packed (ommCpuBake on one GPU)
     float earlyD2hMs = 0.f;
     bool arrayDataFromPinnedPool = false;  // hostArrayData came from the library's page-locked pool (default allocator only)
+    bool descFromPinnedPool = false, indexFromPinnedPool = false;  // the same for hostDescArray / hostIndexBuffer (1 MiB and more)
     int sharedWindowId = -1;               // hostArrayData is a SharedHostWindow of the baker's sharding (root rank of a sharded ommCpuBake)
     bool arrayOnThisRank = true;           // false: sharded bake in rank-0 mode, seen from another rank (descriptors and index buffer only)
     bool deviceArrayComplete = true;       // false: rank 0 of a sharded ommCpuBake in rank-0 mode -- the array was assembled in host memory only
