@@ -196,3 +196,24 @@ def test_user_allocator_is_honoured(product_lib):
     tex.destroy()
     b.destroy()
     assert live == {}, f"leaked {len(live)} host allocations"
+
+
+def test_formats_the_sdk_has_undefined_behaviour_on_are_refused(product_lib):
+    """desc.format outside {OC1_2_State, OC1_4_State}: the SDK only asserts (bake_cpu_impl.cpp:328-333, compiled out in its release build) and then
+    indexes its histograms with format - 1.  Per-triangle formats that differ from desc.format: its arrays are sized from desc.format alone
+    (:1763-1771).  Both are refused before any device work (round-1 advisor finding: the second used to fail only after the whole classification)."""
+    rc, msgs = _attempt(product_lib, _set("format", 0))
+    assert rc == capi.INVALID_ARGUMENT and any("format is not set" in m for _, m in msgs), (rc, msgs)
+    rc, msgs = _attempt(product_lib, _set("format", 3))
+    assert rc == capi.INVALID_ARGUMENT
+
+    keep = []
+
+    def mixed(d):
+        n = d.indexCount // 3
+        f = np.full(n, capi.FORMAT_4_STATE, dtype=np.int32)
+        f[n // 2] = capi.FORMAT_2_STATE
+        keep.append(f)
+        d.formats = f.ctypes.data
+    rc, msgs = _attempt(product_lib, mixed)
+    assert rc == capi.FAILURE and any("per-triangle formats" in m for _, m in msgs), (rc, msgs)

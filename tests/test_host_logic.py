@@ -117,3 +117,13 @@ def test_product_fails_loudly_without_a_gpu(lib):
         with pytest.raises(Exception):
             b.create_texture([np.zeros((4, 4), dtype=np.float32)])
     assert any("no CUDA device" in m for m in msgs)
+
+
+def test_b200_extension_argument_checks(lib):
+    """Host-only behaviour of the round-2 extension entry points (include/omm_b200.h): result mode of a sharded baker, host pool trim."""
+    with Baker(lib) as b:
+        assert lib.dll.ommB200SetShardedResultMode(b.handle, capi.SHARDED_RESULT_ON_RANK0) == capi.SUCCESS
+        assert lib.dll.ommB200SetShardedResultMode(b.handle, capi.SHARDED_RESULT_REPLICATED) == capi.SUCCESS
+        assert lib.dll.ommB200SetShardedResultMode(b.handle, 7) == capi.INVALID_ARGUMENT
+    assert lib.dll.ommB200SetShardedResultMode(None, capi.SHARDED_RESULT_ON_RANK0) == capi.INVALID_ARGUMENT
+    assert lib.dll.ommB200TrimHostPool(0) == 0   # nothing is cached without a bake
