@@ -1,15 +1,20 @@
 // omm_bake.cu -- device pipeline of libomm-b200.so: everything ommCpuBake does between "inputs are in HBM" and
 // "result arrays are in HBM" (SURVEY.md section 8a, rows a3-a21), as CUDA kernels for sm_100a.
 //
-// Pipeline (one stream, two host read-backs of a few counters):
-//   K1 SetupTriangles      fetch indices/UVs, pick subdivision level, 64-bit UV id (a3)
-//   K2 UvTableInsert/Lookup "first triangle wins" UV pre-dedup via a CAS hash table + atomicMin (a3)
-//   K3 BuildItems           compact unique triangles into work items, size their state blocks
-//   K4 ClassifyKernel       one thread per micro-triangle, warp-packed 2-bit states (a5-a14)          <-- hot kernel
-//   K5 ItemPostKernel       special-index detection + XXH64 of the 3-state bytes, one warp per item (a15, a16)
-//   K6 DigestInsert/Resolve "lowest item index wins" exact dedup (a16)
-//   K7 Histogram / SortKeys / radix sort / scan (a19, a20)
-//   K8 WriteDescsAndPack, WriteIndexBuffer (a21)
+// Pipeline (one stream, two host read-back points of a few counters each; DESIGN.md section 4 has the table):
+//   K1  SetupTriangles         fetch indices/UVs, pick subdivision level (a3)
+//   K2  UvTableInsert/Resolve  "first triangle wins" UV pre-dedup via a CAS hash table + atomicMin (a3)
+//   K3  BuildItems             compact unique triangles into work items (the SDK's first-seen order)
+//   K3b ItemKeysAll, radix sort, PermuteItems   the work items in OUTPUT order (the SDK's spatial sort, a20, moved in front)
+//   K4  Hier* kernels          hierarchical classification of the micro-triangles (a5-a14)        <-- 90 % of a bake
+//       ClassifyKernel(Q)      the flat kernels: Nearest filter, foreign SAT cutoff, internal flags
+//   K5  ItemPostKernel, ItemPostBigKernel   special-index detection + XXH64 of the 3-state bytes (a15, a16)
+//   K6  DigestInsert/Resolve   "lowest first-seen item wins" exact dedup (a16)
+//   P   omm_post_passes.cuh    optional: near-duplicate merge, size-budget compression (a17, a18)
+//   K7  EmitInfo, prefix sums, TriangleFinalItems   histograms, descriptor slots, byte offsets (a19, a21)
+//   K8  WriteDescs, PackItems, WriteIndexBuffer      serialization (a21)
+// Sharded over several GPUs: K1-K3b replicated, K4-K5 on a rank's shards, one all-gather of digests + special indices, K6-K7
+// replicated, K8 on the rank's shards, byte ranges exchanged (BakeOnDevice, "the exchange").
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
