@@ -383,7 +383,8 @@ typedef struct ommB200BakeTimings {
     float hostDownloadMs; /* host allocation + D2H of what was not sent during the bake  */
     float hostTotalMs;    /* whole ommCpuBake call                                       */
     float itemPostMs;     /* special-index scan + XXH64 of this rank's items (part of postMs) */
-    float gatherMs;       /* NCCL all-gather of state blocks / digests (0 on one GPU; part of postMs) */
+    float gatherMs;       /* sharded bakes: NCCL all-gather of the per-item records (digest + special index), incl. the wait
+                             for the slowest rank (0 on one GPU; part of postMs) */
 } ommB200BakeTimings;
 
 /* Select the CUDA device used by bakers created afterwards on this thread's process (default: current device). */
