@@ -729,6 +729,29 @@ static unsigned long long HierNominalChunkRegions(int device) {
     if (device >= 0 && device < 64) cached[device] = regions;
     return regions;
 }
+// Blocks per SM of the grid-stride classifier kernels (8 are resident).  The tasks of these kernels differ in cost by an order of magnitude
+// (a leaf the level line crosses against one its edge filter closes), and a block's share is fixed by its stride: with two waves of blocks
+// (16 per SM, rounds 1 and early 2) the last blocks ran long after most SMs had drained.  Many short blocks let the hardware scheduler
+// balance: measured at config 3 on one box, classification 12.92 / 12.24 / 11.75 / 11.38 / 11.27 / 11.37 / 12.24 ms at 8 / 16 / 32 / 64 /
+// 128 / 256 / 1024 blocks per SM (`scripts/gpu_r2r.sh`).  OMM_B200_LIST_GRID_MULT (all kernels), OMM_B200_INIT_GRID_MULT and
+// OMM_B200_LEAF_GRID_MULT override for A/B runs.
+static uint32_t GridMultFromEnv(const char* name, uint32_t fallback) {
+    const char* e = getenv(name);
+    const long n = e ? atol(e) : (long)fallback;
+    return (uint32_t)(n < 1 ? 1 : (n > 4096 ? 4096 : n));
+}
+static uint32_t HierGridBlocksPerSm() {
+    static const uint32_t v = GridMultFromEnv("OMM_B200_LIST_GRID_MULT", 128);
+    return v;
+}
+static uint32_t HierInitGridBlocksPerSm() {
+    static const uint32_t v = GridMultFromEnv("OMM_B200_INIT_GRID_MULT", HierGridBlocksPerSm());
+    return v;
+}
+static uint32_t HierLeafGridBlocksPerSm() {
+    static const uint32_t v = GridMultFromEnv("OMM_B200_LEAF_GRID_MULT", HierGridBlocksPerSm());
+    return v;
+}
 struct HierLists {
     unsigned long long* q[3];        // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
     unsigned long long* unresolved;  // initial regions the whole-cell bitmap did not answer
@@ -3104,7 +3127,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
-            const uint32_t listGrid = (uint32_t)std::max(sms, 1) * 16u;
+            const uint32_t listGrid = (uint32_t)std::max(sms, 1) * HierGridBlocksPerSm(), initGrid = (uint32_t)std::max(sms, 1) * HierInitGridBlocksPerSm(),
+                           leafGrid = (uint32_t)std::max(sms, 1) * HierLeafGridBlocksPerSm();
             for (int k = 0; k < owned.count; ++k) {
                 const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
                 if (itemEnd <= itemBegin) continue;
@@ -3115,11 +3139,11 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     if (i0 >= itemEnd) break;
                     if (i1 <= i0) continue;
                     CUDA_TRY(cudaMemsetAsync(lists.count, 0, 8 * sizeof(unsigned long long), stream));
-                    hier.initial<<<listGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
+                    hier.initial<<<initGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
                     hier.unresolved<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
                     hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
                     hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
-                    hier.leaves<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
+                    hier.leaves<<<leafGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
                     hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
                     launches += 6;
                     if (streaming) {
