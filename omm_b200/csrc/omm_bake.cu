@@ -710,17 +710,14 @@ static unsigned long long HierNominalChunkRegions(int device) {
     // cudaMemGetInfo is a slow driver query (milliseconds with a large memory pool): ask once per device
     static std::mutex mu;
     static unsigned long long cached[64] = {};
+    if (const char* e = getenv("OMM_B200_CHUNK_REGIONS")) {  // A/B runs: initial regions per chunk (read per bake)
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= (1ull << 16)) return v;
+    }
     std::lock_guard<std::mutex> g(mu);
     if (device >= 0 && device < 64 && cached[device]) return cached[device];
     size_t freeB = 0, totalB = 0;
     unsigned long long regions = kHierChunkRegionsMin;
-    if (const char* e = getenv("OMM_B200_CHUNK_REGIONS")) {  // A/B runs: initial regions per chunk
-        const unsigned long long v = strtoull(e, nullptr, 10);
-        if (v >= (1ull << 16)) {
-            if (device >= 0 && device < 64) cached[device] = v;
-            return v;
-        }
-    }
     if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
         const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (21ull * 8ull);
         regions = std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));
@@ -741,16 +738,35 @@ static uint32_t GridMultFromEnv(const char* name, uint32_t fallback) {
     return (uint32_t)(n < 1 ? 1 : (n > 4096 ? 4096 : n));
 }
 static uint32_t HierGridBlocksPerSm() {
-    static const uint32_t v = GridMultFromEnv("OMM_B200_LIST_GRID_MULT", 128);
+    const uint32_t v = GridMultFromEnv("OMM_B200_LIST_GRID_MULT", 128);
     return v;
 }
 static uint32_t HierInitGridBlocksPerSm() {
-    static const uint32_t v = GridMultFromEnv("OMM_B200_INIT_GRID_MULT", HierGridBlocksPerSm());
+    const uint32_t v = GridMultFromEnv("OMM_B200_INIT_GRID_MULT", HierGridBlocksPerSm());
     return v;
 }
 static uint32_t HierLeafGridBlocksPerSm() {
-    static const uint32_t v = GridMultFromEnv("OMM_B200_LEAF_GRID_MULT", HierGridBlocksPerSm());
+    const uint32_t v = GridMultFromEnv("OMM_B200_LEAF_GRID_MULT", HierGridBlocksPerSm());
     return v;
+}
+static uint32_t HierSlowGridBlocksPerSm() {  // HierLeavesSlow: zero-area or huge-coordinate items only
+    const uint32_t v = GridMultFromEnv("OMM_B200_SLOW_GRID_MULT", HierGridBlocksPerSm());
+    return v;
+}
+// Classifier chunks in flight side by side ("lanes"; OMM_B200_CHUNK_LANES = 1..4, default 2; bakes on one GPU).  The level kernels of ONE
+// chunk are a dependent sequence, each with a tail in which the SMs drain, and the per-item post pass (K5) waited for the last of them; chunks
+// are independent of each other (whole work items, lists of their own), so the next chunk runs on a second stream, fills those tails, and a
+// chunk's post pass follows its leaves on its own lane while the other lane classifies.  Measured at config 3 on one box, one process
+// (`scripts/sweep_lanes.py`, `scripts/gpu_r2u.sh`, `gpu_r2v.sh`; every setting reproduces the SDK's digest): 12.53 ms per bake with one lane,
+// **12.34** with two (both 32 M-region chunks in flight), 12.33 with three chunks of 22 M on three lanes, 12.30 with four of 16 M on four;
+// end to end 18.35 -> 18.20 ms.  What it does NOT buy is L2 residency: chunks small enough for a chunk's state words and lists to stay in the
+// 126 MB L2 are slower also when their kernel boundaries overlap (2 lanes: 12.56 ms at 8 M regions per chunk, 12.82 at 4 M; 4 lanes: 12.50 at
+// 8 M, 13.1 at 2 M) -- the kernels are issue-bound, the extra launches cost more than the DRAM round trips.
+constexpr int kMaxChunkLanes = 4;
+static int HierChunkLanes() {  // (read per bake, like the grid switches: one process can compare settings)
+    const char* e = getenv("OMM_B200_CHUNK_LANES");
+    const long n = e ? atol(e) : 2;
+    return (int)(n < 1 ? 1 : (n > kMaxChunkLanes ? kMaxChunkLanes : n));
 }
 struct HierLists {
     unsigned long long* q[3];        // failing regions of 64, 16 and 4 micro-triangles: (item << 32) | region index within the item
@@ -2780,6 +2796,8 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     cudaStream_t copyStream = nullptr;  // early download of the packed array (see K8)
     cudaEvent_t copyEv[2] = {nullptr, nullptr}, sliceEv = nullptr;
     cudaEvent_t gatherEv[3] = {nullptr, nullptr, nullptr};  // OMM_B200_TRACE: phases of the sharded exchange
+    cudaStream_t laneStream[kMaxChunkLanes] = {};            // classifier chunks in flight side by side (lane 0 = the bake's stream)
+    cudaEvent_t laneEv[kMaxChunkLanes] = {}, lanePrepEv = nullptr;
     Scratch scratch{};
     void* cubTemp = nullptr;
     size_t cubTempBytes = 0;
@@ -2813,6 +2831,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
     }
     bool streaming = false, streamFallback = false;
+    bool lanePost = false;  // the per-item post pass ran chunk by chunk on the classifier's lanes
     std::vector<cudaEvent_t> chunkEvs;           // streamed: "chunk c is packed into the device array"
     unsigned long long* chunkEndHost = nullptr;  // streamed: arrayData bytes emitted up to and including chunk c (page-locked, read by the host as chunks complete)
     uint32_t *runDesc = nullptr, *conflictDev = nullptr;
@@ -3117,35 +3136,69 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                 cap = std::max(cap, std::min<unsigned long long>(HierChunkRegions(regions, hierChunkRegions) + (1ull << 18), regions));
             }
             HierItem* hierItems = nullptr;
-            HierLists lists{};
+            // lanes: chunks in flight side by side, each with lists and a stream of its own (HierChunkLanes); lane 0 is the bake's stream.
+            // (A rank of a sharded bake has one chunk per shard at these sizes: nothing to put side by side.)
+            int lanes = (streaming || world > 1) ? 1 : HierChunkLanes();
+            {
+                int chunks = 0;
+                for (int k = 0; k < owned.count; ++k)
+                    for (int c = 0; c < kHierMaxChunks && chunkFirst[k][c] < bounds[owned.shard[k] + 1].item; ++c) chunks += chunkFirst[k][c + 1] > chunkFirst[k][c];
+                lanes = std::max(1, std::min(lanes, chunks));  // a bake of one chunk keeps to the bake's stream
+            }
+            HierLists laneLists[kMaxChunkLanes] = {};
             CUDA_TRY(scratch.alloc(&hierItems, (size_t)W * (size_t)P.tex.mipCount));
-            CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
-            CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
-            CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
-            CUDA_TRY(scratch.alloc(&lists.unresolved, (size_t)cap));
-            CUDA_TRY(scratch.alloc(&lists.slow, (size_t)cap * 16));
-            CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
+            for (int l = 0; l < lanes; ++l) {
+                HierLists& lists = laneLists[l];
+                CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
+                CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
+                CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
+                CUDA_TRY(scratch.alloc(&lists.unresolved, (size_t)cap));
+                CUDA_TRY(scratch.alloc(&lists.slow, (size_t)cap * 16));
+                CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
+            }
+            laneStream[0] = stream;
+            if (lanes > 1) {
+                CUDA_TRY(PoolEventCreate(&lanePrepEv, false));
+                for (int l = 1; l < lanes; ++l) {
+                    CUDA_TRY(PoolStreamCreate(&laneStream[l]));
+                    CUDA_TRY(PoolEventCreate(&laneEv[l], false));
+                }
+            }
+            // with lanes, the per-item post pass of a chunk follows its leaves on the chunk's lane (its state words are still in L2 and the
+            // other lanes keep the SMs busy); the big-block digest kernel shares one work list per bake, so bakes with such items post afterwards
+            lanePost = lanes > 1 && bigItems.capacity == 0;
             CUDA_TRY(scratch.alloc(&uniformVotes, (size_t)W * 2));
             CUDA_TRY(cudaMemsetAsync(uniformVotes, 0, sizeof(uint32_t) * 2 * (size_t)W, stream));
             const uint32_t listGrid = (uint32_t)std::max(sms, 1) * HierGridBlocksPerSm(), initGrid = (uint32_t)std::max(sms, 1) * HierInitGridBlocksPerSm(),
-                           leafGrid = (uint32_t)std::max(sms, 1) * HierLeafGridBlocksPerSm();
+                           leafGrid = (uint32_t)std::max(sms, 1) * HierLeafGridBlocksPerSm(), slowGrid = (uint32_t)std::max(sms, 1) * HierSlowGridBlocksPerSm();
             for (int k = 0; k < owned.count; ++k) {
                 const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
                 if (itemEnd <= itemBegin) continue;
                 HierPrepare<<<(itemEnd - itemBegin + TPB - 1) / TPB, TPB, 0, stream>>>(P, items, itemBegin, itemEnd, hierItems);
                 launches++;
+                if (lanes > 1) {  // the other lanes start behind the shard's constants (and everything else enqueued so far)
+                    CUDA_TRY(cudaEventRecord(lanePrepEv, stream));
+                    for (int l = 1; l < lanes; ++l) CUDA_TRY(cudaStreamWaitEvent(laneStream[l], lanePrepEv, 0));
+                }
+                int nextLane = 0;
                 for (int c = 0; c < kHierMaxChunks; ++c) {
                     const uint32_t i0 = chunkFirst[k][c], i1 = chunkFirst[k][c + 1];
                     if (i0 >= itemEnd) break;
                     if (i1 <= i0) continue;
-                    CUDA_TRY(cudaMemsetAsync(lists.count, 0, 8 * sizeof(unsigned long long), stream));
-                    hier.initial<<<initGrid, kHierInitWarps * 32, 0, stream>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
-                    hier.unresolved<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
-                    hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
-                    hier.list<<<listGrid, 128, 0, stream>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
-                    hier.leaves<<<leafGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
-                    hier.leavesSlow<<<listGrid, 128, 0, stream>>>(P, items, hierItems, wordStart, lists, stateWords);
+                    const HierLists& lists = laneLists[nextLane];
+                    const cudaStream_t cs = laneStream[nextLane];
+                    nextLane = (nextLane + 1) % lanes;
+                    CUDA_TRY(cudaMemsetAsync(lists.count, 0, 8 * sizeof(unsigned long long), cs));
+                    hier.initial<<<initGrid, kHierInitWarps * 32, 0, cs>>>(P, hierItems, nodeStart, wordStart, i0, i1, lists, uniformVotes, stateWords);
+                    hier.unresolved<<<listGrid, 128, 0, cs>>>(P, hierItems, wordStart, lists, uniformVotes, stateWords);
+                    hier.list<<<listGrid, 128, 0, cs>>>(P, hierItems, wordStart, lists.q[0], lists.count + 0, lists.q[1], lists.count + 1, 0, stateWords);
+                    hier.list<<<listGrid, 128, 0, cs>>>(P, hierItems, wordStart, lists.q[1], lists.count + 1, lists.q[2], lists.count + 2, 1, stateWords);
+                    hier.leaves<<<leafGrid, 128, 0, cs>>>(P, items, hierItems, wordStart, lists, stateWords);
+                    hier.leavesSlow<<<slowGrid, 128, 0, cs>>>(P, items, hierItems, wordStart, lists, stateWords);
                     launches += 6;
+                    if (lanePost)
+                        CUDA_TRY(LaunchItemPost(cs, items, wordStart, stateWords, i0, i1, d.rejectionThreshold, (flags & ommCpuBakeFlags_DisableSpecialIndices) != 0, 0, uniformVotes,
+                                                (uint32_t)P.stateGT, (uint32_t)P.stateLE, digest, special, bigItems, &launches));
                     if (streaming) {
                         // the chunk's items are final: special indices + digests, dedup against the chunks so far, descriptor slots and
                         // byte offsets continuing the running totals, then the blocks go to the device array; the host thread forwards each
@@ -3174,6 +3227,10 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
                     }
                 }
             }
+            for (int l = 1; l < lanes; ++l) {  // the bake's stream continues behind every lane
+                CUDA_TRY(cudaEventRecord(laneEv[l], laneStream[l]));
+                CUDA_TRY(cudaStreamWaitEvent(stream, laneEv[l], 0));
+            }
         } else if (myItems > 0) {
             const ClassifyFn classify = SelectClassifyKernel(P);
             for (int k = 0; k < owned.count; ++k) {
@@ -3193,7 +3250,7 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
         }
         myMicroTris = microTris;
         CUDA_TRY(cudaEventRecord(ev[4], stream));  // end of the classification kernels proper
-        for (int k = 0; k < owned.count && !streaming; ++k) {
+        for (int k = 0; k < owned.count && !streaming && !lanePost; ++k) {
             const uint32_t itemBegin = bounds[owned.shard[k]].item, itemEnd = bounds[owned.shard[k] + 1].item;
             if (itemEnd <= itemBegin) continue;
             // special-index scan + XXH64 of this rank's items (their state words are local already)
@@ -3668,6 +3725,14 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
     }
 
 cleanup:
+    for (int l = 1; l < kMaxChunkLanes; ++l) {
+        if (!laneStream[l]) continue;
+        // (a complete bake has joined its lanes into the stream the host has synchronised since; a failed one may have left them running)
+        if (rc != ommResult_SUCCESS) cudaStreamSynchronize(laneStream[l]);
+        PoolStreamRelease(laneStream[l]);
+        PoolEventRelease(laneEv[l], false);
+    }
+    PoolEventRelease(lanePrepEv, false);
     scratch.freeAll();
     for (int i = 0; i < 6; ++i)
         PoolEventRelease(ev[i]);

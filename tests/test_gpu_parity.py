@@ -66,3 +66,28 @@ def test_streamed_download_matches_checker(product_lib, checker_lib):
     finally:
         del os.environ["OMM_B200_STREAMED_DOWNLOAD"]
         del os.environ["OMM_B200_STREAM_CHUNK_REGIONS"]
+
+
+def test_chunk_lanes_match_checker(product_lib, checker_lib):
+    """Classifier chunks in flight side by side on several streams (OMM_B200_CHUNK_LANES; two by default, but only bakes of more than one
+    32 M-region chunk have anything to put side by side): forced here with small chunks on mid-size bakes, for 1 to 4 lanes, incl. a bake
+    whose big blocks keep the per-item post pass behind the classification, mixed levels and both unknown states."""
+    import os
+    from omm_b200 import capi
+    from omm_b200 import workloads as W
+    wls = (W.config3(num_tris=8000, tex_size=1024, level=6), W.config3(num_tris=40, tex_size=512, level=9),
+           W.config5(num_tris=9000, tex_size=512, distinct=2500, flat_tris=1500, max_level=8),
+           W.config3(num_tris=20000, tex_size=512, level=5, promotion=capi.PROMOTE_NEAREST))
+    want = [PC.run_bake(checker_lib, wl) for wl in wls]
+    os.environ["OMM_B200_CHUNK_REGIONS"] = "65536"
+    try:
+        for lanes in (1, 2, 3, 4):
+            os.environ["OMM_B200_CHUNK_LANES"] = str(lanes)
+            for wl, w in zip(wls, want):
+                got = PC.run_bake(product_lib, wl)
+                assert got.diff(w) == [], (wl.name, lanes)
+                if lanes > 1 and wl is wls[0]:
+                    assert got.timings.kernelLaunches > 60, "the bake was expected to run in several chunks"
+    finally:
+        del os.environ["OMM_B200_CHUNK_REGIONS"]
+        os.environ.pop("OMM_B200_CHUNK_LANES", None)
