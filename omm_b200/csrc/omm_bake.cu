@@ -1,7 +1,8 @@
 // omm_bake.cu -- device pipeline of libomm-b200.so: everything ommCpuBake does between "inputs are in HBM" and
 // "result arrays are in HBM" (SURVEY.md section 8a, rows a3-a21), as CUDA kernels for sm_100a.
 //
-// Pipeline (one stream, two host read-back points of a few counters each; DESIGN.md section 4 has the table):
+// Pipeline (one stream -- plus a second one for every other classifier chunk of a single-GPU bake, see HierChunkLanes -- and two host
+// read-back points of a few counters each; DESIGN.md section 4 has the table):
 //   K1  SetupTriangles         fetch indices/UVs, pick subdivision level (a3)
 //   K2  UvTableInsert/Resolve  "first triangle wins" UV pre-dedup via a CAS hash table + atomicMin (a3)
 //   K3  BuildItems             compact unique triangles into work items (the SDK's first-seen order)
