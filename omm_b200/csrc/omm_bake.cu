@@ -702,10 +702,10 @@ __global__ void __launch_bounds__(kClassifyWarps * 32, OMM_CLASSIFYQ_MIN_BLOCKS)
 // Every kernel is small and homogeneous (no divergence between phases, full occupancy); a list entry is (item, region index).
 // The lists are sized for the worst case (every test fails) of one CHUNK of initial regions; a bake is a sequence of chunks.
 // ---------------------------------------------------------------------------------------------------------------------
-// Initial regions per chunk.  The lists are sized for the worst case (every test fails): 21 entries of 8 bytes per initial region.
-// The nominal chunk is 32 M regions = 2.1e9 micro-triangles (5.6 GiB of lists, 3 % of a B200's HBM): a bake of config-3 size is two
-// chunks and pays the kernel-boundary drains twice (one chunk of 64 M is 1 % faster per bake but doubles the one-off cost of growing
-// the memory pool on the first bake); it shrinks to an eighth of the free memory on smaller devices.
+// Initial regions per chunk.  The lists are sized for the worst case (every test fails): 38 entries of 8 bytes per initial region.
+// The nominal chunk is 32 M regions = 2.1e9 micro-triangles (9.7 GiB of lists per lane, two lanes: 11 % of a B200's HBM, held by the
+// stream-ordered pool between bakes): a bake of config-3 size is two chunks, which run side by side (HierChunkLanes); the chunk shrinks
+// so that the lists of two lanes take at most an eighth of the free memory on smaller or busier devices.
 constexpr unsigned long long kHierChunkRegionsMax = 32ull << 20, kHierChunkRegionsMin = 1ull << 20;
 static unsigned long long HierNominalChunkRegions(int device) {
     // cudaMemGetInfo is a slow driver query (milliseconds with a large memory pool): ask once per device
@@ -720,7 +720,8 @@ static unsigned long long HierNominalChunkRegions(int device) {
     size_t freeB = 0, totalB = 0;
     unsigned long long regions = kHierChunkRegionsMin;
     if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) {
-        const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (21ull * 8ull);
+        // 38 list entries of 8 bytes per initial region (1 + 4 + 16 failing regions, 1 unresolved, 16 slow-path), two lanes: an eighth of the free memory
+        const unsigned long long byMemory = (unsigned long long)(freeB / 8) / (2ull * 38ull * 8ull);
         regions = std::max(kHierChunkRegionsMin, std::min(kHierChunkRegionsMax, byMemory));
     } else
         cudaGetLastError();
