@@ -3151,12 +3151,18 @@ ommResult BakeOnDevice(BakerObject* baker, const StagedInputs& in, void* userStr
             CUDA_TRY(scratch.alloc(&hierItems, (size_t)W * (size_t)P.tex.mipCount));
             for (int l = 0; l < lanes; ++l) {
                 HierLists& lists = laneLists[l];
-                CUDA_TRY(scratch.alloc(&lists.q[0], (size_t)cap));
-                CUDA_TRY(scratch.alloc(&lists.q[1], (size_t)cap * 4));
-                CUDA_TRY(scratch.alloc(&lists.q[2], (size_t)cap * 16));
-                CUDA_TRY(scratch.alloc(&lists.unresolved, (size_t)cap));
-                CUDA_TRY(scratch.alloc(&lists.slow, (size_t)cap * 16));
-                CUDA_TRY(scratch.alloc(&lists.count, 8));  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
+                cudaError_t e = scratch.alloc(&lists.q[0], (size_t)cap);
+                if (e == cudaSuccess) e = scratch.alloc(&lists.q[1], (size_t)cap * 4);
+                if (e == cudaSuccess) e = scratch.alloc(&lists.q[2], (size_t)cap * 16);
+                if (e == cudaSuccess) e = scratch.alloc(&lists.unresolved, (size_t)cap);
+                if (e == cudaSuccess) e = scratch.alloc(&lists.slow, (size_t)cap * 16);
+                if (e == cudaSuccess) e = scratch.alloc(&lists.count, 8);  // [0..2] the lists, [3] unresolved initial regions, [5] slow-path 4-regions
+                if (e != cudaSuccess && l > 0) {  // no memory for another set of lists: the bake runs with the lanes it has
+                    cudaGetLastError();
+                    lanes = l;
+                    break;
+                }
+                CUDA_TRY(e);
             }
             laneStream[0] = stream;
             if (lanes > 1) {
