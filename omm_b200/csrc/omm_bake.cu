@@ -1437,6 +1437,23 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
 // 32 lanes load, expand and pre-multiply eight stripes at a time (lane = stripe * 4 + accumulator), and the chain itself -- kept
 // redundantly in every lane for accumulator lane & 3, so there is no divergence -- is a shuffle, a fused multiply-add and two funnel shifts
 // per stripe.  Config 5 (one level-12 item): 13.7 ms -> see DESIGN.md section 6.
+// One step of that chain, s <- rotl(s, 31) * P1 + x.  kFunnel: both halves of the rotation are ONE funnel shift each and the product is split
+// by hand (wide product of the low words with x as its addend, the two cross products added into the high word): six instructions instead
+// of the eight the compiler builds from the 64-bit expression (it assembles the low half of the rotation from a multiply, a shift and an
+// OR).  Same value for every input (200 M random and edge-pattern inputs on the host; the GPU suite's big-level bakes).  A three-level
+// arrangement of the step (rotl(s, 31) * P1 = s * (2^31 P1) + (s >> 33) * P1, everything that depends on the low word alone folded into the
+// addend of the wide product) was built as well: ten instructions, and slower -- a single warp is bound by the instructions it can issue,
+// not by the depth of the chain (measurements below).
+template <bool kFunnel>
+__device__ __forceinline__ uint64_t XxhChainStep(uint64_t s, uint64_t x) {
+    if (!kFunnel) return Rotl64(s, 31) * XP1 + x;
+    const uint32_t slo = (uint32_t)s, shi = (uint32_t)(s >> 32);
+    const uint32_t rlo = __funnelshift_r(shi, slo, 1), rhi = __funnelshift_r(slo, shi, 1);  // the two halves of rotl(s, 31)
+    const uint64_t w = (uint64_t)rlo * (uint32_t)XP1 + x;
+    const uint32_t hi = (uint32_t)(w >> 32) + rhi * (uint32_t)XP1 + rlo * (uint32_t)(XP1 >> 32);
+    return ((uint64_t)hi << 32) | (uint32_t)w;
+}
+template <bool kFunnel>
 __global__ void __launch_bounds__(32) ItemPostBigKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
                                                         const uint32_t* __restrict__ stateWords, const uint32_t* __restrict__ bigList,
                                                         const uint32_t* __restrict__ bigCount, float rejectionThreshold, int disableSpecial, int keepExistingSpecial,
@@ -1470,8 +1487,8 @@ __global__ void __launch_bounds__(32) ItemPostBigKernel(const ItemRec* __restric
         // s = acc + in * P2 of the pending round; every step is rotl(s, 31) * P1 + (next in * P2): one fused multiply-add on the chain
         uint64_t s = acc + xs[0];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) s = Rotl64(s, 31) * XP1 + xs[q];
-        acc = Rotl64(s, 31) * XP1;
+        for (int q = 1; q < 8; ++q) s = XxhChainStep<kFunnel>(s, xs[q]);
+        acc = XxhChainStep<kFunnel>(s, 0ull);
         x = xNext;
     }
     diff = __reduce_or_sync(0xFFFFFFFFu, diff);
@@ -1486,6 +1503,123 @@ __global__ void __launch_bounds__(32) ItemPostBigKernel(const ItemRec* __restric
     int common = (int)s0;
     if (!allEqual && rejectionThreshold > 0.f) {
         const float frac = (float)known / (float)n;
+        if (frac < rejectionThreshold) {
+            allEqual = true;
+            common = ommOpacityState_UnknownTransparent;
+        }
+    }
+    digest[w] = h;
+    if (!(keepExistingSpecial && special[w] != 0)) special[w] = (allEqual && !disableSpecial) ? (-common - 1) : 0;
+}
+
+// The same with the chain in a warp of its own (the default).  The one-warp kernel above spends 23 cycles per stripe whatever the form of the step: its
+// warp also loads, expands, pre-multiplies and shuffles, 11-15 instructions per stripe, and one warp issues about one instruction every
+// two cycles -- the chain is bound by issue slots, not by its depth.  So the preparation moves to a second warp (another scheduler of the SM): it
+// writes  in * P2  for 64 stripes at a time into one half of a double buffer in shared memory while the chain warp consumes the other half,
+// one 8-byte shared load and one six-instruction step per stripe; the two meet at a block barrier per 64 stripes, both running the same
+// loop, so the barrier counts cannot differ.  The chain starts from the state whose step with the first stripe gives  acc0 + x0  (P1 is odd:
+// the step is invertible), so there is no special case for the first stripe.  Config 5 (one level-12 block = 524 288 stripes), same box, one
+// process (`scripts/gpu_r2x.sh`, `gpu_r2z.sh`; every variant reproduces the SDK digest): post pass 6.39 ms with the compiler's step, 6.07 with
+// the funnel step, 6.62 with the three-level step (all one warp); 2.14-2.31 ms with the chain warp (2.41 / 2.53 with the three-level steps
+// in it), **1.86 ms** (7.0 cycles per stripe) with the prefetching producer below.  Config 5: 7.56 -> 3.07 ms per bake, 8.4 -> 3.9 ms end to end.
+constexpr uint64_t MulInverse64(uint64_t a) {  // a odd: Newton iteration doubles the correct bits
+    uint64_t x = a;  // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2ull - a * x;
+    return x;
+}
+constexpr uint64_t XP1Inverse = MulInverse64(XP1);
+static_assert(XP1 * XP1Inverse == 1ull, "modular inverse of PRIME64_1");
+// kStripes = stripes per half of the double buffer.  kPrefetch: the producer keeps the state words of the group after next in registers, so
+// that a group's loads have a whole group time to arrive -- without it the producer's path per group is L2 latency + its own arithmetic, and
+// with the block's data in the far L2 partition that exceeded the chain warp's 512 cycles per 64 stripes (post pass of config 5: 2.1 ms in one
+// process, 3.5 ms in another, same kernel).
+template <int kStripes, bool kPrefetch>
+__global__ void __launch_bounds__(64) ItemPostBigPipelined(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
+                                                           const uint32_t* __restrict__ stateWords, const uint32_t* __restrict__ bigList,
+                                                           const uint32_t* __restrict__ bigCount, float rejectionThreshold, int disableSpecial,
+                                                           int keepExistingSpecial, uint64_t* __restrict__ digest, int32_t* special) {
+    constexpr uint32_t kBatches = kStripes / 8;  // a batch = 8 stripes = 16 state words: one word per lane (each word is read by two lanes)
+    __shared__ uint2 sx[2][kStripes][4];         // in * P2 per stripe and accumulator
+    __shared__ uint32_t sStats[2];
+    if (blockIdx.x >= *bigCount) return;  // (the whole block)
+    const uint32_t w = bigList[blockIdx.x], lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t level = items[w].level;
+    const uint32_t n = 1u << (2 * level);                   // micro-triangles of the item now (uniformity / rejection test)
+    const uint32_t nHash = 1u << (2 * items[w].hashLevel);  // bytes the SDK's digest covers (>= n, differs only after Compress)
+    const uint32_t* words = stateWords + wordStart[w];
+    const uint32_t fullWords = n >> 4;
+    const uint32_t numGroups = nHash / (32u * kStripes);  // hashLevel >= 9: at least 64 groups
+    const uint32_t j = lane & 3u, t = lane >> 2, half = j & 1u, wordInBatch = 2u * t + (j >> 1);  // producer: lane = (stripe of the batch, accumulator)
+    const uint32_t s0 = __ldg(words) & 3u, pattern = s0 * 0x55555555u;
+    uint32_t diff = 0, known = 0;
+    uint32_t pf[kBatches];  // the producer's words of one group (registers: every loop over it is unrolled)
+    auto loadGroup = [&](uint32_t g) {
+        const uint32_t firstWord = g * (kStripes * 2u) + wordInBatch;
+#pragma unroll
+        for (uint32_t b = 0; b < kBatches; ++b) pf[b] = __ldg(words + firstWord + 16u * b);
+    };
+    auto storeGroup = [&](uint32_t g) {  // group g -> buffer g & 1
+        uint2(*buf)[4] = sx[g & 1u];
+        const uint32_t firstWord = g * (kStripes * 2u) + wordInBatch;
+#pragma unroll
+        for (uint32_t b = 0; b < kBatches; ++b) {
+            const uint32_t v = pf[b];
+            if (half == 0 && firstWord + 16u * b < fullWords) {  // statistics once per word
+                diff |= v ^ pattern;
+                known += __popc(~(v >> 1) & 0x55555555u);
+            }
+            const uint64_t x = Expand3State(half ? (v >> 16) : (v & 0xFFFFu)) * XP2;
+            buf[8u * b + t][j] = make_uint2((uint32_t)x, (uint32_t)(x >> 32));
+        }
+    };
+    // chain warp: lane & 3 = accumulator (kept redundantly in all lanes: no divergence)
+    const uint64_t acc0 = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
+    const uint64_t pre = acc0 * XP1Inverse;
+    uint64_t s = (pre >> 31) | (pre << 33);  // rotl(s, 31) * P1 == acc0
+    if (warp == 1) {
+        loadGroup(0);
+        storeGroup(0);
+        if (kPrefetch && numGroups > 1) loadGroup(1);
+    }
+    __syncthreads();
+    for (uint32_t g = 0; g < numGroups; ++g) {
+        if (warp == 1) {
+            if (g + 1 < numGroups) {
+                if (!kPrefetch) loadGroup(g + 1);
+                storeGroup(g + 1);
+                if (kPrefetch && g + 2 < numGroups) loadGroup(g + 2);
+            }
+        } else {
+            const uint2(*buf)[4] = sx[g & 1u];
+#pragma unroll 16
+            for (uint32_t q = 0; q < (uint32_t)kStripes; ++q) {
+                const uint2 x = buf[q][j];
+                s = XxhChainStep<true>(s, ((uint64_t)x.y << 32) | x.x);
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 1) {
+        diff = __reduce_or_sync(0xFFFFFFFFu, diff);
+        known = __reduce_add_sync(0xFFFFFFFFu, known);
+        if (lane == 0) {
+            sStats[0] = diff;
+            sStats[1] = known;
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const uint64_t acc = Rotl64(s, 31) * XP1;
+    const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2), v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
+    if (lane != 0) return;
+    uint64_t h = Rotl64(v1, 1) + Rotl64(v2, 7) + Rotl64(v3, 12) + Rotl64(v4, 18);
+    h = XxhMerge(h, v1); h = XxhMerge(h, v2); h = XxhMerge(h, v3); h = XxhMerge(h, v4);
+    h += (uint64_t)nHash;
+    h = XxhAvalanche(h);
+    bool allEqual = sStats[0] == 0;
+    int common = (int)s0;
+    if (!allEqual && rejectionThreshold > 0.f) {
+        const float frac = (float)sStats[1] / (float)n;
         if (frac < rejectionThreshold) {
             allEqual = true;
             common = ommOpacityState_UnknownTransparent;
@@ -1515,7 +1649,17 @@ static cudaError_t LaunchItemPost(cudaStream_t stream, const ItemRec* items, con
         big.capacity ? big.list : nullptr, big.count);
     (*launches)++;
     if (big.capacity) {
-        ItemPostBigKernel<<<big.capacity, 32, 0, stream>>>(items, wordStart, stateWords, big.list, big.count, rejectionThreshold, disableSpecial, keepExistingSpecial, digest, special);
+        // OMM_B200_BIG_HASH (read per bake, A/B runs): the one-warp kernel with the chain step as the compiler builds it (plain) / with funnel
+        // shifts (funnel); producer warp + chain warp without prefetch (pipe64); default: producer warp with prefetch + chain warp
+        const char* mode = getenv("OMM_B200_BIG_HASH");
+        if (mode && !strcmp(mode, "plain"))
+            ItemPostBigKernel<false><<<big.capacity, 32, 0, stream>>>(items, wordStart, stateWords, big.list, big.count, rejectionThreshold, disableSpecial, keepExistingSpecial, digest, special);
+        else if (mode && !strcmp(mode, "funnel"))
+            ItemPostBigKernel<true><<<big.capacity, 32, 0, stream>>>(items, wordStart, stateWords, big.list, big.count, rejectionThreshold, disableSpecial, keepExistingSpecial, digest, special);
+        else if (mode && !strcmp(mode, "pipe64"))  // producer without prefetch (the first version of the two-warp kernel)
+            ItemPostBigPipelined<64, false><<<big.capacity, 64, 0, stream>>>(items, wordStart, stateWords, big.list, big.count, rejectionThreshold, disableSpecial, keepExistingSpecial, digest, special);
+        else  // default: 128 stripes per buffer half, prefetching producer
+            ItemPostBigPipelined<128, true><<<big.capacity, 64, 0, stream>>>(items, wordStart, stateWords, big.list, big.count, rejectionThreshold, disableSpecial, keepExistingSpecial, digest, special);
         (*launches)++;
     }
     return cudaGetLastError();

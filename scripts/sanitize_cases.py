@@ -2,7 +2,7 @@
 """Small bakes for compute-sanitizer: BASELINE config 1, a slice of config 3 (hierarchical classifier, exact dedup), a small mixed-level
 config 5 (big footprints, constant-area tables), the flat kernels (Nearest), SAT, 2-state packing, and the optional passes (near-duplicate merge, budget
 compression).  Every result is compared with the CPU checker, so a sanitizer run is also a parity run.
-usage: compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck python scripts/sanitize_cases.py"""
+usage: compute-sanitizer --tool memcheck|racecheck|initcheck|synccheck python scripts/sanitize_cases.py [case name ...]"""
 import os
 import sys
 
@@ -25,10 +25,13 @@ cases = {
     "nearest": (W.random_mesh(31, 120, filter=capi.FILTER_NEAREST, unknown_state_promotion=capi.PROMOTE_NEAREST, uv_lo=-0.5, uv_hi=1.5), {}),
     "sat": (W.random_mesh(44, 150, tex_kind="blocky", tex_alpha_cutoff=0.5, addressing_mode=capi.ADDR_CLAMP, tri_texels=20, max_subdivision_level=4), {}),
     "2-state mips": (W.random_mesh(43, 120, mips=3, format=capi.FORMAT_2_STATE), {}),
+    "big blocks": (W.config3(num_tris=3, tex_size=256, level=9), {}),   # digest kernel with a producer and a chain warp (shared-memory double buffer)
 }
 if checker.path.endswith("libomm-lib.so"):
     cases["near-duplicates (LSH)"] = (W.random_mesh(101, 250, tex_kind="blocky", tri_texels=14, max_subdivision_level=3, reuse_frac=0.1, bake_flags=capi.BAKE_ENABLE_NEAR_DUPLICATE_DETECTION), {})
     cases["budget compression"] = (W.random_mesh(104, 150, tri_texels=16, max_subdivision_level=4, max_array_data_size=4000), {})
+if len(sys.argv) > 1:   # only the named cases
+    cases = {k: v for k, v in cases.items() if k in sys.argv[1:]}
 bad = 0
 for name, (wl, over) in cases.items():
     got = PC.run_bake(lib, wl, **over)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One process, config 3 staged once: device-resident bakes under a list of tuning settings (chunk lanes, chunk size, grid shapes -- all read per
 bake from the environment), then the drop-in call and the result digest for each.  usage: python scripts/sweep_lanes.py [steps=4] [set ...]
-where a set is  name:VAR=val,VAR=val  (default: the built-in list)."""
+where a set is  name:VAR=val,VAR=val  (default: the built-in list).  OMM_SWEEP_CONFIG=C5 runs BASELINE config 5 instead of config 3."""
 import ctypes as C
 import json
 import os
@@ -39,18 +39,20 @@ if len(sys.argv) > 2:
     for a in sys.argv[2:]:
         name, _, kv = a.partition(":")
         sets.append((name, dict(x.split("=") for x in kv.split(",") if x)))
-TUNING = ["OMM_B200_CHUNK_LANES", "OMM_B200_CHUNK_REGIONS", "OMM_B200_LIST_GRID_MULT", "OMM_B200_INIT_GRID_MULT", "OMM_B200_LEAF_GRID_MULT", "OMM_B200_SLOW_GRID_MULT"]
+TUNING = ["OMM_B200_CHUNK_LANES", "OMM_B200_CHUNK_REGIONS", "OMM_B200_LIST_GRID_MULT", "OMM_B200_INIT_GRID_MULT", "OMM_B200_LEAF_GRID_MULT", "OMM_B200_SLOW_GRID_MULT",
+          "OMM_B200_BIG_HASH"]
 
 torch.cuda.set_device(0)
 lib = capi.load_product_library()
 assert lib.dll.ommB200SetDevice(0) == capi.SUCCESS
 baker = Baker(lib)
-wl = W.config3()
+CONFIG = os.environ.get("OMM_SWEEP_CONFIG", "C3")
+wl = W.config5() if CONFIG == "C5" else W.config3()
 wl.indices, _k1 = bench.pinned_like(wl.indices)
 wl.texcoords, _k2 = bench.pinned_like(wl.texcoords)
 inp, tex = W.make_input(baker, wl)
 desc = inp.to_desc()
-golden = bench.golden_digests().get("C3", {}).get("sha256")
+golden = bench.golden_digests().get(CONFIG, {}).get("sha256")
 stream = torch.cuda.current_stream()
 sp = C.c_void_p(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
