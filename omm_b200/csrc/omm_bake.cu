@@ -9,7 +9,7 @@
 //   K3b ItemKeysAll, radix sort, PermuteItems   the work items in OUTPUT order (the SDK's spatial sort, a20, moved in front)
 //   K4  Hier* kernels          hierarchical classification of the micro-triangles (a5-a14)        <-- 90 % of a bake
 //       ClassifyKernel(Q)      the flat kernels: Nearest filter, foreign SAT cutoff, internal flags
-//   K5  ItemPostKernel, ItemPostBigKernel   special-index detection + XXH64 of the 3-state bytes (a15, a16)
+//   K5  ItemPostKernel, ItemPostBigPipelined   special-index detection + XXH64 of the 3-state bytes (a15, a16)
 //   K6  DigestInsert/Resolve   "lowest first-seen item wins" exact dedup (a16)
 //   P   omm_post_passes.cuh    optional: near-duplicate merge, size-budget compression (a17, a18)
 //   K7  EmitInfo, prefix sums, TriangleFinalItems   histograms, descriptor slots, byte offsets (a19, a21)
@@ -1344,7 +1344,7 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
                 }
             }
             if (!done) {
-                // blocks of 256 KiB and more: a warp of their own (ItemPostBigKernel) -- here their one sequential XXH64 chain would
+                // blocks of 256 KiB and more: a kernel of their own (ItemPostBigPipelined) -- here their one sequential XXH64 chain would
                 // hold up the seven items sharing the warp, and runs at half the speed
                 if (bigList && items[wi].hashLevel >= kBigHashLevel) bigList[atomicAdd(bigCount, 1u)] = wi;
                 else sList[atomicAdd(&sCount, 1u)] = wi;
