@@ -36,6 +36,7 @@
 
 #include "omm_device_math.cuh"
 #include "omm_hier.cuh"
+#include "omm_xxh64.h"
 
 namespace ommb200 {
 
@@ -1446,12 +1447,7 @@ __global__ void __launch_bounds__(kItemPostItemsPerBlock * 4) ItemPostKernel(con
 // not by the depth of the chain (measurements below).
 template <bool kFunnel>
 __device__ __forceinline__ uint64_t XxhChainStep(uint64_t s, uint64_t x) {
-    if (!kFunnel) return Rotl64(s, 31) * XP1 + x;
-    const uint32_t slo = (uint32_t)s, shi = (uint32_t)(s >> 32);
-    const uint32_t rlo = __funnelshift_r(shi, slo, 1), rhi = __funnelshift_r(slo, shi, 1);  // the two halves of rotl(s, 31)
-    const uint64_t w = (uint64_t)rlo * (uint32_t)XP1 + x;
-    const uint32_t hi = (uint32_t)(w >> 32) + rhi * (uint32_t)XP1 + rlo * (uint32_t)(XP1 >> 32);
-    return ((uint64_t)hi << 32) | (uint32_t)w;
+    return kFunnel ? xxh::ChainStep(s, x) : Rotl64(s, 31) * XP1 + x;  // (the funnel form lives in omm_xxh64.h, where the CPU suite pins it)
 }
 template <bool kFunnel>
 __global__ void __launch_bounds__(32) ItemPostBigKernel(const ItemRec* __restrict__ items, const unsigned long long* __restrict__ wordStart,
@@ -1522,13 +1518,6 @@ __global__ void __launch_bounds__(32) ItemPostBigKernel(const ItemRec* __restric
 // process (`scripts/gpu_r2x.sh`, `gpu_r2z.sh`; every variant reproduces the SDK digest): post pass 6.39 ms with the compiler's step, 6.07 with
 // the funnel step, 6.62 with the three-level step (all one warp); 2.14-2.31 ms with the chain warp (2.41 / 2.53 with the three-level steps
 // in it), **1.86 ms** (7.0 cycles per stripe) with the prefetching producer below.  Config 5: 7.56 -> 3.07 ms per bake, 8.4 -> 3.9 ms end to end.
-constexpr uint64_t MulInverse64(uint64_t a) {  // a odd: Newton iteration doubles the correct bits
-    uint64_t x = a;  // correct to 3 bits
-    for (int i = 0; i < 6; ++i) x *= 2ull - a * x;
-    return x;
-}
-constexpr uint64_t XP1Inverse = MulInverse64(XP1);
-static_assert(XP1 * XP1Inverse == 1ull, "modular inverse of PRIME64_1");
 // kStripes = stripes per half of the double buffer.  kPrefetch: the producer keeps the state words of the group after next in registers, so
 // that a group's loads have a whole group time to arrive -- without it the producer's path per group is L2 latency + its own arithmetic, and
 // with the block's data in the far L2 partition that exceeded the chain warp's 512 cycles per 64 stripes (post pass of config 5: 2.1 ms in one
@@ -1574,8 +1563,7 @@ __global__ void __launch_bounds__(64) ItemPostBigPipelined(const ItemRec* __rest
     };
     // chain warp: lane & 3 = accumulator (kept redundantly in all lanes: no divergence)
     const uint64_t acc0 = j == 0 ? 42ull + XP1 + XP2 : (j == 1 ? 42ull + XP2 : (j == 2 ? 42ull : 42ull - XP1));
-    const uint64_t pre = acc0 * XP1Inverse;
-    uint64_t s = (pre >> 31) | (pre << 33);  // rotl(s, 31) * P1 == acc0
+    uint64_t s = xxh::ChainStart(acc0);  // its step with the first stripe gives acc0 + x0
     if (warp == 1) {
         loadGroup(0);
         storeGroup(0);
@@ -1609,7 +1597,7 @@ __global__ void __launch_bounds__(64) ItemPostBigPipelined(const ItemRec* __rest
     }
     __syncthreads();
     if (warp != 0) return;
-    const uint64_t acc = Rotl64(s, 31) * XP1;
+    const uint64_t acc = xxh::ChainEnd(s);
     const uint64_t v1 = __shfl_sync(0xFFFFFFFFu, acc, 0), v2 = __shfl_sync(0xFFFFFFFFu, acc, 1), v3 = __shfl_sync(0xFFFFFFFFu, acc, 2), v4 = __shfl_sync(0xFFFFFFFFu, acc, 3);
     if (lane != 0) return;
     uint64_t h = Rotl64(v1, 1) + Rotl64(v2, 7) + Rotl64(v3, 12) + Rotl64(v4, 18);

@@ -21,6 +21,39 @@ OMM_XXH_HD uint64_t Avalanche(uint64_t h) {
     h ^= h >> 33; h *= kP2; h ^= h >> 29; h *= kP3; h ^= h >> 32;
     return h;
 }
+// The accumulator chain of a long message,  acc <- Round(acc, in),  restated on  s = acc + in * P2  (the state one addition further):
+//     s' = Rotl(s, 31) * P1 + x',   x' = in' * P2,
+// so that a consumer which receives the pre-multiplied x' has one multiply-add per stripe on its dependent path.  ChainStep is that
+// step with both halves of the rotation as one funnel shift each and the 64-bit product split by hand (the wide product of the low words
+// takes x as its addend, the two cross products go into the high word): six machine instructions on sm_100a.  ChainStart(acc0) is the
+// state whose step with the first x gives acc0 + x (P1 is odd, so the step is invertible): no special case for the first stripe;
+// ChainEnd(s) = Rotl(s, 31) * P1 is the accumulator after the last one.  Used by the big-block digest kernel (omm_bake.cu).
+OMM_XXH_HD uint32_t FunnelShiftR(uint32_t lo, uint32_t hi, uint32_t shift) {  // low word of (hi : lo) >> shift, shift < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (shift & 31u));
+#endif
+}
+OMM_XXH_HD uint64_t ChainStep(uint64_t s, uint64_t x) {
+    const uint32_t slo = (uint32_t)s, shi = (uint32_t)(s >> 32);
+    const uint32_t rlo = FunnelShiftR(shi, slo, 1), rhi = FunnelShiftR(slo, shi, 1);  // the two halves of Rotl(s, 31)
+    const uint64_t w = (uint64_t)rlo * (uint32_t)kP1 + x;
+    const uint32_t hi = (uint32_t)(w >> 32) + rhi * (uint32_t)kP1 + rlo * (uint32_t)(kP1 >> 32);
+    return ((uint64_t)hi << 32) | (uint32_t)w;
+}
+constexpr uint64_t MulInverse64(uint64_t a) {  // a odd; Newton's iteration doubles the correct low bits (3 to begin with)
+    uint64_t x = a;
+    for (int i = 0; i < 6; ++i) x *= 2ull - a * x;
+    return x;
+}
+constexpr uint64_t kP1Inverse = MulInverse64(kP1);
+static_assert(kP1 * kP1Inverse == 1ull, "modular inverse of PRIME64_1");
+OMM_XXH_HD uint64_t ChainStart(uint64_t acc0) {
+    const uint64_t pre = acc0 * kP1Inverse;
+    return (pre >> 31) | (pre << 33);  // Rotl(result, 31) * P1 == acc0
+}
+OMM_XXH_HD uint64_t ChainEnd(uint64_t s) { return Rotl(s, 31) * kP1; }
 // Streaming form over 32-bit little-endian words (all the library needs on the device: the hashed message is an array of uint32 samples).
 struct WordStream {
     uint64_t v1, v2, v3, v4, seed;

@@ -17,6 +17,29 @@ extern "C" unsigned long long words_form(const unsigned* w, size_t n, unsigned l
     for (size_t i = 0; i < n; ++i) s.push(w[i]);
     return s.finish();
 }
+// the accumulator chain as the big-block digest kernel runs it (omm_bake.cu, ItemPostBigPipelined): pre-multiplied stripes, ChainStart /
+// ChainStep / ChainEnd; n is a multiple of 32
+extern "C" unsigned long long chain_form(const unsigned char* p, size_t n, unsigned long long seed) {
+    using namespace ommb200::xxh;
+    const unsigned long long acc0[4] = {seed + kP1 + kP2, seed + kP2, seed, seed - kP1};
+    unsigned long long v[4];
+    for (int j = 0; j < 4; ++j) {
+        unsigned long long s = ChainStart(acc0[j]);
+        for (size_t st = 0; st < n / 32; ++st) {
+            unsigned long long in;
+            memcpy(&in, p + 32 * st + 8 * j, 8);
+            s = ChainStep(s, in * kP2);
+        }
+        v[j] = ChainEnd(s);
+    }
+    unsigned long long h = Rotl(v[0], 1) + Rotl(v[1], 7) + Rotl(v[2], 12) + Rotl(v[3], 18);
+    for (int j = 0; j < 4; ++j) h = MergeRound(h, v[j]);
+    return Avalanche(h + n);
+}
+extern "C" int chain_step_matches(unsigned long long s, unsigned long long x) {
+    using namespace ommb200::xxh;
+    return ChainStep(s, x) == Rotl(s, 31) * kP1 + x;
+}
 '''
 
 
@@ -53,3 +76,32 @@ def test_both_forms_match_the_vendored_xxhash():
             n = 1 << (2 * lvl)
             st = bytes((3 if (b % 3) == 2 else (b % 3)) for b in buf[:n])
             assert lib.bytes_form(st, n, 42) == int(want), lvl
+
+
+def test_chain_form_of_the_big_block_digest():
+    """ChainStart / ChainStep / ChainEnd (the funnel-shift, hand-split form of `acc <- rotl(acc + in * P2, 31) * P1` that the two-warp digest
+    kernel of blocks of level >= 9 runs) against the plain byte-stream XXH64, and the step against its 64-bit definition."""
+    import random
+    with tempfile.TemporaryDirectory() as d:
+        src, so = os.path.join(d, "h.cpp"), os.path.join(d, "h.so")
+        with open(src, "w") as f:
+            f.write(HARNESS)
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "omm_b200", "csrc"), src, "-o", so])
+        lib = C.CDLL(so)
+        lib.bytes_form.restype, lib.bytes_form.argtypes = C.c_uint64, [C.c_char_p, C.c_size_t, C.c_uint64]
+        lib.chain_form.restype, lib.chain_form.argtypes = C.c_uint64, [C.c_char_p, C.c_size_t, C.c_uint64]
+        lib.chain_step_matches.restype, lib.chain_step_matches.argtypes = C.c_int, [C.c_uint64, C.c_uint64]
+        rng = random.Random(20261017)
+        edge = [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0x100000000, 0x7FFFFFFFFFFFFFFF, 0x8000000000000000, 0xFFFFFFFFFFFFFFFF, 0xFFFFFFFF00000000, 0x00000001FFFFFFFF]
+        for s in edge:
+            for x in edge:
+                assert lib.chain_step_matches(s, x), (hex(s), hex(x))
+        for _ in range(20000):
+            assert lib.chain_step_matches(rng.getrandbits(64), rng.getrandbits(64))
+        buf = _xorshift_bytes(1 << 18)                                  # 4^9 bytes: the smallest block the kernel takes
+        states = bytes((3 if (b % 3) == 2 else (b % 3)) for b in buf)   # 3-state values, like the hashed blocks
+        for data in (buf, states):
+            for n in (32, 64, 4096, 1 << 14, 1 << 18):
+                for seed in (42, 0, 0xFFFFFFFFFFFFFFFF):
+                    assert lib.chain_form(data, n, seed) == lib.bytes_form(data, n, seed), (n, seed)
+
